@@ -1,0 +1,190 @@
+/*
+ * pathgraph.h - C ABI of libpathgraph.so (sm_100a), the B200-native hot path of
+ * himangi2003/path_gene_multimodal: nuclei table -> WSI space -> polygon morphology ->
+ * kNN / radius spatial cell graph -> neighbour-type composition + degree statistics.
+ *
+ * The reference has no FFI of its own (pure Python); each entry point below replaces one
+ * reference code block, cited as file:line into /root/reference.  The Python functions in
+ * path_gene_multimodal_b200/ keep the reference's signatures / column names and call these
+ * through ctypes (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative pg_status otherwise; pg_last_error()
+ *    gives the text (owned by the library, valid until the next call on that handle).
+ *  - all array arguments are DEVICE pointers owned by the caller unless marked "host";
+ *    no allocation crosses the boundary; scratch lives in the grow-only per-handle workspace.
+ *  - every call is asynchronous on `stream` except pg_create/pg_destroy, the *_total calls
+ *    (they synchronise the stream to return a count) and workspace growth (cudaMalloc).
+ *  - a handle is bound to one device and is not thread-safe; distinct handles are independent.
+ *  - indices are int32 (N, M, E < 2^31); coordinates float64; there is no CPU fallback.
+ */
+#ifndef PATHGRAPH_H
+#define PATHGRAPH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pg_handle pg_handle;
+typedef void* pg_stream; /* cudaStream_t */
+
+typedef enum {
+  PG_OK = 0,
+  PG_ERR_INVALID = -1,   /* bad argument */
+  PG_ERR_CUDA = -2,      /* CUDA runtime error, text in pg_last_error */
+  PG_ERR_STATE = -3,     /* call order (e.g. query before pg_grid_build) */
+  PG_ERR_CAPACITY = -4,  /* caller buffer smaller than the result */
+  PG_ERR_NOMEM = -5
+} pg_status;
+
+/* flags of pg_radius_count */
+#define PG_RADIUS_SYMMETRIC 0 /* rows hold every j != i with d <= r                          */
+#define PG_RADIUS_UPPER 1     /* rows hold only j > i: the reference's `edges` list, i<j    */
+
+#define PG_MAX_TYPES 16
+#define PG_MAX_K 64
+
+/* device-side degree statistics block (zeroed / initialised by the library) */
+typedef struct {
+  int32_t min_degree;
+  int32_t max_degree;
+  int64_t sum_degree;
+  int64_t sumsq_degree;
+  int64_t n_nodes;
+} pg_degree_stats;
+
+/* optional per-polygon outputs of pg_map_morph (any pointer may be NULL = not wanted) */
+typedef struct {
+  float* area;            /* |shoelace|; shapely p.area, polygon_morphology.py:247             */
+  float* perimeter;       /* closed ring length; shapely p.length, polygon_morphology.py:248   */
+  float* eccentricity;    /* sqrt(1 - l2/l1) of the second central moments; ipynb:2415-2429    */
+  float* circularity;     /* 4 pi A / max(P,1)^2 = `compactness`; ipynb:2441-2443               */
+  float* major_axis;      /* 4 sqrt(l1); ipynb:2423                                            */
+  float* minor_axis;      /* 4 sqrt(l2); ipynb:2424                                            */
+  double* centroid_x;     /* area centroid in WSI space; p.centroid, polygon_morphology.py:240 */
+  double* centroid_y;
+  double* poly_bbox;      /* [N,4] xmin,ymin,xmax,ymax of the shifted ring; p.bounds, :241     */
+} pg_morph_out;
+
+int pg_version(void);
+int pg_create(int device, pg_handle** out);
+int pg_destroy(pg_handle* h);
+const char* pg_last_error(pg_handle* h); /* h may be NULL: error of the last failed pg_create */
+/* bytes currently held by the handle's workspace */
+int64_t pg_workspace_bytes(pg_handle* h);
+
+/* ---- K1: fused tile->WSI shift + polygon morphology --------------------------------------
+ * replaces add_wsi_coords_to_nuclei's numeric body (aggregated_hovernet_run.py:302-334) and the
+ * shapely / cell-18 feature evaluation (polygon_morphology.py:240-248, ipynb:2415-2456).
+ *   poly_off  int32 [N+1]   CSR offsets into poly_xy (vertex units)
+ *   poly_xy   T     [M,2]   tile-local ring vertices, interleaved x,y; closing vertex optional
+ *   nuc_tile  int32 [N]     tile index per nucleus (NULL = no shift)
+ *   tile_x/y  int32 [n_tiles]
+ *   centroid  f64   [N,2]   tile-local centroid (NULL = skip)   -> wsi_centroid f64 [N,2]
+ *   bbox      int32 [N,4]   tile-local bbox     (NULL = skip)   -> wsi_bbox int32 [N,4]
+ *   wsi_poly_xy T   [M,2]   shifted vertices (NULL = skip)
+ * Rows with < 3 vertices give NaN features. */
+int pg_map_morph_f32(pg_handle* h, int32_t n, const int32_t* poly_off, const float* poly_xy,
+                     const int32_t* nuc_tile, const int32_t* tile_x, const int32_t* tile_y,
+                     const double* centroid, const int32_t* bbox, float* wsi_poly_xy,
+                     double* wsi_centroid, int32_t* wsi_bbox, const pg_morph_out* out,
+                     pg_stream stream);
+int pg_map_morph_f64(pg_handle* h, int32_t n, const int32_t* poly_off, const double* poly_xy,
+                     const int32_t* nuc_tile, const int32_t* tile_x, const int32_t* tile_y,
+                     const double* centroid, const int32_t* bbox, double* wsi_poly_xy,
+                     double* wsi_centroid, int32_t* wsi_bbox, const pg_morph_out* out,
+                     pg_stream stream);
+
+/* ---- K2-K4: uniform-grid binning (atomic histogram, decoupled look-back scan, counting-sort
+ * scatter); the cKDTree build of ipynb:1818 / ipynb:2964.
+ *   xy     f64   [N,2]  coordinates (`coords`)
+ *   type   int32 [N]    cell type ids (NULL = all 0)
+ *   gid    int32 [N]    global ids used for tie-breaks / output columns (NULL = identity);
+ *                       set when the points are a strip + halo of a larger slide
+ *   n_query             only points with index < n_query are queried / own output rows
+ *                       (the rest are halo points); pass N for a whole slide
+ *   cell_size           > 0
+ *   bounds  host f64[4] xmin,ymin,xmax,ymax (NULL = computed on the device; costs one sync) */
+int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, const int32_t* type,
+                  const int32_t* gid, double cell_size, const double* bounds, pg_stream stream);
+/* host-side view of the grid chosen: nx, ny, x0, y0, cell */
+int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0, double* cell);
+
+/* ---- K5: kNN; KNN.from_array(coords, k) + neighbor_distances (ipynb:1815-1850).
+ *   knn_idx  int32 [n_query,k] neighbour ids ascending by (d^2, id); self removed by index
+ *   dist64   f64   [n_query,k] sqrt(dx*dx+dy*dy) (NULL = skip);  dist32 the same rounded to f32
+ *   halo_ok  int32 [1] (NULL = skip) set to 0 if some queried point's k-th distance reaches past
+ *            x_lo/x_hi (the region for which all points are present) - see sharding */
+int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64, float* dist32,
+           double x_lo, double x_hi, int32_t* halo_ok, pg_stream stream);
+
+/* ---- K6 (+K8 fused): radius graph, two-pass CSR; cKDTree.query_ball_tree + the i<j loop +
+ * np.linalg.norm (ipynb:2964-2975, ipynb:3041-3042).
+ * count pass: row_ptr int32 [n_query+1] (exclusive scan of per-row counts, total in the last slot),
+ *   and fused over ALL neighbours regardless of `flags`:
+ *   degree int32 [n_query] (NULL = skip), nbr_count int32 [n_query,n_types] for type ids 1..n_types
+ *   (NULL = skip), stats (NULL = skip), hist int32 [hist_len] (last bin collects >= hist_len-1). */
+int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree,
+                    int32_t* nbr_count, int32_t n_types, pg_degree_stats* stats, int32_t* hist,
+                    int32_t hist_len, pg_stream stream);
+/* synchronises `stream`, returns row_ptr[n_query] of the last count pass */
+int pg_radius_total(pg_handle* h, int64_t* total);
+/* fill pass: col int32 [capacity] ascending per row, dist32 / dist64 (either may be NULL),
+ * edges_i64 int64 [capacity,2] rows (i, j) (NULL = skip; the notebook's `edges` when flags=UPPER).
+ * Rows that would pass `capacity` are dropped and pg_check_overflow reports it. */
+int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
+                   int64_t* edges_i64, int64_t capacity, pg_stream stream);
+/* synchronises; PG_ERR_CAPACITY if any fill since the last check overflowed its buffers */
+int pg_check_overflow(pg_handle* h);
+
+/* ---- K7: undirected union of the directed kNN lists; nx.Graph loop of ipynb:1865-1894.
+ * count: und_row_ptr int32 [N+1]; fill: und_col ascending per row, weights = min over directions. */
+int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx,
+                            int32_t* und_row_ptr, pg_stream stream);
+int pg_knn_symmetrize_total(pg_handle* h, int64_t* total);
+int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx,
+                           const double* dist64, const float* dist32, const int32_t* und_row_ptr,
+                           int32_t* und_col, double* und_w64, float* und_w32, pg_stream stream);
+
+/* ---- symmetric CSR (rows ascending by column) -> `edges` (i<j) list; ipynb:2969-2975 / G.edges of
+ * ipynb:1894.  row_id int32 [n] = id of each row in column space (NULL = identity; set for strips). */
+int pg_csr_upper_count(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,
+                       const int32_t* row_id, int32_t* up_ptr, pg_stream stream);
+int pg_csr_upper_total(pg_handle* h, int64_t* total);
+int pg_csr_upper_fill(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,
+                      const double* w64, const float* w32, const int32_t* row_id,
+                      const int32_t* up_ptr, int64_t* edges_i64, double* ew64, float* ew32,
+                      pg_stream stream);
+
+/* ---- K8: neighbour-type composition + degree statistics over any CSR (README.md:127,136; A.5) */
+int pg_compose_degree(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,
+                      const int32_t* type, int32_t n_types, int32_t* nbr_count, int32_t* degree,
+                      pg_degree_stats* stats, int32_t* hist, int32_t hist_len, pg_stream stream);
+
+/* ---- K9: halo selection for strip-sharded slides (no reference counterpart).
+ * Packs the points with x < lo_edge or x >= hi_edge into 24-byte records {x, y, gid, type}
+ * (order unspecified); count_out int32 [1] device.  capacity in records. */
+typedef struct {
+  double x, y;
+  int32_t gid, type;
+} pg_halo_rec;
+int pg_halo_pack(pg_handle* h, int32_t n, const double* xy, const int32_t* type, const int32_t* gid,
+                 double lo_edge, double hi_edge, pg_halo_rec* out, int32_t capacity,
+                 int32_t* count_out, pg_stream stream);
+/* Appends to xy/type/gid (starting at slot n_base) the records of `recs` whose x lies in
+ * [x_lo, x_hi) and whose owner rank differs (recs from `skip_begin..skip_end` are this rank's own
+ * contribution and are ignored). count_out int32 [1] device = number appended. */
+int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_t skip_begin,
+                   int32_t skip_end, double x_lo, double x_hi, double* xy, int32_t* type,
+                   int32_t* gid, int32_t n_base, int32_t capacity, int32_t* count_out,
+                   pg_stream stream);
+
+/* ---- exclusive scan (decoupled look-back), exposed for tests: out[i] = sum in[0..i), out[n] = total */
+int pg_exclusive_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, pg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATHGRAPH_H */

@@ -1,0 +1,36 @@
+"""path_gene_multimodal_b200 - B200-native (sm_100a) nuclei-table hot path of
+himangi2003/path_gene_multimodal: tile->WSI map, polygon morphology, kNN / radius cell graphs,
+neighbour-type composition and degree statistics.
+
+Public surface (reference-style module-level functions; see DESIGN.md / INTEGRATION.md):
+    add_wsi_coords_to_nuclei, map_morph_arrays            (nuclei_wsi)
+    polygon_morphology_table, nuclei_morphology_table     (polygon_morphology)
+    build_knn_graph, build_radius_graph,
+    neighbour_type_composition, degree_stats,
+    filter_graph_by_type                                  (cell_graph)
+Everything computes in libpathgraph.so (csrc/, C ABI in include/pathgraph.h); no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+_EXPORTS = {
+    "add_wsi_coords_to_nuclei": "nuclei_wsi", "map_morph_arrays": "nuclei_wsi",
+    "polygons_to_csr": "nuclei_wsi", "csr_to_polygons": "nuclei_wsi",
+    "polygon_morphology_table": "polygon_morphology", "nuclei_morphology_table": "polygon_morphology",
+    "tag_polygons": "polygon_morphology", "zscore_columns": "polygon_morphology",
+    "build_knn_graph": "cell_graph", "build_radius_graph": "cell_graph",
+    "neighbour_type_composition": "cell_graph", "degree_stats": "cell_graph",
+    "filter_graph_by_type": "cell_graph",
+    "Engine": "engine", "get_engine": "engine",
+}
+
+
+def __getattr__(name):
+    mod = _EXPORTS.get(name)
+    if mod is None:
+        raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+    import importlib
+
+    return getattr(importlib.import_module(f"{__name__}.{mod}"), name)
+
+
+__all__ = sorted(_EXPORTS)

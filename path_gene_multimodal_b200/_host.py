@@ -1,0 +1,53 @@
+"""Host <-> device staging helpers (pinned buffers, dtype checks). Plumbing only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+INT32_MAX = 2**31 - 1
+
+
+def to_device(arr, dtype: np.dtype, device: torch.device, name: str = "array") -> torch.Tensor:
+    """numpy (any layout) -> contiguous device tensor of `dtype`, staged through pinned memory."""
+    if isinstance(arr, torch.Tensor):
+        t = arr.to(device=device, dtype=_torch_dtype(dtype), non_blocking=True)
+        return t.contiguous()
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    if a.size == 0:
+        return torch.empty(a.shape, dtype=_torch_dtype(dtype), device=device)
+    pinned = torch.empty(a.shape, dtype=_torch_dtype(dtype), pin_memory=True)
+    pinned.numpy()[...] = a
+    return pinned.to(device, non_blocking=True)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """device tensor -> numpy through a pinned buffer (synchronises the current stream)."""
+    if t.numel() == 0:
+        return np.empty(tuple(t.shape), dtype=_numpy_dtype(t.dtype))
+    pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    pinned.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return pinned.numpy().copy()
+
+
+def as_int32(arr, name: str) -> np.ndarray:
+    a = np.asarray(arr)
+    if a.dtype.kind not in "iu":
+        if a.dtype.kind == "f" and np.all(a == np.floor(a)):
+            a = a.astype(np.int64)
+        else:
+            raise TypeError(f"{name}: integer values required, got dtype {a.dtype}")
+    if a.size and (a.max() > INT32_MAX or a.min() < -INT32_MAX - 1):
+        raise OverflowError(f"{name}: values do not fit int32")
+    return a.astype(np.int32)
+
+
+def _torch_dtype(dt) -> torch.dtype:
+    return {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+            np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+            np.dtype(np.uint8): torch.uint8}[np.dtype(dt)]
+
+
+def _numpy_dtype(dt: torch.dtype):
+    return {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
+            torch.int64: np.int64, torch.uint8: np.uint8}[dt]

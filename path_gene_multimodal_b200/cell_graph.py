@@ -1,0 +1,159 @@
+"""Spatial cell graphs over nucleus centroids, in the notebook's vocabulary.
+
+Mirrors /root/reference/hovernet_tile_inference.ipynb:
+* ``build_knn_graph``      cell 11 (ipynb:1766-1951): ``knn_neighbors``, ``knn_neighbor_distances``, and the
+  undirected ``nx.Graph`` union (edges ``i<j``, ``weight = min(dist)``);
+* ``build_radius_graph``   cells 23-26 (ipynb:2963-3042): ``edges`` int64 [E,2] (``i<j``), ``edge_index``,
+  ``edge_attr`` float32 [2E,1];
+* ``filter_graph_by_type`` cell 12 (ipynb:1989-2002);
+* ``neighbour_type_composition`` / ``degree_stats``: named in README.md:127,136 only; defined in SURVEY A.5.
+
+Host arrays in, host arrays out; everything in between is libpathgraph (uniform-grid binning, grid
+queries, two-pass CSR) on the GPU.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _host
+from .engine import default_knn_cell, get_engine, radius_cell
+
+TYPE_NAMES = {1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}
+
+
+def _prep(coords, types, eng):
+    c = np.asarray(coords, dtype=np.float64)
+    if c.ndim != 2 or c.shape[1] != 2:
+        raise ValueError("coords must have shape (N, 2)")
+    if c.shape[0] > _host.INT32_MAX:
+        raise OverflowError("more than 2^31 points")
+    if c.size and not np.isfinite(c).all():
+        raise ValueError("coords must be finite")  # cKDTree raises on NaN / inf as well
+    d_xy = _host.to_device(c, np.float64, eng.device)
+    d_t = None
+    if types is not None:
+        t = np.asarray(types)
+        if t.shape[0] != c.shape[0]:
+            raise ValueError("types must have one entry per point")
+        d_t = _host.to_device(_host.as_int32(t, "types"), np.int32, eng.device)
+    return c, d_xy, d_t
+
+
+def _bounds(c):
+    if c.shape[0] == 0:
+        return (0.0, 0.0, 1.0, 1.0)
+    return (float(c[:, 0].min()), float(c[:, 1].min()), float(c[:, 0].max()), float(c[:, 1].max()))
+
+
+def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected: bool = True,
+                    bounds=None, cell_size: float | None = None, device=None) -> dict:
+    """kNN graph of cell 11.
+
+    Returns ``knn_neighbors`` int64 [N,k] (ascending ``(d^2, index)``, self excluded by index),
+    ``knn_neighbor_distances`` float64 [N,k] and, with ``undirected``: ``edges`` int64 [E,2] (``i<j``,
+    sorted), ``weight`` float64 [E], symmetric CSR ``row_ptr`` / ``col`` / ``csr_weight``, ``degree`` int32 [N],
+    ``nbr_count`` int32 [N,n_types] (when ``types`` is given) and ``degree_stats``.
+    Raises ``ValueError`` when ``k >= N`` (as cKDTree-backed KNN does for k+1 > N).
+    """
+    eng = get_engine(device)
+    c, d_xy, d_t = _prep(coords, types, eng)
+    n = c.shape[0]
+    if not (1 <= k):
+        raise ValueError("k must be >= 1")
+    if k >= n:
+        raise ValueError(f"k={k} must be smaller than the number of points ({n})")
+    with torch.cuda.device(eng.device):
+        b = bounds if bounds is not None else _bounds(c)
+        if cell_size is None:
+            cell_size = default_knn_cell(n, max(b[2] - b[0], 1e-9) * max(b[3] - b[1], 1e-9), k)
+        eng.grid_build(d_xy, d_t, None, cell_size, b)
+        kn = eng.knn(k, dist_dtype=torch.float64)
+        out = {"knn_neighbors": _host.to_host(kn["knn_idx"]).astype(np.int64),
+               "knn_neighbor_distances": _host.to_host(kn["dist"])}
+        if undirected:
+            sym = eng.symmetrize(kn["knn_idx"], kn["dist"])
+            up = eng.csr_upper(sym["row_ptr"], sym["col"], sym["w64"])
+            comp = eng.compose_degree(sym["row_ptr"], sym["col"], d_t, n_types, compose=d_t is not None)
+            out.update({
+                "edges": _host.to_host(up["edges"]), "weight": _host.to_host(up["w64"]),
+                "row_ptr": _host.to_host(sym["row_ptr"]).astype(np.int64),
+                "col": _host.to_host(sym["col"]).astype(np.int64), "csr_weight": _host.to_host(sym["w64"]),
+                "degree": _host.to_host(comp["degree"]),
+                "degree_stats": eng.decode_stats(comp["stats"], comp["hist"]),
+            })
+            if d_t is not None:
+                out["nbr_count"] = _host.to_host(comp["nbr_count"])
+    return out
+
+
+def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mpp: float | None = None,
+                       symmetric_csr: bool = False, bounds=None, device=None) -> dict:
+    """Radius graph of cells 23-26: ``d(i, j) <= r`` (inclusive, like query_ball_tree), ``i < j``.
+
+    ``mpp`` scales pixel coordinates to micrometres first (``x_um = x_px * mpp``, ipynb:2046).
+    Returns ``edges`` int64 [E,2] sorted by (i, j); ``edge_index`` int64 [2,2E] = hstack(edges.T,
+    edges[:, ::-1].T) (the reference's vstack yields [4,E]; see SURVEY B-3); ``edge_attr`` float32 [2E,1];
+    ``dist`` float32 [E]; ``degree`` int32 [N]; ``nbr_count`` int32 [N,n_types] (with ``types``);
+    ``degree_stats``; and with ``symmetric_csr`` also ``row_ptr`` / ``col`` / ``csr_dist``.
+    """
+    eng = get_engine(device)
+    c = np.asarray(coords, dtype=np.float64)
+    if mpp is not None:
+        c = c * float(mpp)
+    c, d_xy, d_t = _prep(c, types, eng)
+    if not (r >= 0 and np.isfinite(r)):
+        raise ValueError("r must be finite and >= 0")
+    with torch.cuda.device(eng.device):
+        eng.grid_build(d_xy, d_t, None, radius_cell(r), bounds)  # bounds=None: min/max reduced on the device
+        g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=True, want_edges=True)
+        edges = _host.to_host(g["edges"])
+        d32 = _host.to_host(g["dist32"])
+        out = {
+            "edges": edges,
+            "dist": d32,
+            "edge_index": np.hstack([edges.T, edges[:, ::-1].T]),
+            "edge_attr": np.concatenate([d32[:, None], d32[:, None]], axis=0),
+            "degree": _host.to_host(g["degree"]),
+            "degree_stats": eng.decode_stats(g["stats"], g["hist"]),
+        }
+        if d_t is not None:
+            out["nbr_count"] = _host.to_host(g["nbr_count"])
+        if symmetric_csr:
+            s = eng.radius_graph(r, upper=False, compose=False, stats=False, want_dist32=True)
+            out["row_ptr"] = _host.to_host(s["row_ptr"]).astype(np.int64)
+            out["col"] = _host.to_host(s["col"]).astype(np.int64)
+            out["csr_dist"] = _host.to_host(s["dist32"])
+    return out
+
+
+def neighbour_type_composition(row_ptr, col, types, n_types: int = 5, device=None) -> np.ndarray:
+    """``nbr_count[i, t-1] = #{j in N(i): type[j] == t}`` for t = 1..n_types over any CSR. int32 [N,T]."""
+    eng = get_engine(device)
+    with torch.cuda.device(eng.device):
+        d_rp = _host.to_device(_host.as_int32(row_ptr, "row_ptr"), np.int32, eng.device)
+        d_col = _host.to_device(_host.as_int32(col, "col"), np.int32, eng.device)
+        d_t = _host.to_device(_host.as_int32(types, "types"), np.int32, eng.device)
+        res = eng.compose_degree(d_rp, d_col, d_t, n_types)
+        return _host.to_host(res["nbr_count"])
+
+
+def degree_stats(row_ptr, hist_len: int = 64, device=None) -> dict:
+    """``degree`` int32 [N] and ``min, max, sum, sumsq, mean, std`` (ddof=0, ipynb:2903 convention), ``hist``."""
+    eng = get_engine(device)
+    with torch.cuda.device(eng.device):
+        d_rp = _host.to_device(_host.as_int32(row_ptr, "row_ptr"), np.int32, eng.device)
+        res = eng.compose_degree(d_rp, None, None, 1, hist_len=hist_len, compose=False)
+        out = eng.decode_stats(res["stats"], res["hist"])
+        out["degree"] = _host.to_host(res["degree"])
+        return out
+
+
+def filter_graph_by_type(edges, types, keep_types=(1, 2)):
+    """Cell 12 (ipynb:1989-2002): nodes whose type is kept, and the edges with both ends kept.
+
+    Index bookkeeping on the host (two boolean masks); returns (kept node ids int64, edges int64 [E',2])."""
+    t = np.asarray(types)
+    keep = np.isin(t, list(keep_types))
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    return np.nonzero(keep)[0], e[keep[e[:, 0]] & keep[e[:, 1]]]

@@ -1,0 +1,96 @@
+// Internal header of libpathgraph.so (sm_100a). Public ABI: include/pathgraph.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <cstdio>
+#include "pathgraph.h"
+
+#define PG_WARP 32
+
+struct pg_buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+// Grid (uniform bins) state kept between pg_grid_build and the queries.
+struct pg_grid {
+  bool built = false;
+  int32_t n = 0, n_query = 0;
+  int32_t nx = 0, ny = 0;
+  double x0 = 0, y0 = 0, cell = 0, inv_cell = 0;
+  bool has_gid = false;
+};
+
+struct pg_handle {
+  int device = 0;
+  std::string err;
+  // grow-only workspace
+  pg_buf cell_count;   // int32 [C+1] histogram, then reused
+  pg_buf cell_start;   // int32 [C+1]
+  pg_buf cell_of;      // int32 [N]
+  pg_buf rank;         // int32 [N]
+  pg_buf s_xy;         // double2 [N]   points in cell order
+  pg_buf s_meta;       // int4 [N]      {local idx, gid, type, 0}
+  pg_buf row_count;    // int32 [N+1]   per-row counts before the scan
+  pg_buf scan_state;   // scan descriptors + ticket
+  pg_buf misc;         // bounds / flags / cursors
+  pg_buf sym_extra;    // int32 [N] reverse-only in-degree
+  pg_buf sym_cursor;   // int32 [N]
+  pg_buf sym_recip;    // uint8 [N*k]
+  int32_t* pinned = nullptr;  // host-pinned: [0]=radius total [1]=sym total [2]=upper total [3]=overflow [4..]=scratch
+  uint32_t scan_epoch = 0;
+  pg_grid grid;
+  double radius_r = 0;
+  int32_t radius_flags = 0;
+  cudaStream_t last_stream = nullptr;
+  int32_t sm_count = 148;
+};
+
+// misc buffer layout (byte offsets)
+#define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
+#define PG_MISC_OVERFLOW 64   // int32 overflow flag
+#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory
+#define PG_MISC_BYTES 256
+
+int pg_set_error(pg_handle* h, int code, const char* fmt, ...);
+int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
+
+#define PG_CUDA(h, expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return pg_set_error((h), PG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+  } while (0)
+
+#define PG_LAUNCH_CHECK(h) PG_CUDA(h, cudaGetLastError())
+
+#define PG_REQUIRE(h, cond, ...)                                       \
+  do {                                                                 \
+    if (!(cond)) return pg_set_error((h), PG_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// internal scan entry (pg_scan.cu): out[0..n] exclusive prefix of in[0..n), out[n] = total
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s);
+
+static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// cell coordinate along one axis: identical expression everywhere a point is binned.
+__device__ __forceinline__ int pg_cell_coord(double v, double v0, double inv_cell, int n_cells) {
+  double t = __dmul_rn(__dsub_rn(v, v0), inv_cell);
+  int c = __double2int_rd(t);  // NaN -> 0, saturating
+  c = c < 0 ? 0 : c;
+  c = c >= n_cells ? n_cells - 1 : c;
+  return c;
+}
+
+// squared distance exactly as scipy's sqeuclidean_distance_double evaluates it for m = 2 on a
+// non-FMA build: fl(fl(dx*dx) + fl(dy*dy)). Intrinsics forbid FMA contraction.
+__device__ __forceinline__ double pg_dist2(double ax, double ay, double bx, double by) {
+  double dx = __dsub_rn(ax, bx);
+  double dy = __dsub_rn(ay, by);
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+#endif

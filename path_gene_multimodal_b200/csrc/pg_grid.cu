@@ -1,0 +1,163 @@
+// K2-K4: uniform-grid binning of the centroids - atomic histogram over cells, decoupled look-back
+// scan (pg_scan.cu), counting-sort scatter. Plays the role of the cKDTree build at
+// /root/reference/hovernet_tile_inference.ipynb:1818 (KNN.from_array) and :2964 (cKDTree(coords)).
+#include <cmath>
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ unsigned long long dbl_key(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static inline double key_dbl(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double d;
+  memcpy(&d, &b, sizeof(d));
+  return d;
+}
+
+// keys[0..1] = min x,y  keys[2..3] = max x,y (monotone uint64 encoding; NaN skipped)
+__global__ void __launch_bounds__(TPB)
+bounds_kernel(const double2* __restrict__ xy, int n, unsigned long long* keys) {
+  unsigned long long lo_x = ~0ull, lo_y = ~0ull, hi_x = 0, hi_y = 0;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    double2 p = xy[i];
+    if (p.x == p.x) { unsigned long long k = dbl_key(p.x); lo_x = min(lo_x, k); hi_x = max(hi_x, k); }
+    if (p.y == p.y) { unsigned long long k = dbl_key(p.y); lo_y = min(lo_y, k); hi_y = max(hi_y, k); }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, d));
+    lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, d));
+    hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, d));
+    hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&keys[0], lo_x); atomicMin(&keys[1], lo_y);
+    atomicMax(&keys[2], hi_x); atomicMax(&keys[3], hi_y);
+  }
+}
+
+__global__ void init_bounds_kernel(unsigned long long* keys) {
+  keys[0] = keys[1] = ~0ull;
+  keys[2] = keys[3] = 0ull;
+}
+
+// K2: one thread per point; the atomic's return value is the point's rank inside its cell.
+__global__ void __launch_bounds__(TPB)
+histogram_kernel(const double2* __restrict__ xy, int n, double x0, double y0, double inv_cell, int nx, int ny,
+                 int32_t* __restrict__ cell_count, int32_t* __restrict__ cell_of, int32_t* __restrict__ rank) {
+  int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  double2 p = xy[i];
+  int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
+  cell_of[i] = c;
+  rank[i] = atomicAdd(&cell_count[c], 1);
+}
+
+// K4: counting-sort scatter into cell order, carrying {local idx, gid, type}.
+__global__ void __launch_bounds__(TPB)
+scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
+               int n, const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_of,
+               const int32_t* __restrict__ rank, double2* __restrict__ s_xy, int4* __restrict__ s_meta) {
+  int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  int dst = cell_start[cell_of[i]] + rank[i];
+  s_xy[dst] = xy[i];
+  s_meta[dst] = make_int4(i, gid ? gid[i] : i, type ? type[i] : 0, 0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, const int32_t* type,
+                  const int32_t* gid, double cell_size, const double* bounds, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  h->grid.built = false;
+  PG_REQUIRE(h, n >= 0 && n_query >= 0 && n_query <= n, "pg_grid_build: need 0 <= n_query <= n (n=%d n_query=%d)", n, n_query);
+  PG_REQUIRE(h, cell_size > 0 && std::isfinite(cell_size), "pg_grid_build: cell_size must be finite and > 0");
+  PG_REQUIRE(h, n == 0 || xy != nullptr, "pg_grid_build: xy is NULL");
+  PG_REQUIRE(h, ((uintptr_t)xy & 15) == 0, "pg_grid_build: xy must be 16-byte aligned");
+
+  double b[4] = {0, 0, 1, 1};
+  if (bounds) {
+    for (int i = 0; i < 4; ++i) b[i] = bounds[i];
+    PG_REQUIRE(h, std::isfinite(b[0]) && std::isfinite(b[1]) && std::isfinite(b[2]) && std::isfinite(b[3]) &&
+                      b[2] >= b[0] && b[3] >= b[1], "pg_grid_build: bad bounds");
+  } else if (n > 0) {
+    unsigned long long* keys = (unsigned long long*)((char*)h->misc.p + PG_MISC_BOUNDS);
+    init_bounds_kernel<<<1, 1, 0, s>>>(keys);
+    int blocks = std::min(pg_div_up(n, TPB), h->sm_count * 8);
+    bounds_kernel<<<blocks, TPB, 0, s>>>((const double2*)xy, n, keys);
+    PG_LAUNCH_CHECK(h);
+    unsigned long long hk[4];
+    PG_CUDA(h, cudaMemcpyAsync(hk, keys, sizeof(hk), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(h, cudaStreamSynchronize(s));
+    if (hk[0] == ~0ull || hk[1] == ~0ull)
+      return pg_set_error(h, PG_ERR_INVALID, "pg_grid_build: every coordinate is NaN");
+    for (int i = 0; i < 4; ++i) b[i] = key_dbl(hk[i]);
+    if (!(std::isfinite(b[0]) && std::isfinite(b[1]) && std::isfinite(b[2]) && std::isfinite(b[3])))
+      return pg_set_error(h, PG_ERR_INVALID, "pg_grid_build: coordinates must be finite");
+  }
+
+  // cell count is capped; a larger-than-asked cell only makes queries visit more cells (they
+  // derive their ring radius from the actual cell size), never changes results.
+  const double max_cells = std::min((double)(1 << 28), std::max(8.0 * (double)n, (double)(1 << 20)));
+  double cell = cell_size;
+  int64_t nx, ny;
+  while (true) {
+    nx = (int64_t)std::floor((b[2] - b[0]) / cell) + 1;
+    ny = (int64_t)std::floor((b[3] - b[1]) / cell) + 1;
+    if ((double)nx * (double)ny <= max_cells) break;
+    cell *= 2.0;
+  }
+  const int64_t cells = nx * ny;
+  pg_grid& g = h->grid;
+  g.n = n; g.n_query = n_query; g.nx = (int)nx; g.ny = (int)ny;
+  g.x0 = b[0]; g.y0 = b[1]; g.cell = cell; g.inv_cell = 1.0 / cell; g.has_gid = gid != nullptr;
+
+  int rc;
+  if ((rc = pg_reserve(h, h->cell_count, (cells + 1) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->cell_start, (cells + 4) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->cell_of, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->rank, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->s_xy, (size_t)(n + 1) * sizeof(double2)))) return rc;
+  if ((rc = pg_reserve(h, h->s_meta, (size_t)(n + 1) * sizeof(int4)))) return rc;
+
+  PG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, (cells + 1) * sizeof(int32_t), s));
+  if (n > 0) {
+    histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny,
+                                                      (int32_t*)h->cell_count.p, (int32_t*)h->cell_of.p,
+                                                      (int32_t*)h->rank.p);
+    PG_LAUNCH_CHECK(h);
+  }
+  if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, (int32_t*)h->cell_start.p, (int32_t)cells, s))) return rc;
+  if (n > 0) {
+    scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, (const int32_t*)h->cell_start.p,
+                                                    (const int32_t*)h->cell_of.p, (const int32_t*)h->rank.p,
+                                                    (double2*)h->s_xy.p, (int4*)h->s_meta.p);
+    PG_LAUNCH_CHECK(h);
+  }
+  g.built = true;
+  return PG_OK;
+}
+
+int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0, double* cell) {
+  if (!h) return PG_ERR_INVALID;
+  if (!h->grid.built) return pg_set_error(h, PG_ERR_STATE, "pg_grid_info: no grid built");
+  if (nx) *nx = h->grid.nx;
+  if (ny) *ny = h->grid.ny;
+  if (x0) *x0 = h->grid.x0;
+  if (y0) *y0 = h->grid.y0;
+  if (cell) *cell = h->grid.cell;
+  return PG_OK;
+}
+
+}  // extern "C"

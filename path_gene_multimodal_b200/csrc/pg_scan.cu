@@ -1,0 +1,159 @@
+// K3: single-pass exclusive scan with decoupled look-back (int32), used for cell_start and every
+// CSR row_ptr. One tile of 4096 items per CTA; tiles are handed out by an atomic ticket so a CTA
+// only ever waits on tiles that are already running. Descriptor words carry an epoch tag, so the
+// descriptor array never has to be cleared between scans.
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
+
+__device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint64_t state, int32_t value) {
+  return ((uint64_t)epoch << 34) | (state << 32) | (uint32_t)value;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n,
+                     uint64_t* desc, unsigned int* ticket, uint32_t epoch, int num_tiles) {
+  __shared__ int s_tile;
+  __shared__ int s_warp_sum[SCAN_THREADS / PG_WARP];
+  __shared__ int s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    int t = (int)atomicAdd(ticket, 1u);
+    if (t == num_tiles - 1) atomicExch(ticket, 0u);  // every ticket is out: re-arm for the next scan
+    s_tile = t;
+  }
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
+
+  int v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
+      int4 q = __ldg(p + i);
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+  }
+  int tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { int x = v[i]; v[i] = tsum; tsum += x; }
+  // warp inclusive scan of thread sums
+  int incl = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  int warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / PG_WARP; ++w) {
+    int s = s_warp_sum[w];
+    if (w < warp) warp_off += s;
+    tile_sum += s;
+  }
+  const int thread_off = warp_off + incl - tsum;
+
+  if (warp == 0) {
+    int running = 0;
+    if (tile == 0) {
+      if (lane == 0) st_relaxed_u64(&desc[0], pack_desc(epoch, ST_PREFIX, tile_sum));
+    } else {
+      if (lane == 0) st_relaxed_u64(&desc[tile], pack_desc(epoch, ST_AGG, tile_sum));
+      int look = tile - 1;
+      while (true) {
+        const int idx = look - lane;
+        uint64_t w = pack_desc(epoch, ST_PREFIX, 0);  // virtual tile -1: prefix 0
+        if (idx >= 0) {
+          do {
+            w = ld_relaxed_u64(&desc[idx]);
+          } while ((uint32_t)(w >> 34) != epoch || ((w >> 32) & 3) == 0);
+        }
+        const bool is_prefix = ((w >> 32) & 3) == ST_PREFIX;
+        const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        int contrib = (lane <= first) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        running += contrib;
+        if (pm) break;
+        look -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(&desc[tile], pack_desc(epoch, ST_PREFIX, running + tile_sum));
+    }
+    if (lane == 0) {
+      s_prefix = running;
+      if (tile == num_tiles - 1) out[n] = running + tile_sum;
+    }
+  }
+  __syncthreads();
+  const int off = s_prefix + thread_off;
+  if (base + SCAN_ITEMS <= n) {
+    int4* p = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS / 4; ++i)
+      p[i] = make_int4(v[4 * i] + off, v[4 * i + 1] + off, v[4 * i + 2] + off, v[4 * i + 3] + off);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      if (base + i < n) out[base + i] = v[i] + off;
+  }
+}
+
+__global__ void scan_empty_kernel(int32_t* out) { out[0] = 0; }
+
+}  // namespace
+
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s) {
+  if (n < 0) return pg_set_error(h, PG_ERR_INVALID, "scan: n < 0");
+  if (n == 0) {
+    scan_empty_kernel<<<1, 1, 0, s>>>(out);
+    PG_LAUNCH_CHECK(h);
+    return PG_OK;
+  }
+  if (((uintptr_t)in & 15) || ((uintptr_t)out & 15))
+    return pg_set_error(h, PG_ERR_INVALID, "scan: in/out must be 16-byte aligned");
+  const int num_tiles = pg_div_up(n, SCAN_TILE);
+  const size_t need = 256 + (size_t)num_tiles * sizeof(uint64_t);
+  if (need > h->scan_state.cap) {
+    int rc = pg_reserve(h, h->scan_state, need);
+    if (rc) return rc;
+    PG_CUDA(h, cudaMemsetAsync(h->scan_state.p, 0, h->scan_state.cap, s));
+  }
+  h->scan_epoch += 1;
+  if (h->scan_epoch >= (1u << 30)) {  // epoch field is 30 bits wide: start over on a clean slate
+    PG_CUDA(h, cudaMemsetAsync(h->scan_state.p, 0, h->scan_state.cap, s));
+    h->scan_epoch = 1;
+  }
+  unsigned int* ticket = (unsigned int*)h->scan_state.p;
+  uint64_t* desc = (uint64_t*)((char*)h->scan_state.p + 256);
+  scan_lookback_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, desc, ticket, h->scan_epoch, num_tiles);
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+extern "C" int pg_exclusive_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = (cudaStream_t)stream;
+  return pg_scan_i32(h, in, out, n, (cudaStream_t)stream);
+}

@@ -1,0 +1,365 @@
+"""Device-level driver of libpathgraph.so: torch tensors in, torch tensors out.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only; every
+computation below is one or more hand-written sm_100a kernels behind the C ABI
+(include/pathgraph.h).  All tensors must live on the engine's CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PathGraphError, PgMorphOut
+
+_INF = float("inf")
+
+
+def default_knn_cell(n: int, area: float, k: int) -> float:
+    """Cell size for kNN grids: about the expected k-th neighbour distance sqrt(k / (pi rho))."""
+    if n <= 0 or area <= 0:
+        return 1.0
+    rho = n / area
+    return max(1.15 * math.sqrt(k / (math.pi * rho)), 1e-12)
+
+
+def radius_cell(r: float) -> float:
+    """Cell size for radius grids: just above r, so the 3x3 block around a point covers its ball."""
+    return r * (1.0 + 2.0 ** -20) if r > 0 else 1.0
+
+
+class Engine:
+    """One libpathgraph handle (= one workspace) on one CUDA device. Not thread-safe."""
+
+    def __init__(self, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("path_gene_multimodal_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError(f"Engine needs a cuda device, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.lib = _lib.load_library()
+        h = C.c_void_p()
+        rc = self.lib.pg_create(self.device.index, C.byref(h))
+        if rc != 0:
+            raise PathGraphError(rc, (self.lib.pg_last_error(None) or b"").decode())
+        self._h = h
+        self.launches = 0  # kernels launched through this engine (bench.py's gpu_launches claim)
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PathGraphError(rc, (self.lib.pg_last_error(self._h) or b"").decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _p(self, t: torch.Tensor | None, dtype: torch.dtype, name: str):
+        if t is None:
+            return None
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise ValueError(f"{name}: expected a tensor on {self.device}")
+        if t.dtype != dtype:
+            raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: tensor must be contiguous")
+        return C.c_void_p(t.data_ptr())
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.pg_workspace_bytes(self._h))
+
+    def check_overflow(self):
+        self._check(self.lib.pg_check_overflow(self._h))
+
+    @staticmethod
+    def decode_stats(stats_t: torch.Tensor, hist: torch.Tensor | None = None) -> dict:
+        """pg_degree_stats block (4 x int64 on the device) -> python dict (one D2H copy)."""
+        raw = stats_t.cpu().numpy().view(np.int32)
+        s = stats_t.cpu().numpy()
+        n = int(s[3])
+        tot, sq = int(s[1]), int(s[2])
+        mean = tot / n if n else float("nan")
+        var = max(sq / n - mean * mean, 0.0) if n else float("nan")
+        out = {"min": int(raw[0]), "max": int(raw[1]), "sum": tot, "sumsq": sq, "n": n,
+               "mean": mean, "std": math.sqrt(var) if n else float("nan")}
+        if hist is not None:
+            out["hist"] = hist.cpu().numpy().astype(np.int64)
+        return out
+
+    # ---- K1 ------------------------------------------------------------------------------------
+    def map_morph(self, poly_off, poly_xy, nuc_tile=None, tile_x=None, tile_y=None, centroid=None, bbox=None,
+                  write_polygons=True, extra=False, out=None):
+        """Fused tile->WSI shift + polygon morphology (pg_map_morph_f32 / _f64).
+
+        poly_off int32 [N+1]; poly_xy float32|float64 [M,2]; nuc_tile int32 [N]; tile_x/y int32 [n_tiles];
+        centroid float64 [N,2]; bbox int32 [N,4].  Returns a dict of device tensors:
+        wsi_poly_xy, wsi_centroid, wsi_bbox, area, perimeter, eccentricity, circularity and, with
+        ``extra``, major_axis, minor_axis, centroid_x, centroid_y, poly_bbox.  ``out`` may carry
+        preallocated tensors of the same names (reused, not reallocated).
+        """
+        n = int(poly_off.numel()) - 1
+        vt = poly_xy.dtype
+        if vt not in (torch.float32, torch.float64):
+            raise ValueError("poly_xy must be float32 or float64")
+        m = int(poly_xy.shape[0]) if poly_xy.dim() == 2 else int(poly_xy.numel() // 2)
+        res = dict(out) if out else {}
+
+        def get(name, shape, dtype):
+            t = res.get(name)
+            if t is None:
+                t = self._empty(shape, dtype)
+                res[name] = t
+            return t
+
+        wsi_poly = get("wsi_poly_xy", (m, 2), vt) if write_polygons else None
+        wsi_c = get("wsi_centroid", (n, 2), torch.float64) if centroid is not None else None
+        wsi_b = get("wsi_bbox", (n, 4), torch.int32) if bbox is not None else None
+        mo = PgMorphOut()
+        for name in ("area", "perimeter", "eccentricity", "circularity"):
+            setattr(mo, name, self._p(get(name, (n,), torch.float32), torch.float32, name))
+        if extra:
+            for name in ("major_axis", "minor_axis"):
+                setattr(mo, name, self._p(get(name, (n,), torch.float32), torch.float32, name))
+            for name in ("centroid_x", "centroid_y"):
+                setattr(mo, name, self._p(get(name, (n,), torch.float64), torch.float64, name))
+            mo.poly_bbox = self._p(get("poly_bbox", (n, 4), torch.float64), torch.float64, "poly_bbox")
+        fn = self.lib.pg_map_morph_f32 if vt == torch.float32 else self.lib.pg_map_morph_f64
+        self._check(fn(self._h, n, self._p(poly_off, torch.int32, "poly_off"), self._p(poly_xy, vt, "poly_xy"),
+                       self._p(nuc_tile, torch.int32, "nuc_tile"), self._p(tile_x, torch.int32, "tile_x"),
+                       self._p(tile_y, torch.int32, "tile_y"), self._p(centroid, torch.float64, "centroid"),
+                       self._p(bbox, torch.int32, "bbox"), self._p(wsi_poly, vt, "wsi_poly_xy"),
+                       self._p(wsi_c, torch.float64, "wsi_centroid"), self._p(wsi_b, torch.int32, "wsi_bbox"),
+                       C.byref(mo), self._stream()))
+        self.launches += 1 if n > 0 else 0
+        return res
+
+    # ---- K2-K4 ---------------------------------------------------------------------------------
+    def grid_build(self, xy, types=None, gid=None, cell_size=1.0, bounds=None, n_query=None):
+        """Bin points into the uniform grid kept inside the handle (pg_grid_build)."""
+        n = int(xy.shape[0])
+        nq = n if n_query is None else int(n_query)
+        b = None
+        if bounds is not None:
+            b = (C.c_double * 4)(*[float(v) for v in bounds])
+        self._check(self.lib.pg_grid_build(self._h, n, nq, self._p(xy, torch.float64, "xy"),
+                                           self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
+                                           float(cell_size), b, self._stream()))
+        self._n, self._nq = n, nq
+        self.launches += (3 if n > 0 else 1) + (2 if (bounds is None and n > 0) else 0)
+
+    def grid_info(self) -> dict:
+        nx, ny = C.c_int32(), C.c_int32()
+        x0, y0, cell = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.pg_grid_info(self._h, C.byref(nx), C.byref(ny), C.byref(x0), C.byref(y0), C.byref(cell)))
+        return {"nx": nx.value, "ny": ny.value, "x0": x0.value, "y0": y0.value, "cell": cell.value}
+
+    # ---- K5 ------------------------------------------------------------------------------------
+    def knn(self, k, dist_dtype=torch.float64, both=False, x_lo=-_INF, x_hi=_INF, check_halo=False, out=None):
+        """kNN over the built grid. Returns dict(knn_idx int32 [nq,k], dist (f64 or f32)[, dist32][, halo_ok])."""
+        nq = self._nq
+        res = dict(out) if out else {}
+        idx = res.get("knn_idx")
+        if idx is None:
+            idx = res["knn_idx"] = self._empty((nq, k), torch.int32)
+        d64 = d32 = None
+        if dist_dtype == torch.float64 or both:
+            d64 = res.get("dist64")
+            if d64 is None:
+                d64 = res["dist64"] = self._empty((nq, k), torch.float64)
+        if dist_dtype == torch.float32 or both:
+            d32 = res.get("dist32")
+            if d32 is None:
+                d32 = res["dist32"] = self._empty((nq, k), torch.float32)
+        ok = None
+        if check_halo:
+            ok = res.get("halo_ok")
+            if ok is None:
+                ok = res["halo_ok"] = self._empty((1,), torch.int32)
+        self._check(self.lib.pg_knn(self._h, int(k), self._p(idx, torch.int32, "knn_idx"),
+                                    self._p(d64, torch.float64, "dist64"), self._p(d32, torch.float32, "dist32"),
+                                    float(x_lo), float(x_hi), self._p(ok, torch.int32, "halo_ok"), self._stream()))
+        self.launches += 1 + (1 if check_halo else 0)
+        res["dist"] = d64 if dist_dtype == torch.float64 else d32
+        return res
+
+    # ---- K6 + fused K8 ---------------------------------------------------------------------------
+    def radius_graph(self, r, upper=False, n_types=5, compose=True, stats=True, hist_len=64, want_dist32=True,
+                     want_dist64=False, want_edges=False, capacity=None, out=None):
+        """Radius graph over the built grid: count (+composition / degree) -> scan -> fill.
+
+        With ``capacity`` (entries) the whole sequence is enqueued without a host sync and the
+        returned col / dist tensors have ``capacity`` rows (valid prefix = row_ptr[-1]); call
+        ``check_overflow()`` later.  Without it the total is read back and outputs are exact-size.
+        """
+        nq = self._nq
+        res = dict(out) if out else {}
+
+        def get(name, shape, dtype):
+            t = res.get(name)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = res[name] = self._empty(shape, dtype)
+            return t
+
+        row_ptr = get("row_ptr", (nq + 1,), torch.int32)
+        degree = get("degree", (nq,), torch.int32) if compose else None
+        nbr = get("nbr_count", (nq, n_types), torch.int32) if compose else None
+        st = get("stats", (4,), torch.int64) if stats else None
+        hist = get("hist", (hist_len,), torch.int32) if (stats and hist_len) else None
+        self._check(self.lib.pg_radius_count(self._h, float(r), 1 if upper else 0,
+                                             self._p(row_ptr, torch.int32, "row_ptr"), self._p(degree, torch.int32, "degree"),
+                                             self._p(nbr, torch.int32, "nbr_count"), int(n_types),
+                                             self._p(st, torch.int64, "stats"), self._p(hist, torch.int32, "hist"),
+                                             int(hist_len) if hist is not None else 0, self._stream()))
+        self.launches += 3 + (2 if stats else 0)
+        if capacity is None:
+            total = C.c_int64()
+            self._check(self.lib.pg_radius_total(self._h, C.byref(total)))
+            cap = int(total.value)
+            res["total"] = cap
+        else:
+            cap = int(capacity)
+        col = get("col", (cap,), torch.int32)
+        d32 = get("dist32", (cap,), torch.float32) if want_dist32 else None
+        d64 = get("dist64", (cap,), torch.float64) if want_dist64 else None
+        edges = get("edges", (cap, 2), torch.int64) if want_edges else None
+        self._check(self.lib.pg_radius_fill(self._h, self._p(row_ptr, torch.int32, "row_ptr"),
+                                            self._p(col, torch.int32, "col"), self._p(d32, torch.float32, "dist32"),
+                                            self._p(d64, torch.float64, "dist64"), self._p(edges, torch.int64, "edges"),
+                                            cap, self._stream()))
+        self.launches += 1
+        return res
+
+    # ---- K7 ------------------------------------------------------------------------------------
+    def symmetrize(self, knn_idx, knn_dist, want_w32=False):
+        """Undirected union of directed kNN lists -> symmetric CSR (row_ptr, col ascending, weight=min)."""
+        n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
+        row_ptr = self._empty((n + 1,), torch.int32)
+        self._check(self.lib.pg_knn_symmetrize_count(self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+                                                     self._p(row_ptr, torch.int32, "row_ptr"), self._stream()))
+        total = C.c_int64()
+        self._check(self.lib.pg_knn_symmetrize_total(self._h, C.byref(total)))
+        e = int(total.value)
+        col = self._empty((e,), torch.int32)
+        is64 = knn_dist.dtype == torch.float64
+        w64 = self._empty((e,), torch.float64) if is64 else None
+        w32 = self._empty((e,), torch.float32) if (want_w32 or not is64) else None
+        self._check(self.lib.pg_knn_symmetrize_fill(
+            self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+            self._p(knn_dist, torch.float64, "dist64") if is64 else None,
+            None if is64 else self._p(knn_dist, torch.float32, "dist32"),
+            self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
+            self._p(w64, torch.float64, "w64"), self._p(w32, torch.float32, "w32"), self._stream()))
+        self.launches += 6 if n > 0 else 2
+        return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}
+
+    def csr_upper(self, row_ptr, col, w=None, row_id=None, want_w32=False):
+        """Symmetric CSR (rows ascending) -> edges int64 [E,2] with i<j, sorted by (i,j), + weights."""
+        n = int(row_ptr.numel()) - 1
+        up_ptr = self._empty((n + 1,), torch.int32)
+        self._check(self.lib.pg_csr_upper_count(self._h, n, self._p(row_ptr, torch.int32, "row_ptr"),
+                                                self._p(col, torch.int32, "col"), self._p(row_id, torch.int32, "row_id"),
+                                                self._p(up_ptr, torch.int32, "up_ptr"), self._stream()))
+        total = C.c_int64()
+        self._check(self.lib.pg_csr_upper_total(self._h, C.byref(total)))
+        e = int(total.value)
+        edges = self._empty((e, 2), torch.int64)
+        w64 = w32 = ew64 = ew32 = None
+        if w is not None:
+            if w.dtype == torch.float64:
+                w64, ew64 = w, self._empty((e,), torch.float64)
+                if want_w32:
+                    ew32 = self._empty((e,), torch.float32)
+            else:
+                w32, ew32 = w, self._empty((e,), torch.float32)
+        self._check(self.lib.pg_csr_upper_fill(
+            self._h, n, self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
+            self._p(w64, torch.float64, "w64"), self._p(w32, torch.float32, "w32"),
+            self._p(row_id, torch.int32, "row_id"), self._p(up_ptr, torch.int32, "up_ptr"),
+            self._p(edges, torch.int64, "edges"), self._p(ew64, torch.float64, "ew64"),
+            self._p(ew32, torch.float32, "ew32"), self._stream()))
+        self.launches += 4 if n > 0 else 2
+        return {"edges": edges, "w64": ew64, "w32": ew32, "up_ptr": up_ptr}
+
+    # ---- K8 ------------------------------------------------------------------------------------
+    def compose_degree(self, row_ptr, col, types, n_types=5, hist_len=64, compose=True):
+        n = int(row_ptr.numel()) - 1
+        nbr = self._empty((n, n_types), torch.int32) if compose else None
+        degree = self._empty((n,), torch.int32)
+        st = self._empty((4,), torch.int64)
+        hist = self._empty((hist_len,), torch.int32) if hist_len else None
+        self._check(self.lib.pg_compose_degree(
+            self._h, n, self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
+            self._p(types, torch.int32, "types"), int(n_types), self._p(nbr, torch.int32, "nbr_count"),
+            self._p(degree, torch.int32, "degree"), self._p(st, torch.int64, "stats"),
+            self._p(hist, torch.int32, "hist"), int(hist_len) if hist is not None else 0, self._stream()))
+        self.launches += 3 if n > 0 else 2
+        return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
+
+    # ---- K9 ------------------------------------------------------------------------------------
+    def halo_pack(self, xy, types, gid, lo_edge, hi_edge, capacity):
+        """Records (24 B: x, y, gid, type) of the points with x < lo_edge or x >= hi_edge."""
+        n = int(xy.shape[0])
+        recs = self._empty((max(int(capacity), 1), 3), torch.float64)  # 24-byte records
+        count = self._empty((1,), torch.int32)
+        self._check(self.lib.pg_halo_pack(self._h, n, self._p(xy, torch.float64, "xy"), self._p(types, torch.int32, "types"),
+                                          self._p(gid, torch.int32, "gid"), float(lo_edge), float(hi_edge),
+                                          C.c_void_p(recs.data_ptr()), int(capacity), self._p(count, torch.int32, "count"),
+                                          self._stream()))
+        self.launches += 1 if n > 0 else 0
+        return recs, count
+
+    def halo_unpack(self, recs, n_recs, skip_begin, skip_end, x_lo, x_hi, xy, types, gid, n_base):
+        count = self._empty((1,), torch.int32)
+        self._check(self.lib.pg_halo_unpack(self._h, C.c_void_p(recs.data_ptr()), int(n_recs), int(skip_begin), int(skip_end),
+                                            float(x_lo), float(x_hi), self._p(xy, torch.float64, "xy"),
+                                            self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
+                                            int(n_base), int(xy.shape[0]), self._p(count, torch.int32, "count"), self._stream()))
+        self.launches += 1 if n_recs > 0 else 0
+        return count
+
+    def exclusive_scan(self, x):
+        n = int(x.numel())
+        out = self._empty((n + 1,), torch.int32)
+        self._check(self.lib.pg_exclusive_scan_i32(self._h, self._p(x, torch.int32, "in"), self._p(out, torch.int32, "out"),
+                                                   n, self._stream()))
+        self.launches += 1
+        return out
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int | torch.device | None = None) -> Engine:
+    """Process-wide engine per CUDA device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("path_gene_multimodal_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        idx = torch.cuda.current_device()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        d = torch.device(device)
+        idx = d.index if d.index is not None else torch.cuda.current_device()
+    eng = _engines.get(idx)
+    if eng is None:
+        eng = _engines[idx] = Engine(idx)
+    return eng

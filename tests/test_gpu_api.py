@@ -1,0 +1,131 @@
+"""GPU: the reference-style Python surface (DataFrame / array functions) against golden fixtures made by
+the reference's own code and against the oracle."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, frames_from_golden
+from oracle import graph as ograph
+from oracle import morphology as omorph
+from oracle import tile_to_wsi as omap
+from path_gene_multimodal_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_add_wsi_coords_matches_reference_golden(golden_add_wsi):
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    nuc, tiles, expected = frames_from_golden(golden_add_wsi)
+    nuc_before, tiles_before = nuc.copy(deep=True), tiles.copy(deep=True)
+    got = add_wsi_coords_to_nuclei(nuc, tiles, tile_key_col_nuc="tile_path", tile_key_col_tiles="png_path")
+    assert list(got.columns) == golden_add_wsi["out_columns"]
+    for c in golden_add_wsi["out_columns"]:
+        if c in ("polygon", "centroid", "bounding_box", "wsi_polygon"):
+            assert got[c].tolist() == expected[c].tolist(), c                    # lists of exact floats / None
+        elif got[c].dtype.kind in "fi":
+            assert np.array_equal(got[c].to_numpy(), expected[c].to_numpy()), c  # bit-exact
+            assert str(got[c].dtype) == golden_add_wsi["out_dtypes"][c], c
+        else:
+            assert got[c].tolist() == expected[c].tolist(), c
+    pd.testing.assert_frame_equal(nuc, nuc_before)      # inputs untouched (aggregated_hovernet_run.py:281-282)
+    pd.testing.assert_frame_equal(tiles, tiles_before)
+
+
+def test_add_wsi_coords_missing_tile_raises(golden_add_wsi):
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    nuc, tiles, _ = frames_from_golden(golden_add_wsi)
+    nuc.loc[2, "tile_path"] = "/nowhere/patches/123_456.png"
+    ref_msg = (GOLDEN / "add_wsi_ref_error.txt").read_text()
+    with pytest.raises(ValueError) as ei:
+        add_wsi_coords_to_nuclei(nuc, tiles)
+    assert str(ei.value).startswith("Some nuclei have tile_key with no matching tile coords:")
+    assert "123_456" in str(ei.value) and "123_456" in ref_msg
+
+
+def test_add_wsi_coords_vs_oracle_2k_with_morphology():
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    tab = synth.make_table(2000, seed=5, dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab, closed_rings=True)
+    got = add_wsi_coords_to_nuclei(nuc, tiles, morphology=True)
+    exp = omap.add_wsi_coords_to_nuclei_oracle(nuc, tiles)
+    pd.testing.assert_frame_equal(got[exp.columns], exp)
+    feat = omorph.polygon_features_csr(tab.poly_off, tab.poly_xy)
+    for name in ("area", "perimeter", "circularity"):
+        np.testing.assert_allclose(got[name], feat[name], rtol=1e-5)
+    np.testing.assert_allclose(got["eccentricity"], feat["eccentricity"], rtol=1e-5, atol=2e-6)
+
+
+def test_add_wsi_coords_empty_frame():
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    tab = synth.make_table(10, seed=5, dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    got = add_wsi_coords_to_nuclei(nuc.iloc[:0], tiles)
+    assert len(got) == 0 and "wsi_polygon" in got.columns and "wsi_centroid_x" in got.columns
+
+
+def test_polygon_morphology_tables(known_answers):
+    from path_gene_multimodal_b200 import nuclei_morphology_table, polygon_morphology_table
+
+    rings = [[[0, 0], [4, 0], [4, 3], [0, 3]], [[10, 10], [20, 10], [20, 20], [10, 20], [10, 10]],
+             [[5 * np.cos(t) + 100, 5 * np.sin(t) - 7] for t in np.linspace(0, 2 * np.pi, 65)[:-1]]]
+    tab = polygon_morphology_table(rings)
+    assert list(tab.columns) == ["area_px2", "perimeter_px", "centroid_x", "centroid_y",
+                                 "bbox_xmin", "bbox_ymin", "bbox_xmax", "bbox_ymax"]
+    assert tab["area_px2"].tolist()[:2] == [12.0, 100.0] and tab["perimeter_px"].tolist()[:2] == [14.0, 40.0]
+    np.testing.assert_allclose(tab.loc[0, ["centroid_x", "centroid_y"]].to_numpy(dtype=float), [2.0, 1.5], rtol=1e-12)
+    assert tab.loc[1, ["bbox_xmin", "bbox_ymin", "bbox_xmax", "bbox_ymax"]].tolist() == [10.0, 10.0, 20.0, 20.0]
+    np.testing.assert_allclose(tab.loc[2, "area_px2"], 0.5 * 64 * 25 * np.sin(2 * np.pi / 64), rtol=1e-5)
+    for i, ring in enumerate(rings):
+        a, l = omorph.geos_area_length(ring)
+        np.testing.assert_allclose([tab.loc[i, "area_px2"], tab.loc[i, "perimeter_px"]], [a, l], rtol=1e-5)
+    m = nuclei_morphology_table(rings, zscore=True)
+    d = omorph.derived_features(m["area"], m["perimeter"], m["major_axis_length"], m["minor_axis_length"])
+    for name in ("perimeter_area", "compactness", "roundness", "elongation"):
+        np.testing.assert_allclose(m[name], d[name], rtol=1e-12)
+    np.testing.assert_allclose(m["compactness"], m["circularity"], rtol=1e-5)
+    np.testing.assert_allclose(m["area_z"], omorph.zscore(m["area"]), rtol=1e-12)
+
+
+def test_build_radius_graph_api(golden_graph):
+    from path_gene_multimodal_b200 import build_radius_graph
+
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    g = build_radius_graph(coords, r=25.0, types=types, symmetric_csr=True)
+    ref = ograph.radius_graph(coords, 25.0)
+    assert g["edges"].dtype == np.int64 and np.array_equal(g["edges"], golden_graph["radius_25_edges"])
+    assert np.array_equal(g["edge_index"], ref["edge_index"]) and g["edge_index"].shape == (2, 2 * len(ref["edges"]))
+    assert g["edge_attr"].dtype == np.float32 and np.array_equal(g["edge_attr"], ref["edge_attr"])
+    assert np.array_equal(g["row_ptr"], ref["row_ptr"]) and np.array_equal(g["col"], ref["col"])
+    assert np.array_equal(g["nbr_count"], ograph.composition(ref["row_ptr"], ref["col"], types, 5))
+    # the notebook's unit handling: r in micrometres on pixel coordinates scaled by mpp (ipynb:2046, :2966)
+    g_um = build_radius_graph(coords, r=40.0, mpp=0.25)
+    assert np.array_equal(g_um["edges"], ograph.radius_graph(coords * 0.25, 40.0)["edges"])
+
+
+def test_build_knn_graph_api(golden_graph):
+    from path_gene_multimodal_b200 import (build_knn_graph, degree_stats, filter_graph_by_type,
+                                           neighbour_type_composition)
+
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    g = build_knn_graph(coords, k=5, types=types)
+    assert g["knn_neighbors"].dtype == np.int64 and np.array_equal(g["knn_neighbors"], golden_graph["knn_5_idx"])
+    assert g["knn_neighbor_distances"].dtype == np.float64
+    assert np.array_equal(g["knn_neighbor_distances"], golden_graph["knn_5_dist"])
+    assert np.array_equal(g["edges"], golden_graph["knn_5_und_edges"])
+    assert np.array_equal(g["weight"], golden_graph["knn_5_und_weight"])
+    nx_g = ograph.undirected_union_networkx(g["knn_neighbors"], g["knn_neighbor_distances"])  # literal cell-11 loop
+    assert nx_g.number_of_edges() == len(g["edges"])
+    assert np.array_equal(g["degree"], np.array([nx_g.degree(i) for i in range(len(coords))]))
+    comp = neighbour_type_composition(g["row_ptr"], g["col"], types)
+    assert np.array_equal(comp, g["nbr_count"]) and np.array_equal(comp, ograph.composition(g["row_ptr"], g["col"], types, 5))
+    st = degree_stats(g["row_ptr"])
+    assert np.array_equal(st["degree"], g["degree"]) and st["max"] == g["degree"].max()
+    nodes, sub = filter_graph_by_type(g["edges"], types, keep_types=(1, 2))
+    on, oe = ograph.filter_types(g["edges"], types, (1, 2))
+    assert np.array_equal(nodes, on) and np.array_equal(sub, oe)
+    with pytest.raises(ValueError):
+        build_knn_graph(coords[:5], k=5)

@@ -1,0 +1,336 @@
+"""GPU parity: every CUDA entry point of libpathgraph.so against the CPU oracle (oracle/).
+
+Bars (north_star): bit-exact edge indices, degrees, type counts and (float64) distances;
+float32 features within 1e-5 relative (eccentricity additionally 2e-6 absolute: for a ring whose
+two principal moments coincide the value is sqrt of a rounding residue).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as ograph
+from oracle import morphology as omorph
+from oracle import tile_to_wsi as omap
+from path_gene_multimodal_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ECC_ATOL = 2e-6
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+# ---------------------------------------------------------------- scan
+@pytest.mark.parametrize("n", [0, 1, 31, 4095, 4096, 4097, 100_000, 1_234_567])
+def test_exclusive_scan(engine, n):
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 50, size=n).astype(np.int32)
+    out = engine.exclusive_scan(dev(x)).cpu().numpy()
+    ref = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(x, out=ref[1:])
+    assert np.array_equal(out, ref)
+
+
+def test_exclusive_scan_repeated(engine):
+    # epoch-tagged descriptors: back-to-back scans of different sizes must not see stale state
+    rng = np.random.default_rng(5)
+    for n in [70_000, 5_000, 300_000, 4096 * 3, 9]:
+        x = rng.integers(0, 9, size=n).astype(np.int32)
+        out = engine.exclusive_scan(dev(x)).cpu().numpy()
+        assert out[-1] == x.sum() and np.array_equal(out[1:], np.cumsum(x))
+
+
+# ---------------------------------------------------------------- K1
+def _check_morph(res, off, xy, tab=None):
+    feat = omorph.polygon_features_csr(off, xy)
+    for name in ("area", "perimeter", "circularity"):
+        np.testing.assert_allclose(res[name].cpu().numpy(), feat[name], rtol=RTOL, equal_nan=True, err_msg=name)
+    np.testing.assert_allclose(res["eccentricity"].cpu().numpy(), feat["eccentricity"], rtol=RTOL, atol=ECC_ATOL,
+                               equal_nan=True)
+    if "major_axis" in res:
+        np.testing.assert_allclose(res["major_axis"].cpu().numpy(), feat["major_axis_length"], rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(res["minor_axis"].cpu().numpy(), feat["minor_axis_length"], rtol=RTOL, atol=1e-5,
+                                   equal_nan=True)
+    return feat
+
+
+@pytest.mark.parametrize("vt", [np.float32, np.float64])
+def test_map_morph_table(engine, vt):
+    tab = synth.make_table(20_000, seed=11, dtype=vt)
+    res = engine.map_morph(dev(tab.poly_off), dev(tab.poly_xy), dev(tab.nuc_tile), dev(tab.tile_x), dev(tab.tile_y),
+                           dev(tab.centroid), dev(tab.bbox), write_polygons=True, extra=True)
+    wsi_c, wsi_b, wsi_p = omap.map_arrays(tab.tile_x, tab.tile_y, tab.nuc_tile, tab.centroid, tab.bbox, tab.poly_off,
+                                          tab.poly_xy)
+    assert np.array_equal(res["wsi_centroid"].cpu().numpy(), wsi_c)          # float64 add: bit-exact
+    assert np.array_equal(res["wsi_bbox"].cpu().numpy().astype(np.int64), wsi_b)
+    assert np.array_equal(res["wsi_poly_xy"].cpu().numpy().astype(np.float64), wsi_p)  # lattice coords: exact in f32 too
+    feat = _check_morph(res, tab.poly_off, tab.poly_xy)
+    tx = tab.tile_x[tab.nuc_tile].astype(np.float64)
+    ty = tab.tile_y[tab.nuc_tile].astype(np.float64)
+    np.testing.assert_allclose(res["centroid_x"].cpu().numpy(), feat["centroid_x"] + tx, rtol=1e-12)
+    np.testing.assert_allclose(res["centroid_y"].cpu().numpy(), feat["centroid_y"] + ty, rtol=1e-12)
+    bb = res["poly_bbox"].cpu().numpy()
+    assert np.array_equal(bb[:, 0], feat["bbox_xmin"] + tx) and np.array_equal(bb[:, 3], feat["bbox_ymax"] + ty)
+
+
+def test_map_morph_ragged_and_degenerate(engine):
+    # empty rows, 1- and 2-vertex rows, a collinear ring, a long ring (> 32 vertices), closed == open ring
+    rings = [
+        [], [[1.0, 2.0]], [[0.0, 0.0], [3.0, 4.0]],
+        [[0.0, 0.0], [1.0, 1.0], [2.0, 2.0]],                                   # zero area
+        [[0.0, 0.0], [4.0, 0.0], [4.0, 3.0], [0.0, 3.0]],                       # rectangle 4x3
+        [[0.0, 0.0], [4.0, 0.0], [4.0, 3.0], [0.0, 3.0], [0.0, 0.0]],           # same, explicitly closed
+        [[0.0, 3.0], [4.0, 3.0], [4.0, 0.0], [0.0, 0.0]],                       # clockwise
+        [[100000.5 + 10 * np.cos(t), 200000.25 + 6 * np.sin(t)] for t in np.linspace(0, 2 * np.pi, 257)[:-1]],
+        [],
+    ]
+    off = np.zeros(len(rings) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(r) for r in rings])
+    xy = np.array([p for r in rings for p in r], dtype=np.float64).reshape(-1, 2)
+    res = engine.map_morph(dev(off), dev(xy), write_polygons=False, extra=True)
+    feat = _check_morph(res, off, xy)
+    area = res["area"].cpu().numpy()
+    per = res["perimeter"].cpu().numpy()
+    assert np.isnan(area[[0, 1, 2, 8]]).all() and area[3] == 0.0
+    assert area[4] == 12.0 and area[5] == 12.0 and area[6] == 12.0 and per[4] == 14.0 and per[5] == 14.0
+    ecc = res["eccentricity"].cpu().numpy()
+    assert np.isnan(ecc[3]) and abs(ecc[4] - np.sqrt(1 - 9.0 / 16.0)) < 1e-6
+    # ellipse with semi-axes 10 and 6: eccentricity -> sqrt(1 - 0.36)
+    assert abs(ecc[7] - 0.8) < 1e-3
+    assert np.allclose(res["centroid_x"].cpu().numpy()[7], 100000.5, atol=1e-6)
+    assert feat["area"][4] == 12.0
+
+
+def test_map_morph_full_size_properties(engine):
+    # C3 shape (reduced count so the oracle finishes in seconds is covered above); here: 2M x 32, invariants only
+    n = 2_000_000
+    off, xy = synth.make_polygons(n, seed=1003, v_fixed=32)
+    rng = np.random.default_rng(3)
+    side = 64
+    tile_x = ((np.arange(side * side) % side) * 508).astype(np.int32)
+    tile_y = ((np.arange(side * side) // side) * 508).astype(np.int32)
+    nuc_tile = rng.integers(0, side * side, size=n).astype(np.int32)
+    d_off, d_xy = dev(off), dev(xy)
+    a = engine.map_morph(d_off, d_xy, dev(nuc_tile), dev(tile_x), dev(tile_y), write_polygons=True)
+    b = engine.map_morph(d_off, d_xy, write_polygons=False)               # no shift
+    c = engine.map_morph(d_off, a["wsi_poly_xy"], write_polygons=False)   # features of the shifted rings
+    for name in ("area", "perimeter", "eccentricity", "circularity"):
+        assert torch.equal(a[name], b[name]), name                       # translation invariance, bitwise (local frame)
+        assert torch.equal(a[name], c[name]), name
+    shift = torch.stack([dev(tile_x)[dev(nuc_tile).long()], dev(tile_y)[dev(nuc_tile).long()]], dim=1).float()
+    owner = torch.repeat_interleave(torch.arange(n, device="cuda"), 32)
+    assert torch.equal(a["wsi_poly_xy"], d_xy + shift[owner])
+    assert bool((a["area"] > 0).all()) and bool((a["eccentricity"] < 1).all()) and bool((a["circularity"] <= 1.0001).all())
+
+
+# ---------------------------------------------------------------- grid + radius
+def _radius(engine, coords, types, r, upper, bounds=None, cell=None):
+    from path_gene_multimodal_b200.engine import radius_cell
+
+    engine.grid_build(dev(coords), dev(types), None, cell or radius_cell(r), bounds)
+    return engine.radius_graph(r, upper=upper, n_types=5, want_dist32=True, want_dist64=True, want_edges=True)
+
+
+def _check_radius(engine, coords, types, r, **kw):
+    ref = ograph.radius_graph(coords, r)
+    n = len(coords)
+    g = _radius(engine, coords, types, r, upper=True, **kw)
+    edges = g["edges"].cpu().numpy()
+    assert np.array_equal(edges, ref["edges"])
+    assert np.array_equal(g["dist64"].cpu().numpy(), ref["dist"])                    # bit-exact float64
+    assert np.array_equal(g["dist32"].cpu().numpy(), ref["dist"].astype(np.float32))
+    deg, stats = ograph.degree_stats(ref["row_ptr"])
+    assert np.array_equal(g["degree"].cpu().numpy(), deg)
+    assert np.array_equal(g["nbr_count"].cpu().numpy(), ograph.composition(ref["row_ptr"], ref["col"], types, 5))
+    st = engine.decode_stats(g["stats"], g["hist"])
+    assert (st["min"], st["max"], st["sum"], st["sumsq"], st["n"]) == (stats["min"], stats["max"], stats["sum"], stats["sumsq"], n)
+    assert abs(st["mean"] - stats["mean"]) < 1e-12 and abs(st["std"] - stats["std"]) < 1e-9
+    h = np.zeros(64, dtype=np.int64)
+    np.add.at(h, np.minimum(deg, 63), 1)
+    assert np.array_equal(st["hist"], h)
+    s = _radius(engine, coords, types, r, upper=False, **kw)
+    assert np.array_equal(s["row_ptr"].cpu().numpy(), ref["row_ptr"])
+    assert np.array_equal(s["col"].cpu().numpy(), ref["col"])
+    assert np.array_equal(s["dist64"].cpu().numpy(), ref["csr_dist"])
+    return ref
+
+
+def test_radius_golden(engine, golden_graph):
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    for r in (10.0, 25.0, 40.0):
+        ref = _check_radius(engine, coords, types, r)
+        assert np.array_equal(ref["edges"], golden_graph[f"radius_{int(r)}_edges"])   # scipy's own output, committed
+
+
+def test_radius_uniform_50k(engine):
+    xy, types, side = synth.make_points(50_000, seed=21)
+    _check_radius(engine, xy, types, 50.0)
+    _check_radius(engine, xy, types, 50.0, bounds=(0.0, 0.0, float(side), float(side)))
+    _check_radius(engine, xy, types, 50.0, cell=17.0)     # cell smaller than r: ring radius 3
+    _check_radius(engine, xy, types, 50.0, cell=400.0)    # cell much larger than r
+
+
+def test_radius_lattice_inclusive_and_duplicates(engine):
+    gx, gy = np.meshgrid(np.arange(40.0) * 5.0, np.arange(40.0) * 5.0)
+    c = np.stack([gx.ravel(), gy.ravel()], axis=1)
+    c = np.concatenate([c, c[:100], c[:10]])  # duplicates (distance 0) are neighbours
+    t = (np.arange(len(c)) % 5 + 1).astype(np.int32)
+    _check_radius(engine, c, t, 5.0)      # distance exactly r is included
+    _check_radius(engine, c, t, 10.0)
+    _check_radius(engine, c, t, 0.0)      # only duplicates
+
+
+def test_radius_heavy_rows(engine):
+    # a dense clump: rows far longer than the fill kernel's chunk, plus isolated points
+    rng = np.random.default_rng(8)
+    c = np.concatenate([rng.normal(500.0, 3.0, size=(300, 2)), rng.random((2000, 2)) * 5000.0])
+    t = rng.integers(1, 6, size=len(c)).astype(np.int32)
+    _check_radius(engine, c, t, 40.0)
+
+
+def test_radius_empty_and_tiny(engine):
+    t1 = np.ones(1, dtype=np.int32)
+    g = _radius(engine, np.zeros((1, 2)), t1, 5.0, upper=True)
+    assert g["total"] == 0 and g["row_ptr"].cpu().tolist() == [0, 0] and g["degree"].cpu().tolist() == [0]
+    g = _radius(engine, np.array([[0.0, 0.0], [3.0, 4.0]]), np.array([1, 2], dtype=np.int32), 5.0, upper=True)
+    assert g["edges"].cpu().tolist() == [[0, 1]] and g["dist64"].cpu().tolist() == [5.0]
+    assert g["nbr_count"].cpu().tolist() == [[0, 1, 0, 0, 0], [1, 0, 0, 0, 0]]
+    g = _radius(engine, np.zeros((0, 2)), np.zeros(0, dtype=np.int32), 5.0, upper=True)
+    assert g["total"] == 0
+
+
+def test_radius_capacity_overflow(engine):
+    from path_gene_multimodal_b200._lib import PathGraphError
+    from path_gene_multimodal_b200.engine import radius_cell
+
+    xy, types, _ = synth.make_points(5000, seed=2)
+    engine.grid_build(dev(xy), dev(types), None, radius_cell(50.0), None)
+    g = engine.radius_graph(50.0, upper=True, capacity=100_000)
+    engine.check_overflow()
+    total = int(g["row_ptr"][-1])
+    ref = ograph.radius_graph(xy, 50.0)
+    assert total == len(ref["edges"]) and np.array_equal(g["col"][:total].cpu().numpy(), ref["edges"][:, 1])
+    engine.radius_graph(50.0, upper=True, capacity=10)
+    with pytest.raises(PathGraphError):
+        engine.check_overflow()
+    engine.check_overflow()  # flag is cleared by the check
+
+
+# ---------------------------------------------------------------- kNN + union + composition
+def _check_knn(engine, coords, types, k, cell=None, bounds=None):
+    from path_gene_multimodal_b200.engine import default_knn_cell
+
+    n = len(coords)
+    ref_idx, ref_d = ograph.knn(coords, k)
+    span = np.ptp(coords, axis=0)
+    cell = cell or default_knn_cell(n, max(span[0], 1e-9) * max(span[1], 1e-9), k)
+    engine.grid_build(dev(coords), dev(types), None, cell, bounds)
+    kn = engine.knn(k, dist_dtype=torch.float64, both=True)
+    assert np.array_equal(kn["knn_idx"].cpu().numpy(), ref_idx)
+    assert np.array_equal(kn["dist64"].cpu().numpy(), ref_d)
+    assert np.array_equal(kn["dist32"].cpu().numpy(), ref_d.astype(np.float32))
+    e, w, rp, col, ww = ograph.undirected_union(ref_idx, ref_d)
+    sym = engine.symmetrize(kn["knn_idx"], kn["dist64"], want_w32=True)
+    assert np.array_equal(sym["row_ptr"].cpu().numpy(), rp)
+    assert np.array_equal(sym["col"].cpu().numpy(), col)
+    assert np.array_equal(sym["w64"].cpu().numpy(), ww)
+    assert np.array_equal(sym["w32"].cpu().numpy(), ww.astype(np.float32))
+    up = engine.csr_upper(sym["row_ptr"], sym["col"], sym["w64"])
+    assert np.array_equal(up["edges"].cpu().numpy(), e) and np.array_equal(up["w64"].cpu().numpy(), w)
+    comp = engine.compose_degree(sym["row_ptr"], sym["col"], dev(types), 5)
+    deg, stats = ograph.degree_stats(rp)
+    assert np.array_equal(comp["degree"].cpu().numpy(), deg)
+    assert np.array_equal(comp["nbr_count"].cpu().numpy(), ograph.composition(rp, col, types, 5))
+    st = engine.decode_stats(comp["stats"], comp["hist"])
+    assert (st["min"], st["max"], st["sum"], st["sumsq"]) == (stats["min"], stats["max"], stats["sum"], stats["sumsq"])
+    return ref_idx, ref_d, e, w
+
+
+def test_knn_golden(engine, golden_graph, known_answers):
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    for k in (5, 8, 16):
+        idx, d, e, w = _check_knn(engine, coords, types, k)
+        assert np.array_equal(idx, golden_graph[f"knn_{k}_idx"]) and np.array_equal(d, golden_graph[f"knn_{k}_dist"])
+        assert np.array_equal(e, golden_graph[f"knn_{k}_und_edges"])
+        # distances agree with scipy's own cKDTree.query(k+1) output (self at 0; tie order aside)
+        full = np.sort(np.concatenate([np.zeros((len(coords), 1)), d], axis=1), axis=1)
+        assert np.array_equal(full, golden_graph[f"knn_{k}_scipy_dist_sorted"])
+
+
+def test_knn_notebook_distances(engine, known_answers):
+    # D-1: the five centroids printed in the notebook; cell 11 swaps (y, x) -> Point(x, y)
+    c = np.array(known_answers["centroids_yx"])[:, ::-1].copy()
+    engine.grid_build(dev(c), None, None, 50.0, None)
+    kn = engine.knn(4, dist_dtype=torch.float64)
+    idx, d = kn["knn_idx"].cpu().numpy(), kn["dist"].cpu().numpy()
+    for key, val in known_answers["distances"].items():
+        i, j = map(int, key.split(","))
+        got = d[i][list(idx[i]).index(j)]
+        assert abs(got - val) < 5e-7, (key, got, val)
+
+
+@pytest.mark.parametrize("k", [1, 5, 8, 16, 33])
+def test_knn_uniform_30k(engine, k):
+    xy, types, side = synth.make_points(30_000, seed=31)
+    _check_knn(engine, xy, types, k)
+
+
+def test_knn_cell_sizes_and_bounds(engine):
+    xy, types, side = synth.make_points(20_000, seed=32)
+    _check_knn(engine, xy, types, 8, cell=10.0)      # many rings
+    _check_knn(engine, xy, types, 8, cell=1000.0)    # one big block
+    _check_knn(engine, xy, types, 8, bounds=(0.0, 0.0, float(side), float(side)))
+    _check_knn(engine, xy, types, 8, bounds=(1000.0, 1000.0, 3000.0, 3000.0))  # points outside the bounds are clamped
+
+
+def test_knn_clustered_and_ties(engine):
+    rng = np.random.default_rng(41)
+    clusters = np.concatenate([rng.normal(c, 15.0, size=(800, 2)) for c in rng.random((12, 2)) * 20000.0])
+    t = rng.integers(1, 6, size=len(clusters)).astype(np.int32)
+    _check_knn(engine, clusters, t, 8)               # density holes: ring expansion across empty cells
+    gx, gy = np.meshgrid(np.arange(30.0), np.arange(30.0))
+    lat = np.stack([gx.ravel(), gy.ravel()], axis=1)
+    lat = np.concatenate([lat, lat[:50]])
+    tl = (np.arange(len(lat)) % 5 + 1).astype(np.int32)
+    for k in (4, 5, 8):
+        _check_knn(engine, lat, tl, k, cell=2.5)     # exact ties everywhere: (d^2, index) order
+
+
+def test_knn_small_n(engine):
+    c = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 2.0], [5.0, 5.0]])
+    t = np.array([1, 2, 3, 4], dtype=np.int32)
+    _check_knn(engine, c, t, 3)                      # k = N - 1
+    from path_gene_multimodal_b200._lib import PathGraphError
+
+    engine.grid_build(dev(c), dev(t), None, 1.0, None)
+    with pytest.raises(PathGraphError):
+        engine.knn(4)                                # k >= N is an error
+
+
+def test_full_size_c2_against_scipy(engine):
+    # BASELINE config 2 at full size: 1M nuclei, r = 50 px - scipy finishes in seconds, so compare outright
+    xy, types, side = synth.make_points(1_000_000, seed=synth.SEEDS["C2"])
+    ref = ograph.radius_graph(xy, 50.0)
+    g = _radius(engine, xy, types, 50.0, upper=True, bounds=(0.0, 0.0, float(side), float(side)))
+    assert np.array_equal(g["edges"].cpu().numpy(), ref["edges"])
+    assert np.array_equal(g["dist32"].cpu().numpy(), ref["dist"].astype(np.float32))
+    deg = np.diff(ref["row_ptr"])
+    assert np.array_equal(g["degree"].cpu().numpy(), deg)
+    assert np.array_equal(g["nbr_count"].cpu().numpy(), ograph.composition(ref["row_ptr"], ref["col"], types, 5))
+    # size-independent properties
+    assert int(g["degree"].sum()) == 2 * len(ref["edges"])
+    e = g["edges"]
+    assert bool((e[:, 0] < e[:, 1]).all())
+    key = e[:, 0] * len(xy) + e[:, 1]
+    assert bool((key[1:] > key[:-1]).all())          # strictly sorted by (i, j)
+
+
+def test_full_size_c1_knn_against_scipy(engine):
+    xy, types, side = synth.make_points(100_000, seed=synth.SEEDS["C1"])
+    _check_knn(engine, xy, types, 8, bounds=(0.0, 0.0, float(side), float(side)))
