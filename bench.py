@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py - nuclei/s of the radius-graph + neighbour-type composition + degree-statistics build on
+a 1M-nucleus synthetic WSI (BASELINE.json configs[1], "C2"), per GPU, weak-scaled by slide over N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one slide:
+  pg_grid_build (histogram, look-back scan, counting-sort scatter) -> pg_radius_count (fused
+  neighbour-type histogram + degree statistics) -> scan -> pg_radius_fill (edges i<j, float32 distances).
+`value`    : inputs resident in HBM, device time from CUDA events, L2 flushed between steps.
+`e2e`      : the public call build_radius_graph(host coords, ...) -> host arrays (H2D + kernels + D2H).
+`roofline` : the dominant kernel, timed inside the library with CUDA events on its own stream.
+`cpu_baseline` / `--impl reference`: the notebook's scipy path (oracle/graph.py) on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_NUCLEI = 1_000_000
+RADIUS = 50.0
+N_TYPES = 5
+METRIC = "nuclei/s, kNN+radius graph+morphology, 1/2/4/8 B200; % of HBM peak"
+WORKLOAD = "C2: 1M-nuclei WSI, radius graph r=50px + neighbour-type composition + degree stats"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict | None:
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in Path(self.path).read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            return None
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference
+def reference_pipeline(coords, types, r, n_types=N_TYPES):
+    """The notebook's radius-graph path (cells 23-26) + numpy composition / degree. Returns n_edges."""
+    from oracle import graph as ograph
+
+    edges = ograph.radius_graph_notebook_loop(coords, r)            # cKDTree, query_ball_tree, i<j Python loop
+    edge_index = np.vstack([edges.T, edges[:, ::-1].T])             # ipynb:3021 (as written)
+    d = np.linalg.norm(coords[edges[:, 0]] - coords[edges[:, 1]], axis=1)
+    edge_attr = np.concatenate([d[:, None], d[:, None]], axis=0).astype(np.float32)
+    row_ptr, col, _ = ograph.symmetric_csr(edges, d, len(coords))
+    ograph.composition(row_ptr, col, types, n_types)
+    ograph.degree_stats(row_ptr)
+    return len(edges), edge_index.shape, edge_attr.shape
+
+
+def cpu_sample(n, seed):
+    from path_gene_multimodal_b200 import synth
+
+    xy, types, side = synth.make_points(n, seed)
+    return xy, types, side
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # calibrate on a small slide, then size the per-step sample so K+W steps fit in ~150 s
+    xy, types, _ = cpu_sample(50_000, 77)
+    t0 = time.perf_counter()
+    reference_pipeline(xy, types, RADIUS)
+    rate = 50_000 / (time.perf_counter() - t0)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    n = int(min(N_NUCLEI, max(50_000, rate * budget * 0.8)))
+    xy, types, side = cpu_sample(n, 1002)
+    for _ in range(args.warmup):
+        reference_pipeline(xy, types, RADIUS)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_pipeline(xy, types, RADIUS)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = (f"{n} nuclei per step (same density, r=50px) of the 1M-nuclei slide; scipy cKDTree.query_ball_tree + "
+              "the notebook's i<j Python loop + numpy composition/degree")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "nuclei/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nuclei_per_step": n, "radius_px": RADIUS, "n_types": N_TYPES},
+        "cpu_baseline": {"value": val, "unit": "nuclei/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": len(os.sched_getaffinity(0)),
+                         "note": "query_ball_tree has no workers parameter and the edge loop is GIL-bound: 1 thread is all it can use"},
+        "e2e": {"value": val, "unit": "nuclei/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ ours
+def algorithmic_bytes(n, e_dir):
+    """radius + composition + degree = 48 N + 8 E_dir bytes (E_dir = 2 E_und)."""
+    return 48 * n + 8 * e_dir
+
+
+def kernel_bytes(name, n, e_und, cells):
+    """Compulsory bytes of one launch of each kernel (its own inputs read once + outputs written once)."""
+    table = {
+        "histogram_kernel": 16 * n + 8 * n + 4 * cells,            # xy in; cell_of + rank out; cell counters
+        "scan_lookback_kernel": None,                               # depends on which scan: filled by caller
+        "scatter_kernel": 16 * n + 4 * n + 12 * n + 32 * n,         # xy, type, cell_of+rank+start in; sorted xy + meta out
+        "radius_count_kernel<8>": 32 * n + 4 * cells + 4 * n + 4 * n + 4 * N_TYPES * n,  # sorted xy+meta, cell_start in; count, degree, nbr out
+        "radius_fill_kernel": 32 * n + 4 * cells + 8 * n + 4 * e_und + 4 * e_und + 16 * e_und,  # + row_ptr in; col, dist32, edges out
+    }
+    return table.get(name)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    from path_gene_multimodal_b200 import _host, build_radius_graph, synth
+    from path_gene_multimodal_b200.engine import get_engine, radius_cell
+
+    eng = get_engine(local_rank)
+    peak, peak_src = measured_peak()
+    n = N_NUCLEI
+    xy_np, types_np, side = synth.make_points(n, synth.SEEDS["C2"] + rank)   # one slide per rank (weak scaling)
+    bounds = (0.0, 0.0, float(side), float(side))
+    # pinned host copies (e2e input) and device-resident copies (value)
+    h_xy = _host.pinned_empty((n, 2), np.float64); h_xy[...] = xy_np
+    h_ty = _host.pinned_empty((n,), np.int32); h_ty[...] = types_np
+    d_xy = torch.from_numpy(h_xy).to(dev)
+    d_ty = torch.from_numpy(h_ty).to(dev)
+    cell = radius_cell(RADIUS)
+
+    # exact-size pass once: sizes the reusable output buffers and gives E for the byte counts
+    eng.grid_build(d_xy, d_ty, None, cell, bounds)
+    g0 = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_edges=True)
+    e_und = int(g0["total"])
+    info = eng.grid_info()
+    cells = info["nx"] * info["ny"]
+    cap = int(e_und * 1.25) + 1024
+    out = {}
+
+    def step():
+        nonlocal out
+        eng.grid_build(d_xy, d_ty, None, cell, bounds)
+        out = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True, capacity=cap, out=out)
+
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    eng.check_overflow()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launches
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = eng.launches - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    clocks = sampler.stop()
+    eng.check_overflow()
+    total_ms = float(sum(step_ms))
+    assert int(out["row_ptr"][-1]) == e_und
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: public host API, pinned host inputs, H2D + kernels + D2H inside the timed region
+    res = None
+    for _ in range(3):
+        res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=bounds, device=local_rank)
+    assert res["edges"].shape[0] == e_und
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=bounds, device=local_rank)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * n * e2e_steps / (e2e_ms / 1e3)
+    h2d = h_xy.nbytes + h_ty.nbytes
+    d2h = res["edge_index"].nbytes + res["edge_attr"].nbytes + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nuclei_per_gpu": n, "radius_px": RADIUS, "n_types": N_TYPES,
+                   "undirected_edges": e_und, "grid_cells": cells, "parallelism": f"slide-parallel x{world} (one slide per GPU, no data-path collective)",
+                   "l2": "512 MB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step, summed, max over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "nuclei/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps, "steps": e2e_steps,
+                "api": "path_gene_multimodal_b200.build_radius_graph(host coords, r, types) -> host edge_index/edge_attr/degree/nbr_count"},
+        "gpu_launches": int(launches),
+    }
+
+    if rank == 0:
+        # ---- per-kernel timing inside the library (CUDA events on the launching stream), L2 flushed
+        eng.profile(True)
+        reps = 10
+        for _ in range(reps):
+            flush.zero_()
+            step()
+        recs = eng.profile_records()
+        eng.profile(False)
+        per = {}
+        for name, ms in recs:
+            per.setdefault(name, []).append(ms)
+        avg = {k: sum(v) / len(v) for k, v in per.items()}
+        share = {k: sum(v) / reps for k, v in per.items()}  # ms per step
+        dom = max(share, key=share.get)
+        kb = kernel_bytes(dom, n, e_und, cells)
+        step_sum = sum(share.values())
+        line["kernels_ms_per_step"] = {k: round(v, 5) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}
+        if kb is not None:
+            ach = kb / (avg[dom] / 1e3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": None, "algorithmic_bytes_per_launch": int(kb), "avg_launch_ms": avg[dom],
+                                "share_of_step": share[dom] / step_sum, "peak_source": peak_src}
+        alg = algorithmic_bytes(n, 2 * e_und)
+        ach_step = alg / (total_ms / args.steps / 1e3) / 1e9
+        line["roofline_step"] = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
+                                 "algorithmic_bytes_per_step": int(alg), "bytes_per_nucleus": alg / n,
+                                 "note": "SURVEY 8(d): 48 N + 8 E_dir over the whole step (all kernels + launch gaps)"}
+        line["stages"] = other_stages(eng, dev, flush, peak)
+        if world == 1:
+            t0 = time.perf_counter()
+            ne, _, _ = reference_pipeline(xy_np, types_np, RADIUS)
+            dt = time.perf_counter() - t0
+            assert ne == e_und
+            line["cpu_baseline"] = {
+                "value": n / dt, "unit": "nuclei/s", "cores": 1, "kind": "port",
+                "sample": "the full 1M-nuclei slide once: scipy cKDTree + query_ball_tree + the notebook's i<j Python loop + "
+                          "np.linalg.norm + numpy composition/degree (oracle/graph.py); same edges as the GPU run",
+                "seconds": dt, "host_cores_available": len(os.sched_getaffinity(0))}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def other_stages(eng, dev, flush, peak):
+    """Device-resident timings of the other hot-path stages (informational; not the headline)."""
+    import torch
+
+    from path_gene_multimodal_b200 import synth
+    from path_gene_multimodal_b200.engine import default_knn_cell
+
+    def timed(fn, reps=5):
+        ms = []
+        for i in range(reps + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(e0.elapsed_time(e1))
+        return statistics.median(ms)
+
+    out = {}
+    # C3: 2M polygons x 32 vertices, fused tile->WSI shift + morphology, float32 vertices
+    n3 = 2_000_000
+    off, xy = synth.make_polygons(n3, synth.SEEDS["C3"], v_fixed=32)
+    rng = np.random.default_rng(3)
+    side = 73
+    tile_x = torch.from_numpy(((np.arange(side * side) % side) * 508).astype(np.int32)).to(dev)
+    tile_y = torch.from_numpy(((np.arange(side * side) // side) * 508).astype(np.int32)).to(dev)
+    nuc_tile = torch.from_numpy(rng.integers(0, side * side, size=n3).astype(np.int32)).to(dev)
+    cen = torch.from_numpy(rng.random((n3, 2)) * 508).to(dev)
+    bb = torch.from_numpy(rng.integers(0, 508, size=(n3, 4)).astype(np.int32)).to(dev)
+    d_off, d_xy = torch.from_numpy(off).to(dev), torch.from_numpy(xy).to(dev)
+    res = {}
+
+    def morph():
+        nonlocal res
+        res = eng.map_morph(d_off, d_xy, nuc_tile, tile_x, tile_y, cen, bb, write_polygons=True, out=res)
+
+    ms = timed(morph)
+    m = int(xy.shape[0])
+    b3 = 16 * m + 84 * n3
+    out["C3_map_morph_2Mx32_f32"] = {"ms": ms, "polygons_per_s": n3 / ms * 1e3, "algorithmic_bytes": b3,
+                                     "achieved_GBs": b3 / ms / 1e6, "frac_of_peak": b3 / ms / 1e6 / peak}
+    del d_xy, res, cen, bb
+    # C1-style kNN k=8 + undirected union + composition on the 1M slide
+    xy1, ty1, side1 = synth.make_points(N_NUCLEI, synth.SEEDS["C2"])
+    dx, dt_ = torch.from_numpy(xy1).to(dev), torch.from_numpy(ty1).to(dev)
+    cellk = default_knn_cell(N_NUCLEI, float(side1) ** 2, 8)
+    kres = {}
+
+    def knn():
+        nonlocal kres
+        eng.grid_build(dx, dt_, None, cellk, (0.0, 0.0, float(side1), float(side1)))
+        kres = eng.knn(8, dist_dtype=torch.float32, out=kres)
+
+    ms = timed(knn)
+    out["knn_k8_1M_grid+query"] = {"ms": ms, "nuclei_per_s": N_NUCLEI / ms * 1e3}
+
+    def knn_union():
+        knn()
+        sym = eng.symmetrize(kres["knn_idx"], kres["dist32"])
+        eng.compose_degree(sym["row_ptr"], sym["col"], dt_, N_TYPES)
+
+    ms = timed(knn_union, reps=3)
+    out["knn_k8_1M_full(grid+query+union+composition)"] = {"ms": ms, "nuclei_per_s": N_NUCLEI / ms * 1e3}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,9 +133,13 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
 int pg_radius_total(pg_handle* h, int64_t* total);
 /* fill pass: col int32 [capacity] ascending per row, dist32 / dist64 (either may be NULL),
  * edges_i64 int64 [capacity,2] rows (i, j) (NULL = skip; the notebook's `edges` when flags=UPPER).
+ * With flags=UPPER and the exact total n_edges = E (from pg_radius_total) the notebook's packed
+ * tensors can be written directly: edge_index int64 [2,2E] = hstack(edges.T, edges[:, ::-1].T)
+ * (ipynb:3021) and edge_attr float32 [2E] = concat(d, d) (ipynb:3041-3042); NULL = skip.
  * Rows that would pass `capacity` are dropped and pg_check_overflow reports it. */
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
-                   int64_t* edges_i64, int64_t capacity, pg_stream stream);
+                   int64_t* edges_i64, int64_t* edge_index, float* edge_attr, int64_t n_edges,
+                   int64_t capacity, pg_stream stream);
 /* synchronises; PG_ERR_CAPACITY if any fill since the last check overflowed its buffers */
 int pg_check_overflow(pg_handle* h);
 
@@ -180,6 +184,16 @@ int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_
                    int32_t skip_end, double x_lo, double x_hi, double* xy, int32_t* type,
                    int32_t* gid, int32_t n_base, int32_t capacity, int32_t* count_out,
                    pg_stream stream);
+
+/* ---- launch accounting and per-kernel timing (CUDA events recorded on the launching stream) ----
+ * pg_launch_count: kernels launched through this handle so far.
+ * pg_profile_enable(1) starts recording one (name, start, stop) event pair per kernel launch and
+ * clears earlier records; pg_profile_count synchronises the device and returns how many records
+ * there are; pg_profile_get returns the kernel name (library-owned) and its duration in ms. */
+int64_t pg_launch_count(pg_handle* h);
+int pg_profile_enable(pg_handle* h, int on);
+int pg_profile_count(pg_handle* h);
+int pg_profile_get(pg_handle* h, int i, const char** name, float* ms);
 
 /* ---- exclusive scan (decoupled look-back), exposed for tests: out[i] = sum in[0..i), out[n] = total */
 int pg_exclusive_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, pg_stream stream);

@@ -15,19 +15,45 @@ def to_device(arr, dtype: np.dtype, device: torch.device, name: str = "array") -
     a = np.ascontiguousarray(arr, dtype=dtype)
     if a.size == 0:
         return torch.empty(a.shape, dtype=_torch_dtype(dtype), device=device)
-    pinned = torch.empty(a.shape, dtype=_torch_dtype(dtype), pin_memory=True)
+    t = torch.from_numpy(a)
+    if t.is_pinned():  # caller already staged it (e.g. pinned_empty): DMA straight from it
+        return t.to(device, non_blocking=True)
+    pinned = torch.empty(a.shape, dtype=_torch_dtype(dtype), pin_memory=True)  # torch caches pinned blocks
     pinned.numpy()[...] = a
     return pinned.to(device, non_blocking=True)
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by page-locked memory; to_device() copies from it without re-staging."""
+    return torch.empty(shape, dtype=_torch_dtype(dtype), pin_memory=True).numpy()
+
+
 def to_host(t: torch.Tensor) -> np.ndarray:
-    """device tensor -> numpy through a pinned buffer (synchronises the current stream)."""
+    """device tensor -> numpy array that owns a pinned buffer (synchronises the current stream)."""
     if t.numel() == 0:
         return np.empty(tuple(t.shape), dtype=_numpy_dtype(t.dtype))
     pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     pinned.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return pinned.numpy().copy()
+    return pinned.numpy()
+
+
+def to_host_many(tensors: dict) -> dict:
+    """Several device tensors -> numpy with one stream synchronisation."""
+    out, dev = {}, None
+    for k, t in tensors.items():
+        if t is None:
+            continue
+        if t.numel() == 0:
+            out[k] = np.empty(tuple(t.shape), dtype=_numpy_dtype(t.dtype))
+            continue
+        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pinned.copy_(t, non_blocking=True)
+        out[k] = pinned
+        dev = t.device
+    if dev is not None:
+        torch.cuda.current_stream(dev).synchronize()
+    return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
 
 def as_int32(arr, name: str) -> np.ndarray:

@@ -54,7 +54,11 @@ SIGNATURES = {
     "pg_knn": (C.c_int, [vp, i32, vp, vp, vp, f64, f64, vp, vp]),
     "pg_radius_count": (C.c_int, [vp, f64, i32, vp, vp, vp, i32, vp, vp, i32, vp]),
     "pg_radius_total": (C.c_int, [vp, C.POINTER(i64)]),
-    "pg_radius_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, vp]),
+    "pg_radius_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+    "pg_launch_count": (C.c_int64, [vp]),
+    "pg_profile_enable": (C.c_int, [vp, C.c_int]),
+    "pg_profile_count": (C.c_int, [vp]),
+    "pg_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "pg_check_overflow": (C.c_int, [vp]),
     "pg_knn_symmetrize_count": (C.c_int, [vp, i32, i32, vp, vp, vp]),
     "pg_knn_symmetrize_total": (C.c_int, [vp, C.POINTER(i64)]),

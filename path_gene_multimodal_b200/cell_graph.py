@@ -106,19 +106,21 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
         raise ValueError("r must be finite and >= 0")
     with torch.cuda.device(eng.device):
         eng.grid_build(d_xy, d_t, None, radius_cell(r), bounds)  # bounds=None: min/max reduced on the device
-        g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=True, want_edges=True)
-        edges = _host.to_host(g["edges"])
-        d32 = _host.to_host(g["dist32"])
+        g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=False, want_edge_index=True)
+        e = int(g["total"])
+        host = _host.to_host_many({"edge_index": g["edge_index"], "edge_attr": g["edge_attr"], "degree": g["degree"],
+                                   "nbr_count": g["nbr_count"] if d_t is not None else None,
+                                   "stats": g["stats"], "hist": g["hist"]})
         out = {
-            "edges": edges,
-            "dist": d32,
-            "edge_index": np.hstack([edges.T, edges[:, ::-1].T]),
-            "edge_attr": np.concatenate([d32[:, None], d32[:, None]], axis=0),
-            "degree": _host.to_host(g["degree"]),
-            "degree_stats": eng.decode_stats(g["stats"], g["hist"]),
+            "edges": host["edge_index"][:, :e].T,      # view: rows (i, j), i < j, sorted by (i, j)
+            "dist": host["edge_attr"][:e, 0],
+            "edge_index": host["edge_index"],
+            "edge_attr": host["edge_attr"],
+            "degree": host["degree"],
+            "degree_stats": eng.decode_stats(host["stats"], host["hist"]),
         }
         if d_t is not None:
-            out["nbr_count"] = _host.to_host(g["nbr_count"])
+            out["nbr_count"] = host["nbr_count"]
         if symmetric_csr:
             s = eng.radius_graph(r, upper=False, compose=False, stats=False, want_dist32=True)
             out["row_ptr"] = _host.to_host(s["row_ptr"]).astype(np.int64)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include <cstdio>
 #include "pathgraph.h"
 
@@ -45,7 +46,33 @@ struct pg_handle {
   int32_t radius_flags = 0;
   cudaStream_t last_stream = nullptr;
   int32_t sm_count = 148;
+  // launch accounting / optional per-kernel CUDA-event timing (pg_profile_*)
+  int64_t launches = 0;
+  bool profiling = false;
+  struct prof_rec { const char* name; cudaEvent_t e0, e1; };
+  std::vector<prof_rec> prof;
 };
+
+// Brackets one kernel launch: counts it and, when profiling is on, records CUDA events on the
+// launching stream around it.
+struct pg_kernel_scope {
+  pg_handle* h; cudaStream_t s; bool on;
+  pg_kernel_scope(pg_handle* h_, cudaStream_t s_, const char* name) : h(h_), s(s_), on(h_->profiling) {
+    h->launches += 1;
+    if (on) {
+      pg_handle::prof_rec r; r.name = name;
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, s);
+      h->prof.push_back(r);
+    }
+  }
+  ~pg_kernel_scope() { if (on) cudaEventRecord(h->prof.back().e1, s); }
+};
+#define PG_LAUNCH(h, s, name, ...)              \
+  do {                                          \
+    pg_kernel_scope _pg_scope((h), (s), (name)); \
+    __VA_ARGS__;                                \
+  } while (0)
 
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max

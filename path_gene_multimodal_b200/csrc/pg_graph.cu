@@ -288,14 +288,14 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
   if ((rc = pg_reserve(h, h->row_count, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if (n > 0) {
     PG_CUDA(h, cudaMemsetAsync(h->sym_extra.p, 0, (size_t)n * sizeof(int32_t), s));
-    sym_mark_kernel<<<pg_div_up((int64_t)n * k, TPB), TPB, 0, s>>>(knn_idx, n, k, (uint8_t*)h->sym_recip.p,
-                                                                  (int32_t*)h->sym_extra.p);
-    sym_degree_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const uint8_t*)h->sym_recip.p, (const int32_t*)h->sym_extra.p,
-                                                       n, k, (int32_t*)h->sym_cursor.p, (int32_t*)h->row_count.p);
+    PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<<<pg_div_up((int64_t)n * k, TPB), TPB, 0, s>>>(knn_idx, n, k, (uint8_t*)h->sym_recip.p,
+                                                                  (int32_t*)h->sym_extra.p));
+    PG_LAUNCH(h, s, "sym_degree_kernel", sym_degree_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const uint8_t*)h->sym_recip.p, (const int32_t*)h->sym_extra.p,
+                                                       n, k, (int32_t*)h->sym_cursor.p, (int32_t*)h->row_count.p));
     PG_LAUNCH_CHECK(h);
   }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->row_count.p, und_row_ptr, n, s))) return rc;
-  copy_total_kernel<<<1, 1, 0, s>>>(und_row_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1);
+  PG_LAUNCH(h, s, "copy_total_kernel", copy_total_kernel<<<1, 1, 0, s>>>(und_row_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -332,13 +332,13 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
   if ((rc = pg_reserve(h, tw, ((size_t)total + 4) * sizeof(double)))) return rc;
   const int blocks_e = pg_div_up((int64_t)n * k, TPB);
   if (dist64)
-    sym_scatter_kernel<double><<<blocks_e, TPB, 0, s>>>(knn_idx, dist64, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
-                                                       (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p);
+    PG_LAUNCH(h, s, "sym_scatter_kernel<double>", sym_scatter_kernel<double><<<blocks_e, TPB, 0, s>>>(knn_idx, dist64, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
+                                                       (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
   else
-    sym_scatter_kernel<float><<<blocks_e, TPB, 0, s>>>(knn_idx, dist32, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
-                                                      (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p);
-  sym_sort_rows_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(und_row_ptr, n, (const int32_t*)tcol.p, (const double*)tw.p,
-                                                        und_col, und_w64, und_w32);
+    PG_LAUNCH(h, s, "sym_scatter_kernel<float>", sym_scatter_kernel<float><<<blocks_e, TPB, 0, s>>>(knn_idx, dist32, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
+                                                      (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
+  PG_LAUNCH(h, s, "sym_sort_rows_kernel", sym_sort_rows_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(und_row_ptr, n, (const int32_t*)tcol.p, (const double*)tw.p,
+                                                        und_col, und_w64, und_w32));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -353,11 +353,11 @@ int pg_csr_upper_count(pg_handle* h, int32_t n, const int32_t* row_ptr, const in
   int rc;
   if ((rc = pg_reserve(h, h->row_count, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if (n > 0) {
-    upper_count_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, row_id, n, (int32_t*)h->row_count.p);
+    PG_LAUNCH(h, s, "upper_count_kernel", upper_count_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, row_id, n, (int32_t*)h->row_count.p));
     PG_LAUNCH_CHECK(h);
   }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->row_count.p, up_ptr, n, s))) return rc;
-  copy_total_kernel<<<1, 1, 0, s>>>(up_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 2);
+  PG_LAUNCH(h, s, "copy_total_kernel", copy_total_kernel<<<1, 1, 0, s>>>(up_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 2));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -382,8 +382,8 @@ int pg_csr_upper_fill(pg_handle* h, int32_t n, const int32_t* row_ptr, const int
   PG_REQUIRE(h, n >= 0 && row_ptr && up_ptr, "pg_csr_upper_fill: bad argument");
   PG_REQUIRE(h, !(ew64 || ew32) || (w64 || w32), "pg_csr_upper_fill: weights requested but none given");
   if (n == 0) return PG_OK;
-  upper_fill_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, w64, w32, row_id, up_ptr, n, (long long*)edges_i64,
-                                                     ew64, ew32);
+  PG_LAUNCH(h, s, "upper_fill_kernel", upper_fill_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, w64, w32, row_id, up_ptr, n, (long long*)edges_i64,
+                                                     ew64, ew32));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -399,17 +399,17 @@ int pg_compose_degree(pg_handle* h, int32_t n, const int32_t* row_ptr, const int
   PG_REQUIRE(h, !nbr_count || (type && col && n_types >= 1 && n_types <= PG_MAX_TYPES),
              "pg_compose_degree: nbr_count needs type, col and 1 <= n_types <= %d", PG_MAX_TYPES);
   PG_REQUIRE(h, !hist || hist_len >= 1, "pg_compose_degree: hist_len must be >= 1");
-  if (stats) init_stats_kernel<<<1, 1, 0, s>>>(stats);
+  if (stats) PG_LAUNCH(h, s, "init_stats_kernel", init_stats_kernel<<<1, 1, 0, s>>>(stats));
   if (hist) PG_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)hist_len * sizeof(int32_t), s));
   if (n > 0) {
     const size_t smem = (hist && hist_len <= HIST_SMEM_MAX) ? (size_t)hist_len * sizeof(int) : 0;
     if (!nbr_count || n_types <= 8)
-      compose_kernel<8><<<pg_div_up(n, TPB), TPB, smem, s>>>(row_ptr, col, type, n, n_types, nbr_count, degree, stats, hist, hist_len);
+      PG_LAUNCH(h, s, "compose_kernel<8>", compose_kernel<8><<<pg_div_up(n, TPB), TPB, smem, s>>>(row_ptr, col, type, n, n_types, nbr_count, degree, stats, hist, hist_len));
     else
-      compose_kernel<16><<<pg_div_up(n, TPB), TPB, smem, s>>>(row_ptr, col, type, n, n_types, nbr_count, degree, stats, hist, hist_len);
+      PG_LAUNCH(h, s, "compose_kernel<16>", compose_kernel<16><<<pg_div_up(n, TPB), TPB, smem, s>>>(row_ptr, col, type, n, n_types, nbr_count, degree, stats, hist, hist_len));
     PG_LAUNCH_CHECK(h);
   }
-  if (stats) finish_stats_kernel<<<1, 1, 0, s>>>(stats);
+  if (stats) PG_LAUNCH(h, s, "finish_stats_kernel", finish_stats_kernel<<<1, 1, 0, s>>>(stats));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -424,8 +424,8 @@ int pg_halo_pack(pg_handle* h, int32_t n, const double* xy, const int32_t* type,
   PG_REQUIRE(h, n >= 0 && capacity >= 0 && count_out && (capacity == 0 || out), "pg_halo_pack: bad argument");
   PG_CUDA(h, cudaMemsetAsync(count_out, 0, sizeof(int32_t), s));
   if (n > 0) {
-    halo_pack_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, lo_edge, hi_edge, out, capacity,
-                                                      count_out, (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW));
+    PG_LAUNCH(h, s, "halo_pack_kernel", halo_pack_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, lo_edge, hi_edge, out, capacity,
+                                                      count_out, (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW)));
     PG_LAUNCH_CHECK(h);
   }
   return PG_OK;
@@ -441,9 +441,9 @@ int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_
   PG_REQUIRE(h, n_recs >= 0 && n_base >= 0 && capacity >= n_base && count_out && xy, "pg_halo_unpack: bad argument");
   PG_CUDA(h, cudaMemsetAsync(count_out, 0, sizeof(int32_t), s));
   if (n_recs > 0) {
-    halo_unpack_kernel<<<pg_div_up(n_recs, TPB), TPB, 0, s>>>(recs, n_recs, skip_begin, skip_end, x_lo, x_hi, (double2*)xy,
+    PG_LAUNCH(h, s, "halo_unpack_kernel", halo_unpack_kernel<<<pg_div_up(n_recs, TPB), TPB, 0, s>>>(recs, n_recs, skip_begin, skip_end, x_lo, x_hi, (double2*)xy,
                                                              type, gid, n_base, capacity, count_out,
-                                                             (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW));
+                                                             (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW)));
     PG_LAUNCH_CHECK(h);
   }
   return PG_OK;

@@ -93,9 +93,9 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
                       b[2] >= b[0] && b[3] >= b[1], "pg_grid_build: bad bounds");
   } else if (n > 0) {
     unsigned long long* keys = (unsigned long long*)((char*)h->misc.p + PG_MISC_BOUNDS);
-    init_bounds_kernel<<<1, 1, 0, s>>>(keys);
+    PG_LAUNCH(h, s, "init_bounds_kernel", init_bounds_kernel<<<1, 1, 0, s>>>(keys));
     int blocks = std::min(pg_div_up(n, TPB), h->sm_count * 8);
-    bounds_kernel<<<blocks, TPB, 0, s>>>((const double2*)xy, n, keys);
+    PG_LAUNCH(h, s, "bounds_kernel", bounds_kernel<<<blocks, TPB, 0, s>>>((const double2*)xy, n, keys));
     PG_LAUNCH_CHECK(h);
     unsigned long long hk[4];
     PG_CUDA(h, cudaMemcpyAsync(hk, keys, sizeof(hk), cudaMemcpyDeviceToHost, s));
@@ -133,16 +133,16 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
 
   PG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, (cells + 1) * sizeof(int32_t), s));
   if (n > 0) {
-    histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny,
+    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny,
                                                       (int32_t*)h->cell_count.p, (int32_t*)h->cell_of.p,
-                                                      (int32_t*)h->rank.p);
+                                                      (int32_t*)h->rank.p));
     PG_LAUNCH_CHECK(h);
   }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, (int32_t*)h->cell_start.p, (int32_t)cells, s))) return rc;
   if (n > 0) {
-    scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, (const int32_t*)h->cell_start.p,
+    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, (const int32_t*)h->cell_start.p,
                                                     (const int32_t*)h->cell_of.p, (const int32_t*)h->rank.p,
-                                                    (double2*)h->s_xy.p, (int4*)h->s_meta.p);
+                                                    (double2*)h->s_xy.p, (int4*)h->s_meta.p));
     PG_LAUNCH_CHECK(h);
   }
   g.built = true;

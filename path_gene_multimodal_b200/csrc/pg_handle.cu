@@ -39,6 +39,11 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes) {
   return PG_OK;
 }
 
+static void pg_profile_clear(pg_handle* h) {
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  h->prof.clear();
+}
+
 extern "C" {
 
 int pg_version(void) { return 100; }
@@ -102,6 +107,7 @@ int pg_destroy(pg_handle* h) {
   for (pg_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->pinned) cudaFreeHost(h->pinned);
+  pg_profile_clear(h);
   delete h;
   return PG_OK;
 }
@@ -115,6 +121,31 @@ int64_t pg_workspace_bytes(pg_handle* h) {
   int64_t t = 0;
   for (pg_buf* b : bufs) t += (int64_t)b->cap;
   return t;
+}
+
+int64_t pg_launch_count(pg_handle* h) { return h ? h->launches : 0; }
+
+int pg_profile_enable(pg_handle* h, int on) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaDeviceSynchronize());
+  pg_profile_clear(h);
+  h->profiling = on != 0;
+  return PG_OK;
+}
+
+int pg_profile_count(pg_handle* h) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaDeviceSynchronize());
+  return (int)h->prof.size();
+}
+
+int pg_profile_get(pg_handle* h, int i, const char** name, float* ms) {
+  if (!h || i < 0 || i >= (int)h->prof.size()) return PG_ERR_INVALID;
+  if (name) *name = h->prof[i].name;
+  if (ms) PG_CUDA(h, cudaEventElapsedTime(ms, h->prof[i].e0, h->prof[i].e1));
+  return PG_OK;
 }
 
 int pg_check_overflow(pg_handle* h) {

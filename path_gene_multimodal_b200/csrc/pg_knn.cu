@@ -127,15 +127,15 @@ extern "C" int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64,
   PG_REQUIRE(h, k >= 1 && k <= PG_MAX_K, "pg_knn: k must be in 1..%d (got %d)", PG_MAX_K, k);
   PG_REQUIRE(h, k < gr.n, "pg_knn: k (%d) must be smaller than the number of points (%d)", k, gr.n);
   PG_REQUIRE(h, knn_idx != nullptr, "pg_knn: knn_idx is NULL");
-  if (halo_ok) { set_flag_kernel<<<1, 1, 0, s>>>(halo_ok, 1); }
+  if (halo_ok) { PG_LAUNCH(h, s, "set_flag_kernel", set_flag_kernel<<<1, 1, 0, s>>>(halo_ok, 1)); }
   if (gr.n_query == 0) return PG_OK;
   pg_grid_view v = pg_make_view(h);
   const int blocks = pg_div_up(gr.n, TPB);
-  if (k <= 4) knn_kernel<4><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok);
-  else if (k <= 8) knn_kernel<8><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok);
-  else if (k <= 16) knn_kernel<16><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok);
-  else if (k <= 32) knn_kernel<32><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok);
-  else knn_kernel<64><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok);
+  if (k <= 4) PG_LAUNCH(h, s, "knn_kernel<4>", knn_kernel<4><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
+  else if (k <= 8) PG_LAUNCH(h, s, "knn_kernel<8>", knn_kernel<8><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
+  else if (k <= 16) PG_LAUNCH(h, s, "knn_kernel<16>", knn_kernel<16><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
+  else if (k <= 32) PG_LAUNCH(h, s, "knn_kernel<32>", knn_kernel<32><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
+  else PG_LAUNCH(h, s, "knn_kernel<64>", knn_kernel<64><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

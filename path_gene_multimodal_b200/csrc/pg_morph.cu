@@ -190,13 +190,13 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   const bool extra = o.major_axis || o.minor_axis || o.centroid_x || o.centroid_y || o.poly_bbox;
   const int blocks = pg_div_up(n, TPB);  // 32 polygons per warp, 8 warps per CTA
   if (extra)
-    map_morph_kernel<T, true><<<blocks, TPB, 0, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,
+    PG_LAUNCH(h, s, "map_morph_kernel<T, true>", map_morph_kernel<T, true><<<blocks, TPB, 0, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,
                                                      (const double2*)centroid, (const int4*)bbox, (V2*)wsi_poly_xy,
-                                                     (double2*)wsi_centroid, (int4*)wsi_bbox, o);
+                                                     (double2*)wsi_centroid, (int4*)wsi_bbox, o));
   else
-    map_morph_kernel<T, false><<<blocks, TPB, 0, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,
+    PG_LAUNCH(h, s, "map_morph_kernel<T, false>", map_morph_kernel<T, false><<<blocks, TPB, 0, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,
                                                       (const double2*)centroid, (const int4*)bbox, (V2*)wsi_poly_xy,
-                                                      (double2*)wsi_centroid, (int4*)wsi_bbox, o);
+                                                      (double2*)wsi_centroid, (int4*)wsi_bbox, o));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

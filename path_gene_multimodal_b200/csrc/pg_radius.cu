@@ -135,7 +135,8 @@ radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __rest
 __global__ void __launch_bounds__(TPB)
 radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* __restrict__ row_ptr,
                    int32_t* __restrict__ col, float* __restrict__ dist32, double* __restrict__ dist64,
-                   long long* __restrict__ edges, long long capacity, int32_t* overflow) {
+                   long long* __restrict__ edges, long long* __restrict__ edge_index,
+                   float* __restrict__ edge_attr, long long n_edges, long long capacity, int32_t* overflow) {
   const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= g.n) return;
   const int4 me = g.s_meta[p];
@@ -167,6 +168,11 @@ radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* _
       if (dist32) dist32[o] = (float)d;
       if (dist64) dist64[o] = d;
       if (edges) { edges[2 * o] = me.y; edges[2 * o + 1] = buf.key[t]; }
+      if (edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
+        edge_index[o] = me.y; edge_index[n_edges + o] = buf.key[t];
+        edge_index[2 * n_edges + o] = buf.key[t]; edge_index[3 * n_edges + o] = me.y;
+      }
+      if (edge_attr) { edge_attr[o] = (float)d; edge_attr[n_edges + o] = (float)d; }  // ipynb:3041-3042
     }
     emitted += buf.m;
     last = buf.key[buf.m - 1];
@@ -202,7 +208,7 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   if (R < 1) R = 1;
   h->radius_r = r;
   h->radius_flags = flags;
-  if (stats) { init_stats_kernel<<<1, 1, 0, s>>>(stats); }
+  if (stats) { PG_LAUNCH(h, s, "init_stats_kernel", init_stats_kernel<<<1, 1, 0, s>>>(stats)); }
   if (hist) PG_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)hist_len * sizeof(int32_t), s));
   // ghost rows never write their count: clear so the scan sees zeros (n_query rows only are scanned)
   if (gr.n > 0 && nq > 0) {
@@ -212,16 +218,16 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
     const size_t smem = (hist && hist_len <= HIST_SMEM_MAX) ? (size_t)hist_len * sizeof(int) : 0;
     const int upper = flags == PG_RADIUS_UPPER;
     if (!nbr_count || n_types <= 8)
-      radius_count_kernel<8><<<blocks, TPB, smem, s>>>(v, r2, R, upper, (int32_t*)h->row_count.p, degree, nbr_count,
-                                                      n_types, stats, hist, hist_len);
+      PG_LAUNCH(h, s, "radius_count_kernel<8>", radius_count_kernel<8><<<blocks, TPB, smem, s>>>(v, r2, R, upper, (int32_t*)h->row_count.p, degree, nbr_count,
+                                                      n_types, stats, hist, hist_len));
     else
-      radius_count_kernel<16><<<blocks, TPB, smem, s>>>(v, r2, R, upper, (int32_t*)h->row_count.p, degree, nbr_count,
-                                                       n_types, stats, hist, hist_len);
+      PG_LAUNCH(h, s, "radius_count_kernel<16>", radius_count_kernel<16><<<blocks, TPB, smem, s>>>(v, r2, R, upper, (int32_t*)h->row_count.p, degree, nbr_count,
+                                                       n_types, stats, hist, hist_len));
     PG_LAUNCH_CHECK(h);
   }
-  if (stats) { finish_stats_kernel<<<1, 1, 0, s>>>(stats); }
+  if (stats) { PG_LAUNCH(h, s, "finish_stats_kernel", finish_stats_kernel<<<1, 1, 0, s>>>(stats)); }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->row_count.p, row_ptr, nq, s))) return rc;
-  copy_total_kernel<<<1, 1, 0, s>>>(row_ptr + nq, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS));
+  PG_LAUNCH(h, s, "copy_total_kernel", copy_total_kernel<<<1, 1, 0, s>>>(row_ptr + nq, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS)));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -237,7 +243,8 @@ int pg_radius_total(pg_handle* h, int64_t* total) {
 }
 
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
-                   int64_t* edges_i64, int64_t capacity, pg_stream stream) {
+                   int64_t* edges_i64, int64_t* edge_index, float* edge_attr, int64_t n_edges,
+                   int64_t capacity, pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
@@ -246,6 +253,8 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   PG_REQUIRE(h, row_ptr != nullptr, "pg_radius_fill: row_ptr is NULL");
   PG_REQUIRE(h, capacity >= 0, "pg_radius_fill: capacity < 0");
   PG_REQUIRE(h, capacity == 0 || col != nullptr, "pg_radius_fill: col is NULL");
+  PG_REQUIRE(h, !(edge_index || edge_attr) || (h->radius_flags == PG_RADIUS_UPPER && n_edges >= 0 && n_edges <= capacity),
+             "pg_radius_fill: edge_index / edge_attr need the UPPER count pass and 0 <= n_edges <= capacity");
   const pg_grid& gr = h->grid;
   if (gr.n == 0 || gr.n_query == 0 || capacity == 0) {
     // an empty buffer is only fine for an empty result: let the kernel flag rows it cannot place
@@ -254,9 +263,10 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   int R = (int)std::ceil(h->radius_r * gr.inv_cell * (1.0 + 1e-9) + 1e-9);
   if (R < 1) R = 1;
   pg_grid_view v = pg_make_view(h);
-  radius_fill_kernel<<<pg_div_up(gr.n, TPB), TPB, 0, s>>>(
+  PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<<<pg_div_up(gr.n, TPB), TPB, 0, s>>>(
       v, h->radius_r * h->radius_r, R, h->radius_flags == PG_RADIUS_UPPER, row_ptr, col, dist32, dist64,
-      (long long*)edges_i64, (long long)capacity, (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW));
+      (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges, (long long)capacity,
+      (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW)));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

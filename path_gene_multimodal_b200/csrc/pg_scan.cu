@@ -126,7 +126,7 @@ __global__ void scan_empty_kernel(int32_t* out) { out[0] = 0; }
 int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s) {
   if (n < 0) return pg_set_error(h, PG_ERR_INVALID, "scan: n < 0");
   if (n == 0) {
-    scan_empty_kernel<<<1, 1, 0, s>>>(out);
+    PG_LAUNCH(h, s, "scan_empty_kernel", scan_empty_kernel<<<1, 1, 0, s>>>(out));
     PG_LAUNCH_CHECK(h);
     return PG_OK;
   }
@@ -146,7 +146,7 @@ int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaSt
   }
   unsigned int* ticket = (unsigned int*)h->scan_state.p;
   uint64_t* desc = (uint64_t*)((char*)h->scan_state.p + 256);
-  scan_lookback_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, desc, ticket, h->scan_epoch, num_tiles);
+  PG_LAUNCH(h, s, "scan_lookback_kernel", scan_lookback_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, desc, ticket, h->scan_epoch, num_tiles));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

@@ -49,7 +49,6 @@ class Engine:
         if rc != 0:
             raise PathGraphError(rc, (self.lib.pg_last_error(None) or b"").decode())
         self._h = h
-        self.launches = 0  # kernels launched through this engine (bench.py's gpu_launches claim)
 
     # ---- plumbing ----------------------------------------------------------------------------
     def close(self):
@@ -84,6 +83,25 @@ class Engine:
     def _empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    @property
+    def launches(self) -> int:
+        """Kernels launched through this handle so far (counted inside the library)."""
+        return int(self.lib.pg_launch_count(self._h))
+
+    def profile(self, on: bool = True):
+        """Start / stop per-kernel CUDA-event timing inside the library (clears earlier records)."""
+        self._check(self.lib.pg_profile_enable(self._h, 1 if on else 0))
+
+    def profile_records(self) -> list[tuple[str, float]]:
+        """[(kernel name, milliseconds)] for every launch since profile(True); synchronises."""
+        n = self.lib.pg_profile_count(self._h)
+        out = []
+        name, ms = C.c_char_p(), C.c_float()
+        for i in range(n):
+            self._check(self.lib.pg_profile_get(self._h, i, C.byref(name), C.byref(ms)))
+            out.append((name.value.decode(), float(ms.value)))
+        return out
+
     def workspace_bytes(self) -> int:
         return int(self.lib.pg_workspace_bytes(self._h))
 
@@ -93,8 +111,8 @@ class Engine:
     @staticmethod
     def decode_stats(stats_t: torch.Tensor, hist: torch.Tensor | None = None) -> dict:
         """pg_degree_stats block (4 x int64 on the device) -> python dict (one D2H copy)."""
-        raw = stats_t.cpu().numpy().view(np.int32)
-        s = stats_t.cpu().numpy()
+        s = stats_t.cpu().numpy() if isinstance(stats_t, torch.Tensor) else np.asarray(stats_t)
+        raw = s.view(np.int32)
         n = int(s[3])
         tot, sq = int(s[1]), int(s[2])
         mean = tot / n if n else float("nan")
@@ -102,7 +120,7 @@ class Engine:
         out = {"min": int(raw[0]), "max": int(raw[1]), "sum": tot, "sumsq": sq, "n": n,
                "mean": mean, "std": math.sqrt(var) if n else float("nan")}
         if hist is not None:
-            out["hist"] = hist.cpu().numpy().astype(np.int64)
+            out["hist"] = (hist.cpu().numpy() if isinstance(hist, torch.Tensor) else np.asarray(hist)).astype(np.int64)
         return out
 
     # ---- K1 ------------------------------------------------------------------------------------
@@ -149,7 +167,6 @@ class Engine:
                        self._p(bbox, torch.int32, "bbox"), self._p(wsi_poly, vt, "wsi_poly_xy"),
                        self._p(wsi_c, torch.float64, "wsi_centroid"), self._p(wsi_b, torch.int32, "wsi_bbox"),
                        C.byref(mo), self._stream()))
-        self.launches += 1 if n > 0 else 0
         return res
 
     # ---- K2-K4 ---------------------------------------------------------------------------------
@@ -164,7 +181,6 @@ class Engine:
                                            self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
                                            float(cell_size), b, self._stream()))
         self._n, self._nq = n, nq
-        self.launches += (3 if n > 0 else 1) + (2 if (bounds is None and n > 0) else 0)
 
     def grid_info(self) -> dict:
         nx, ny = C.c_int32(), C.c_int32()
@@ -197,18 +213,19 @@ class Engine:
         self._check(self.lib.pg_knn(self._h, int(k), self._p(idx, torch.int32, "knn_idx"),
                                     self._p(d64, torch.float64, "dist64"), self._p(d32, torch.float32, "dist32"),
                                     float(x_lo), float(x_hi), self._p(ok, torch.int32, "halo_ok"), self._stream()))
-        self.launches += 1 + (1 if check_halo else 0)
         res["dist"] = d64 if dist_dtype == torch.float64 else d32
         return res
 
     # ---- K6 + fused K8 ---------------------------------------------------------------------------
     def radius_graph(self, r, upper=False, n_types=5, compose=True, stats=True, hist_len=64, want_dist32=True,
-                     want_dist64=False, want_edges=False, capacity=None, out=None):
+                     want_dist64=False, want_edges=False, want_edge_index=False, capacity=None, out=None):
         """Radius graph over the built grid: count (+composition / degree) -> scan -> fill.
 
         With ``capacity`` (entries) the whole sequence is enqueued without a host sync and the
         returned col / dist tensors have ``capacity`` rows (valid prefix = row_ptr[-1]); call
         ``check_overflow()`` later.  Without it the total is read back and outputs are exact-size.
+        ``want_edge_index`` (needs ``upper`` and the exact total) adds the notebook's packed tensors
+        ``edge_index`` int64 [2,2E] and ``edge_attr`` float32 [2E,1], written by the fill kernel.
         """
         nq = self._nq
         res = dict(out) if out else {}
@@ -229,7 +246,6 @@ class Engine:
                                              self._p(nbr, torch.int32, "nbr_count"), int(n_types),
                                              self._p(st, torch.int64, "stats"), self._p(hist, torch.int32, "hist"),
                                              int(hist_len) if hist is not None else 0, self._stream()))
-        self.launches += 3 + (2 if stats else 0)
         if capacity is None:
             total = C.c_int64()
             self._check(self.lib.pg_radius_total(self._h, C.byref(total)))
@@ -241,11 +257,17 @@ class Engine:
         d32 = get("dist32", (cap,), torch.float32) if want_dist32 else None
         d64 = get("dist64", (cap,), torch.float64) if want_dist64 else None
         edges = get("edges", (cap, 2), torch.int64) if want_edges else None
+        ei = ea = None
+        if want_edge_index:
+            if capacity is not None or not upper:
+                raise ValueError("want_edge_index needs upper=True and no capacity (exact total)")
+            ei = get("edge_index", (2, 2 * cap), torch.int64)
+            ea = get("edge_attr", (2 * cap, 1), torch.float32)
         self._check(self.lib.pg_radius_fill(self._h, self._p(row_ptr, torch.int32, "row_ptr"),
                                             self._p(col, torch.int32, "col"), self._p(d32, torch.float32, "dist32"),
                                             self._p(d64, torch.float64, "dist64"), self._p(edges, torch.int64, "edges"),
-                                            cap, self._stream()))
-        self.launches += 1
+                                            self._p(ei, torch.int64, "edge_index"), self._p(ea, torch.float32, "edge_attr"),
+                                            cap if want_edge_index else 0, cap, self._stream()))
         return res
 
     # ---- K7 ------------------------------------------------------------------------------------
@@ -268,7 +290,6 @@ class Engine:
             None if is64 else self._p(knn_dist, torch.float32, "dist32"),
             self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
             self._p(w64, torch.float64, "w64"), self._p(w32, torch.float32, "w32"), self._stream()))
-        self.launches += 6 if n > 0 else 2
         return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}
 
     def csr_upper(self, row_ptr, col, w=None, row_id=None, want_w32=False):
@@ -296,7 +317,6 @@ class Engine:
             self._p(row_id, torch.int32, "row_id"), self._p(up_ptr, torch.int32, "up_ptr"),
             self._p(edges, torch.int64, "edges"), self._p(ew64, torch.float64, "ew64"),
             self._p(ew32, torch.float32, "ew32"), self._stream()))
-        self.launches += 4 if n > 0 else 2
         return {"edges": edges, "w64": ew64, "w32": ew32, "up_ptr": up_ptr}
 
     # ---- K8 ------------------------------------------------------------------------------------
@@ -311,7 +331,6 @@ class Engine:
             self._p(types, torch.int32, "types"), int(n_types), self._p(nbr, torch.int32, "nbr_count"),
             self._p(degree, torch.int32, "degree"), self._p(st, torch.int64, "stats"),
             self._p(hist, torch.int32, "hist"), int(hist_len) if hist is not None else 0, self._stream()))
-        self.launches += 3 if n > 0 else 2
         return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
 
     # ---- K9 ------------------------------------------------------------------------------------
@@ -324,7 +343,6 @@ class Engine:
                                           self._p(gid, torch.int32, "gid"), float(lo_edge), float(hi_edge),
                                           C.c_void_p(recs.data_ptr()), int(capacity), self._p(count, torch.int32, "count"),
                                           self._stream()))
-        self.launches += 1 if n > 0 else 0
         return recs, count
 
     def halo_unpack(self, recs, n_recs, skip_begin, skip_end, x_lo, x_hi, xy, types, gid, n_base):
@@ -333,7 +351,6 @@ class Engine:
                                             float(x_lo), float(x_hi), self._p(xy, torch.float64, "xy"),
                                             self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
                                             int(n_base), int(xy.shape[0]), self._p(count, torch.int32, "count"), self._stream()))
-        self.launches += 1 if n_recs > 0 else 0
         return count
 
     def exclusive_scan(self, x):
@@ -341,7 +358,6 @@ class Engine:
         out = self._empty((n + 1,), torch.int32)
         self._check(self.lib.pg_exclusive_scan_i32(self._h, self._p(x, torch.int32, "in"), self._p(out, torch.int32, "out"),
                                                    n, self._stream()))
-        self.launches += 1
         return out
 
 
