@@ -1,0 +1,49 @@
+"""Short driver for `ncu --set full`: each hot-path kernel a few times at its bench shape (C2 radius pipeline
+on 1M nuclei, C3 map+morphology on 2M x 32, kNN k=8 on 1M). Not a benchmark - nothing printed here is a result."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from path_gene_multimodal_b200 import synth  # noqa: E402
+from path_gene_multimodal_b200.engine import default_knn_cell, get_engine, radius_cell  # noqa: E402
+
+eng = get_engine(0)
+dev = torch.device("cuda", 0)
+n = 1_000_000
+xy, ty, side = synth.make_points(n, synth.SEEDS["C2"])
+d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+bounds = (0.0, 0.0, float(side), float(side))
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+out = {}
+for _ in range(reps):
+    flush.zero_()
+    eng.grid_build(d_xy, d_ty, None, radius_cell(50.0), bounds)
+    out = eng.radius_graph(50.0, upper=True, want_dist32=True, want_edges=True, capacity=2_000_000, out=out)
+kres = {}
+for _ in range(reps):
+    flush.zero_()
+    eng.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, 8), bounds)
+    kres = eng.knn(8, dist_dtype=torch.float32, out=kres)
+sym = eng.symmetrize(kres["knn_idx"], kres["dist32"])
+eng.compose_degree(sym["row_ptr"], sym["col"], d_ty, 5)
+n3 = 2_000_000
+off, pxy = synth.make_polygons(n3, synth.SEEDS["C3"], v_fixed=32)
+rng = np.random.default_rng(3)
+t = 73
+tile_x = torch.from_numpy(((np.arange(t * t) % t) * 508).astype(np.int32)).to(dev)
+tile_y = torch.from_numpy(((np.arange(t * t) // t) * 508).astype(np.int32)).to(dev)
+nuc_tile = torch.from_numpy(rng.integers(0, t * t, size=n3).astype(np.int32)).to(dev)
+cen = torch.from_numpy(rng.random((n3, 2)) * 508).to(dev)
+bb = torch.from_numpy(rng.integers(0, 508, size=(n3, 4)).astype(np.int32)).to(dev)
+d_off, d_p = torch.from_numpy(off).to(dev), torch.from_numpy(pxy).to(dev)
+res = {}
+for _ in range(reps):
+    flush.zero_()
+    res = eng.map_morph(d_off, d_p, nuc_tile, tile_x, tile_y, cen, bb, write_polygons=True, out=res)
+torch.cuda.synchronize()
+eng.check_overflow()
+print("capture ok", eng.launches)
