@@ -144,13 +144,18 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
 int pg_check_overflow(pg_handle* h);
 
 /* ---- K7: undirected union of the directed kNN lists; nx.Graph loop of ipynb:1865-1894.
- * count: und_row_ptr int32 [N+1]; fill: und_col ascending per row, weights = min over directions. */
+ * count: und_row_ptr int32 [N+1]; fill: und_col ascending per row, weights = min over directions.
+ * The lists hold ids; for a whole slide ids are row numbers (row_id = id_map = NULL). For a strip +
+ * halo, row_id int32 [n] gives the (global) id of each row and id_map int32 [n_ids] the row of an
+ * id (-1 = not present); neighbours without a row only contribute their forward entry. */
 int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx,
+                            const int32_t* row_id, const int32_t* id_map, int32_t n_ids,
                             int32_t* und_row_ptr, pg_stream stream);
 int pg_knn_symmetrize_total(pg_handle* h, int64_t* total);
 int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx,
-                           const double* dist64, const float* dist32, const int32_t* und_row_ptr,
-                           int32_t* und_col, double* und_w64, float* und_w32, pg_stream stream);
+                           const double* dist64, const float* dist32, const int32_t* row_id,
+                           const int32_t* id_map, const int32_t* und_row_ptr, int32_t* und_col,
+                           double* und_w64, float* und_w32, pg_stream stream);
 
 /* ---- symmetric CSR (rows ascending by column) -> `edges` (i<j) list; ipynb:2969-2975 / G.edges of
  * ipynb:1894.  row_id int32 [n] = id of each row in column space (NULL = identity; set for strips). */

@@ -12,18 +12,24 @@ constexpr uint8_t RECIP_INVALID = 255, RECIP_NONE = 254;
 
 // pass A: one thread per directed edge i->j. Records the slot of i inside j's list (or NONE) and
 // counts, per node, the reverse-only edges it will receive.
+// Lists hold ids in "column space" (global ids when the rows are a strip + halo of a larger slide):
+// row_id[i] is the id of row i, id_map[id] the row of an id (-1 / >= n: no row here). NULL = identity.
 __global__ void __launch_bounds__(TPB)
-sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k, uint8_t* __restrict__ recip,
+sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k, const int32_t* __restrict__ row_id,
+                const int32_t* __restrict__ id_map, int n_ids, uint8_t* __restrict__ recip,
                 int32_t* __restrict__ extra) {
   const int64_t e = (int64_t)blockIdx.x * TPB + threadIdx.x;
   if (e >= (int64_t)n * k) return;
   const int i = (int)(e / k);
-  const int j = knn_idx[e];
-  if (j < 0 || j >= n || j == i) { recip[e] = RECIP_INVALID; return; }
+  const int my_id = row_id ? row_id[i] : i;
+  const int jid = knn_idx[e];
+  if (jid < 0 || jid == my_id || (id_map && jid >= n_ids) || (!id_map && jid >= n)) { recip[e] = RECIP_INVALID; return; }
+  const int j = id_map ? id_map[jid] : jid;
+  if (j < 0 || j >= n) { recip[e] = RECIP_NONE; return; }  // neighbour has no row here: own entry only
   const int32_t* row = knn_idx + (int64_t)j * k;
   int found = RECIP_NONE;
   for (int s = 0; s < k; ++s)
-    if (row[s] == i) { found = s; break; }
+    if (row[s] == my_id) { found = s; break; }
   recip[e] = (uint8_t)found;
   if (found == RECIP_NONE) atomicAdd(&extra[j], 1);
 }
@@ -43,6 +49,7 @@ sym_degree_kernel(const uint8_t* __restrict__ recip, const int32_t* __restrict__
 template <class DT>
 __global__ void __launch_bounds__(TPB)
 sym_scatter_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k,
+                   const int32_t* __restrict__ row_id, const int32_t* __restrict__ id_map,
                    const uint8_t* __restrict__ recip, const int32_t* __restrict__ row_ptr,
                    int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_col, double* __restrict__ tmp_w) {
   const int64_t e = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -50,17 +57,18 @@ sym_scatter_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ d
   const uint8_t rc = recip[e];
   if (rc == RECIP_INVALID) return;
   const int i = (int)(e / k), slot = (int)(e - (int64_t)i * k);
-  const int j = knn_idx[e];
+  const int jid = knn_idx[e];
+  const int j = id_map ? id_map[jid] : jid;
   double w = (double)dist[e];
   if (rc != RECIP_NONE) w = fmin(w, (double)dist[(int64_t)j * k + rc]);  // weight = min over directions
   int own_rank = 0;
   for (int s = 0; s < slot; ++s) own_rank += recip[(int64_t)i * k + s] != RECIP_INVALID;
   const int64_t o = (int64_t)row_ptr[i] + own_rank;
-  tmp_col[o] = j;
+  tmp_col[o] = jid;
   tmp_w[o] = w;
-  if (rc == RECIP_NONE) {
+  if (rc == RECIP_NONE && j >= 0 && j < n) {
     const int64_t r = (int64_t)row_ptr[j] + atomicAdd(&cursor[j], 1);
-    tmp_col[r] = i;
+    tmp_col[r] = row_id ? row_id[i] : i;
     tmp_w[r] = w;
   }
 }
@@ -272,8 +280,8 @@ halo_unpack_kernel(const pg_halo_rec* __restrict__ recs, int n_recs, int skip_be
 
 extern "C" {
 
-int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx,
-                            int32_t* und_row_ptr, pg_stream stream) {
+int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
+                            const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
@@ -281,6 +289,8 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
   PG_REQUIRE(h, n >= 0 && k >= 1 && k <= PG_MAX_K, "pg_knn_symmetrize_count: need n >= 0 and 1 <= k <= %d", PG_MAX_K);
   PG_REQUIRE(h, und_row_ptr != nullptr && (n == 0 || knn_idx != nullptr), "pg_knn_symmetrize_count: NULL argument");
   PG_REQUIRE(h, (int64_t)n * k < (int64_t)1 << 31, "pg_knn_symmetrize_count: n*k must be < 2^31");
+  PG_REQUIRE(h, (row_id == nullptr) == (id_map == nullptr) && (!id_map || n_ids > 0),
+             "pg_knn_symmetrize_count: row_id and id_map go together (both NULL = identity)");
   int rc;
   if ((rc = pg_reserve(h, h->sym_extra, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if ((rc = pg_reserve(h, h->sym_cursor, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
@@ -288,7 +298,7 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
   if ((rc = pg_reserve(h, h->row_count, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if (n > 0) {
     PG_CUDA(h, cudaMemsetAsync(h->sym_extra.p, 0, (size_t)n * sizeof(int32_t), s));
-    PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<<<pg_div_up((int64_t)n * k, TPB), TPB, 0, s>>>(knn_idx, n, k, (uint8_t*)h->sym_recip.p,
+    PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<<<pg_div_up((int64_t)n * k, TPB), TPB, 0, s>>>(knn_idx, n, k, row_id, id_map, n_ids, (uint8_t*)h->sym_recip.p,
                                                                   (int32_t*)h->sym_extra.p));
     PG_LAUNCH(h, s, "sym_degree_kernel", sym_degree_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const uint8_t*)h->sym_recip.p, (const int32_t*)h->sym_extra.p,
                                                        n, k, (int32_t*)h->sym_cursor.p, (int32_t*)h->row_count.p));
@@ -311,8 +321,9 @@ int pg_knn_symmetrize_total(pg_handle* h, int64_t* total) {
 }
 
 int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const double* dist64,
-                           const float* dist32, const int32_t* und_row_ptr, int32_t* und_col, double* und_w64,
-                           float* und_w32, pg_stream stream) {
+                           const float* dist32, const int32_t* row_id, const int32_t* id_map,
+                           const int32_t* und_row_ptr, int32_t* und_col, double* und_w64, float* und_w32,
+                           pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
@@ -332,10 +343,10 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
   if ((rc = pg_reserve(h, tw, ((size_t)total + 4) * sizeof(double)))) return rc;
   const int blocks_e = pg_div_up((int64_t)n * k, TPB);
   if (dist64)
-    PG_LAUNCH(h, s, "sym_scatter_kernel<double>", sym_scatter_kernel<double><<<blocks_e, TPB, 0, s>>>(knn_idx, dist64, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
+    PG_LAUNCH(h, s, "sym_scatter_kernel<double>", sym_scatter_kernel<double><<<blocks_e, TPB, 0, s>>>(knn_idx, dist64, n, k, row_id, id_map, (const uint8_t*)h->sym_recip.p, und_row_ptr,
                                                        (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
   else
-    PG_LAUNCH(h, s, "sym_scatter_kernel<float>", sym_scatter_kernel<float><<<blocks_e, TPB, 0, s>>>(knn_idx, dist32, n, k, (const uint8_t*)h->sym_recip.p, und_row_ptr,
+    PG_LAUNCH(h, s, "sym_scatter_kernel<float>", sym_scatter_kernel<float><<<blocks_e, TPB, 0, s>>>(knn_idx, dist32, n, k, row_id, id_map, (const uint8_t*)h->sym_recip.p, und_row_ptr,
                                                       (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
   PG_LAUNCH(h, s, "sym_sort_rows_kernel", sym_sort_rows_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(und_row_ptr, n, (const int32_t*)tcol.p, (const double*)tw.p,
                                                         und_col, und_w64, und_w32));

@@ -271,11 +271,17 @@ class Engine:
         return res
 
     # ---- K7 ------------------------------------------------------------------------------------
-    def symmetrize(self, knn_idx, knn_dist, want_w32=False):
-        """Undirected union of directed kNN lists -> symmetric CSR (row_ptr, col ascending, weight=min)."""
+    def symmetrize(self, knn_idx, knn_dist, want_w32=False, row_id=None, id_map=None):
+        """Undirected union of directed kNN lists -> symmetric CSR (row_ptr, col ascending, weight=min).
+
+        ``row_id`` / ``id_map`` (both or neither): the lists hold global ids, row i has id row_id[i] and
+        id_map[id] is the row of an id (-1 when it has no row here) - used for strips + halo."""
         n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
         row_ptr = self._empty((n + 1,), torch.int32)
+        n_ids = int(id_map.numel()) if id_map is not None else 0
         self._check(self.lib.pg_knn_symmetrize_count(self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+                                                     self._p(row_id, torch.int32, "row_id"),
+                                                     self._p(id_map, torch.int32, "id_map"), n_ids,
                                                      self._p(row_ptr, torch.int32, "row_ptr"), self._stream()))
         total = C.c_int64()
         self._check(self.lib.pg_knn_symmetrize_total(self._h, C.byref(total)))
@@ -288,6 +294,7 @@ class Engine:
             self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
             self._p(knn_dist, torch.float64, "dist64") if is64 else None,
             None if is64 else self._p(knn_dist, torch.float32, "dist32"),
+            self._p(row_id, torch.int32, "row_id"), self._p(id_map, torch.int32, "id_map"),
             self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
             self._p(w64, torch.float64, "w64"), self._p(w32, torch.float32, "w32"), self._stream()))
         return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}

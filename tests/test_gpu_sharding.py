@@ -1,0 +1,117 @@
+"""GPU: strip-sharded graphs equal the single-GPU graphs bit for bit (ranks emulated in lockstep on one GPU;
+the same generators run over NCCL in tests/multi_gpu_check.py / bench.py --workload c5)."""
+import numpy as np
+import pytest
+import torch
+
+from path_gene_multimodal_b200 import sharding, synth
+from path_gene_multimodal_b200.engine import default_knn_cell, radius_cell
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(xy, ty, world, edges=None):
+    dev = torch.device("cuda", 0)
+    n = len(xy)
+    d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+    gid = torch.arange(n, dtype=torch.int32, device=dev)
+    if edges is None:
+        chunks = [slice(q * n // world, (q + 1) * n // world) for q in range(world)]
+        edges = sharding.run_emulated([sharding.equal_count_edges(d_xy[c][:, 0].contiguous(), world, float(xy[:, 0].min()),
+                                                                  float(xy[:, 0].max())) for c in chunks])[0]
+    strips = sharding.strips_from_edges(edges)
+    parts = []
+    for s in strips:
+        m = (d_xy[:, 0] >= s.x_lo) & (d_xy[:, 0] < s.x_hi)
+        parts.append((d_xy[m].contiguous(), d_ty[m].contiguous(), gid[m].contiguous()))
+    return d_xy, d_ty, strips, parts
+
+
+@pytest.mark.parametrize("world", [2, 4, 7])
+def test_sharded_radius_equals_single(engine, world):
+    xy, ty, side = synth.make_points(60_000, seed=51)
+    d_xy, d_ty, strips, parts = _split(xy, ty, world)
+    engine.grid_build(d_xy, d_ty, None, radius_cell(50.0), None)
+    ref = engine.radius_graph(50.0, upper=True, want_dist32=True, want_dist64=True, want_edges=True)
+    ref_edges = ref["edges"].cpu().numpy()
+    res = sharding.run_emulated([sharding.sharded_radius_graph(engine, p[0], p[1], p[2], 50.0, s, q, world)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])
+    edges = np.concatenate([r["edges"].cpu().numpy() for r in res])
+    d64 = np.concatenate([r["dist64"].cpu().numpy() for r in res])
+    order = np.lexsort((edges[:, 1], edges[:, 0]))
+    assert np.array_equal(edges[order], ref_edges)                                   # every edge once, global ids
+    assert np.array_equal(d64[order], ref["dist64"].cpu().numpy())
+    deg = np.zeros(len(xy), dtype=np.int32)
+    nbr = np.zeros((len(xy), 5), dtype=np.int32)
+    for r, p in zip(res, parts):
+        g = p[2].cpu().numpy()
+        deg[g] = r["degree"].cpu().numpy()
+        nbr[g] = r["nbr_count"].cpu().numpy()
+        assert r["n_ghost"] > 0
+    assert np.array_equal(deg, ref["degree"].cpu().numpy()) and np.array_equal(nbr, ref["nbr_count"].cpu().numpy())
+    # per-strip statistics combine to the whole-slide statistics
+    tot = sum(int(r["stats"].cpu().numpy()[1]) for r in res)
+    assert tot == int(ref["stats"].cpu().numpy()[1])
+
+
+@pytest.mark.parametrize("world,k", [(2, 8), (4, 16), (5, 5)])
+def test_sharded_knn_equals_single(engine, world, k):
+    xy, ty, side = synth.make_points(50_000, seed=52)
+    n = len(xy)
+    d_xy, d_ty, strips, parts = _split(xy, ty, world)
+    engine.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, k), None)
+    kn = engine.knn(k, dist_dtype=torch.float64)
+    ref_idx, ref_d = kn["knn_idx"].cpu().numpy(), kn["dist"].cpu().numpy()
+    sym = engine.symmetrize(kn["knn_idx"], kn["dist"])
+    up = engine.csr_upper(sym["row_ptr"], sym["col"], sym["w64"])
+    comp = engine.compose_degree(sym["row_ptr"], sym["col"], d_ty, 5)
+    res = sharding.run_emulated([sharding.sharded_knn_graph(engine, p[0], p[1], p[2], k, s, q, world, n_global=n, h0=20.0)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])   # h0 too small on purpose: must retry
+    idx = np.zeros_like(ref_idx)
+    dist = np.zeros_like(ref_d)
+    deg = np.zeros(n, dtype=np.int32)
+    nbr = np.zeros((n, 5), dtype=np.int32)
+    for r, p in zip(res, parts):
+        g = p[2].cpu().numpy()
+        idx[g] = r["knn_idx"].cpu().numpy()
+        dist[g] = r["dist"].cpu().numpy()
+        deg[g] = r["degree"].cpu().numpy()
+        nbr[g] = r["nbr_count"].cpu().numpy()
+        assert r["halo"] > 20.0
+        # owned rows of the union CSR equal the single-GPU rows
+        rp = sym["row_ptr"].cpu().numpy()
+        col = sym["col"].cpu().numpy()
+        mine_rp = r["row_ptr"].cpu().numpy()
+        mine_col = r["col"].cpu().numpy()
+        for t in (0, len(g) // 2, len(g) - 1):
+            assert np.array_equal(mine_col[mine_rp[t]:mine_rp[t + 1]], col[rp[g[t]]:rp[g[t] + 1]])
+    assert np.array_equal(idx, ref_idx) and np.array_equal(dist, ref_d)
+    assert np.array_equal(deg, comp["degree"].cpu().numpy()) and np.array_equal(nbr, comp["nbr_count"].cpu().numpy())
+    edges = np.concatenate([r["edges"].cpu().numpy() for r in res])
+    w = np.concatenate([r["weight"].cpu().numpy() for r in res])
+    order = np.lexsort((edges[:, 1], edges[:, 0]))
+    assert np.array_equal(edges[order], up["edges"].cpu().numpy()) and np.array_equal(w[order], up["w64"].cpu().numpy())
+
+
+def test_sharded_with_ties_on_strip_edges(engine):
+    # lattice points sitting exactly on strip boundaries and exact distance ties across strips
+    gx, gy = np.meshgrid(np.arange(60.0) * 4.0, np.arange(40.0) * 4.0)
+    xy = np.stack([gx.ravel(), gy.ravel()], axis=1)
+    ty = (np.arange(len(xy)) % 5 + 1).astype(np.int32)
+    n = len(xy)
+    d_xy, d_ty, strips, parts = _split(xy, ty, 3, edges=[0.0, 80.0, 160.0, 236.0])
+    engine.grid_build(d_xy, d_ty, None, radius_cell(8.0), None)
+    ref = engine.radius_graph(8.0, upper=True, want_edges=True)
+    res = sharding.run_emulated([sharding.sharded_radius_graph(engine, p[0], p[1], p[2], 8.0, s, q, 3)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])
+    edges = np.concatenate([r["edges"].cpu().numpy() for r in res])
+    order = np.lexsort((edges[:, 1], edges[:, 0]))
+    assert np.array_equal(edges[order], ref["edges"].cpu().numpy())
+    engine.grid_build(d_xy, d_ty, None, 6.0, None)
+    kn = engine.knn(6, dist_dtype=torch.float64)
+    res = sharding.run_emulated([sharding.sharded_knn_graph(engine, p[0], p[1], p[2], 6, s, q, 3, n_global=n, h0=5.0, union=False)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])
+    idx = np.zeros((n, 6), dtype=np.int32)
+    for r, p in zip(res, parts):
+        idx[p[2].cpu().numpy()] = r["knn_idx"].cpu().numpy()
+    assert np.array_equal(idx, kn["knn_idx"].cpu().numpy())      # (d^2, global id) tie-break survives sharding
