@@ -162,11 +162,11 @@ def algorithmic_bytes(n, e_dir):
 def kernel_bytes(name, n, e_und, cells):
     """Compulsory bytes of one launch of each kernel (its own inputs read once + outputs written once)."""
     table = {
-        "histogram_kernel": 16 * n + 8 * n + 4 * cells,            # xy in; cell_of + rank out; cell counters
-        "scan_lookback_kernel": None,                               # depends on which scan: filled by caller
-        "scatter_kernel": 16 * n + 4 * n + 12 * n + 32 * n,         # xy, type, cell_of+rank+start in; sorted xy + meta out
-        "radius_count_kernel<8>": 32 * n + 4 * cells + 4 * n + 4 * n + 4 * N_TYPES * n,  # sorted xy+meta, cell_start in; count, degree, nbr out
-        "radius_fill_kernel": 32 * n + 4 * cells + 8 * n + 4 * e_und + 4 * e_und + 16 * e_und,  # + row_ptr in; col, dist32, edges out
+        "histogram_kernel": 16 * n + 4 * cells,                       # xy in; cell counters
+        "scatter_kernel": 16 * n + 4 * n + 4 * cells + 24 * n,        # xy, type, cursors in; sorted xy + meta out
+        "radius_count_kernel": 24 * n + 4 * cells + 4 * n + 4 * n + 4 * N_TYPES * n,  # sorted xy+meta, cell_start in; count, degree, nbr out
+        "radius_fill_kernel": 24 * n + 4 * cells + 8 * n + 4 * e_und + 4 * e_und + 16 * e_und,  # + row_ptr in; col, dist32, edges out
+        "scan_kernel": 8 * max(n, cells),
     }
     return table.get(name)
 

@@ -27,12 +27,14 @@ struct pg_handle {
   int device = 0;
   std::string err;
   // grow-only workspace
-  pg_buf cell_count;   // int32 [C+1] histogram, then reused
-  pg_buf cell_start;   // int32 [C+1]
-  pg_buf cell_of;      // int32 [N]
-  pg_buf rank;         // int32 [N]
+  pg_buf cell_count;   // int32 [C+1] histogram
+  pg_buf cell_start;   // int32 [3 pad | 0 | C+1]: scan output lands one slot late, the scatter's cursor
+                       // atomics turn it into the start-of-cell array in place (see pg_grid.cu)
+  pg_buf cell_of;      // scratch (K7 staging columns)
+  pg_buf rank;         // scratch (K7 staging weights)
   pg_buf s_xy;         // double2 [N]   points in cell order
-  pg_buf s_meta;       // int4 [N]      {local idx, gid, type, 0}
+  pg_buf s_meta;       // int2 [N]      {local idx, type}
+  pg_buf s_gid;        // int32 [N]     global ids in cell order (only when gid was given)
   pg_buf row_count;    // int32 [N+1]   per-row counts before the scan
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
@@ -99,7 +101,8 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
   } while (0)
 
 // internal scan entry (pg_scan.cu): out[0..n] exclusive prefix of in[0..n), out[n] = total
-int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s);
+// total_copy (optional): a second device location that also receives the total
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy = nullptr);
 
 static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

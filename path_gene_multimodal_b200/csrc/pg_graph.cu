@@ -98,8 +98,6 @@ sym_sort_rows_kernel(const int32_t* __restrict__ row_ptr, int n, const int32_t* 
   }
 }
 
-__global__ void copy_total_kernel(const int32_t* src, int32_t* dst) { *dst = *src; }
-
 // rows are ascending by column: entries above the row's own id start at the first col > id
 __global__ void __launch_bounds__(TPB)
 upper_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
@@ -304,10 +302,7 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
                                                        n, k, (int32_t*)h->sym_cursor.p, (int32_t*)h->row_count.p));
     PG_LAUNCH_CHECK(h);
   }
-  if ((rc = pg_scan_i32(h, (const int32_t*)h->row_count.p, und_row_ptr, n, s))) return rc;
-  PG_LAUNCH(h, s, "copy_total_kernel", copy_total_kernel<<<1, 1, 0, s>>>(und_row_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1));
-  PG_LAUNCH_CHECK(h);
-  return PG_OK;
+  return pg_scan_i32(h, (const int32_t*)h->row_count.p, und_row_ptr, n, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1);
 }
 
 int pg_knn_symmetrize_total(pg_handle* h, int64_t* total) {
@@ -367,10 +362,7 @@ int pg_csr_upper_count(pg_handle* h, int32_t n, const int32_t* row_ptr, const in
     PG_LAUNCH(h, s, "upper_count_kernel", upper_count_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, row_id, n, (int32_t*)h->row_count.p));
     PG_LAUNCH_CHECK(h);
   }
-  if ((rc = pg_scan_i32(h, (const int32_t*)h->row_count.p, up_ptr, n, s))) return rc;
-  PG_LAUNCH(h, s, "copy_total_kernel", copy_total_kernel<<<1, 1, 0, s>>>(up_ptr + n, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 2));
-  PG_LAUNCH_CHECK(h);
-  return PG_OK;
+  return pg_scan_i32(h, (const int32_t*)h->row_count.p, up_ptr, n, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 2);
 }
 
 int pg_csr_upper_total(pg_handle* h, int64_t* total) {

@@ -1,6 +1,12 @@
-// K2-K4: uniform-grid binning of the centroids - atomic histogram over cells, decoupled look-back
-// scan (pg_scan.cu), counting-sort scatter. Plays the role of the cKDTree build at
+// K2-K4: uniform-grid binning of the centroids - atomic histogram over cells, single-pass scan
+// (pg_scan.cu), counting-sort scatter. Plays the role of the cKDTree build at
 // /root/reference/hovernet_tile_inference.ipynb:1818 (KNN.from_array) and :2964 (cKDTree(coords)).
+//
+// Passes over the points: (1) histogram with fire-and-forget atomics (nothing written per point),
+// (2) scatter that re-derives the cell and claims its slot with one atomicAdd on the scanned array.
+// The scan writes start(c) into B[c+1] (B[0] = 0 stays put); after the scatter's cursor increments
+// B[c+1] = start(c) + count(c) = start(c+1), i.e. B has become the start-of-cell array itself - no
+// per-point rank / cell arrays and no cursor copy.
 #include <cmath>
 #include "pg_common.cuh"
 
@@ -46,28 +52,31 @@ __global__ void init_bounds_kernel(unsigned long long* keys) {
   keys[2] = keys[3] = 0ull;
 }
 
-// K2: one thread per point; the atomic's return value is the point's rank inside its cell.
+// K2: one thread per point, reduction atomics (no return value, nothing else written)
 __global__ void __launch_bounds__(TPB)
 histogram_kernel(const double2* __restrict__ xy, int n, double x0, double y0, double inv_cell, int nx, int ny,
-                 int32_t* __restrict__ cell_count, int32_t* __restrict__ cell_of, int32_t* __restrict__ rank) {
-  int i = blockIdx.x * TPB + threadIdx.x;
+                 int32_t* __restrict__ cell_count) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  double2 p = xy[i];
-  int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
-  cell_of[i] = c;
-  rank[i] = atomicAdd(&cell_count[c], 1);
+  const double2 p = xy[i];
+  const int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
+  atomicAdd(&cell_count[c], 1);
 }
 
-// K4: counting-sort scatter into cell order, carrying {local idx, gid, type}.
+// K4: counting-sort scatter into cell order, carrying {local idx, type} (+ gid when given).
+// cursor = B + 1: cursor[c] starts as start(c) and ends as start(c+1).
 __global__ void __launch_bounds__(TPB)
 scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
-               int n, const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_of,
-               const int32_t* __restrict__ rank, double2* __restrict__ s_xy, int4* __restrict__ s_meta) {
-  int i = blockIdx.x * TPB + threadIdx.x;
+               int n, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
+               double2* __restrict__ s_xy, int2* __restrict__ s_meta, int32_t* __restrict__ s_gid) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  int dst = cell_start[cell_of[i]] + rank[i];
-  s_xy[dst] = xy[i];
-  s_meta[dst] = make_int4(i, gid ? gid[i] : i, type ? type[i] : 0, 0);
+  const double2 p = xy[i];
+  const int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
+  const int dst = atomicAdd(&cursor[c], 1);
+  s_xy[dst] = p;
+  s_meta[dst] = make_int2(i, type ? type[i] : 0);
+  if (gid) s_gid[dst] = gid[i];
 }
 
 }  // namespace
@@ -124,25 +133,28 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   g.x0 = b[0]; g.y0 = b[1]; g.cell = cell; g.inv_cell = 1.0 / cell; g.has_gid = gid != nullptr;
 
   int rc;
-  if ((rc = pg_reserve(h, h->cell_count, (cells + 1) * sizeof(int32_t)))) return rc;
-  if ((rc = pg_reserve(h, h->cell_start, (cells + 4) * sizeof(int32_t)))) return rc;
-  if ((rc = pg_reserve(h, h->cell_of, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
-  if ((rc = pg_reserve(h, h->rank, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->cell_count, (cells + 4) * sizeof(int32_t)))) return rc;
+  const size_t cs_need = (cells + 8) * sizeof(int32_t);
+  if (cs_need > h->cell_start.cap) {
+    if ((rc = pg_reserve(h, h->cell_start, cs_need))) return rc;
+    PG_CUDA(h, cudaMemsetAsync(h->cell_start.p, 0, 16, s));  // B[0] = 0 (and the alignment pad) once per allocation
+  }
   if ((rc = pg_reserve(h, h->s_xy, (size_t)(n + 1) * sizeof(double2)))) return rc;
-  if ((rc = pg_reserve(h, h->s_meta, (size_t)(n + 1) * sizeof(int4)))) return rc;
+  if ((rc = pg_reserve(h, h->s_meta, (size_t)(n + 1) * sizeof(int2)))) return rc;
+  if (gid && (rc = pg_reserve(h, h->s_gid, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
+  int32_t* B = (int32_t*)h->cell_start.p + 3;  // B[0] = 0, B + 1 is 16-byte aligned for the scan
 
   PG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, (cells + 1) * sizeof(int32_t), s));
   if (n > 0) {
-    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny,
-                                                      (int32_t*)h->cell_count.p, (int32_t*)h->cell_of.p,
-                                                      (int32_t*)h->rank.p));
+    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
+        (const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p));
     PG_LAUNCH_CHECK(h);
   }
-  if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, (int32_t*)h->cell_start.p, (int32_t)cells, s))) return rc;
+  if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, B + 1, (int32_t)cells, s))) return rc;
   if (n > 0) {
-    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const double2*)xy, type, gid, n, (const int32_t*)h->cell_start.p,
-                                                    (const int32_t*)h->cell_of.p, (const int32_t*)h->rank.p,
-                                                    (double2*)h->s_xy.p, (int4*)h->s_meta.p));
+    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
+        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (double2*)h->s_xy.p,
+        (int2*)h->s_meta.p, gid ? (int32_t*)h->s_gid.p : nullptr));
     PG_LAUNCH_CHECK(h);
   }
   g.built = true;

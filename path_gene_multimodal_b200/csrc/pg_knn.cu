@@ -54,7 +54,7 @@ knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restr
            float* __restrict__ dist32, double x_lo, double x_hi, int32_t* halo_ok) {
   const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= g.n) return;
-  const int4 me = g.s_meta[p];
+  const int2 me = g.s_meta[p];
   if (me.x >= g.n_query) return;
   const double2 q = g.s_xy[p];
   const int cx = pg_cell_coord(q.x, g.x0, g.inv_cell, g.nx);
@@ -68,7 +68,7 @@ knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restr
       const double2 c = g.s_xy[j];
       const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
       if (d2 <= wd2 && j != p) {
-        const int cid = g.s_meta[j].y;
+        const int cid = g.s_gid ? g.s_gid[j] : g.s_meta[j].x;
         if (d2 < wd2 || cid < wid) {
           top.insert(d2, cid, k);
           wd2 = top.worst_d2(k);

@@ -5,22 +5,29 @@
 struct pg_grid_view {
   const int32_t* __restrict__ cell_start;
   const double2* __restrict__ s_xy;
-  const int4* __restrict__ s_meta;  // {local idx, gid, type, 0}
+  const int2* __restrict__ s_meta;  // {local idx, type}
+  const int32_t* __restrict__ s_gid;  // global ids in cell order, or NULL when ids are the local indices
   int32_t n, n_query, nx, ny;
   double x0, y0, cell, inv_cell;
 };
 
 static inline pg_grid_view pg_make_view(const pg_handle* h) {
   pg_grid_view v;
-  v.cell_start = (const int32_t*)h->cell_start.p;
+  v.cell_start = (const int32_t*)h->cell_start.p + 3;  // see pg_grid.cu: B[c] = first point of cell c
   v.s_xy = (const double2*)h->s_xy.p;
-  v.s_meta = (const int4*)h->s_meta.p;
+  v.s_meta = (const int2*)h->s_meta.p;
+  v.s_gid = h->grid.has_gid ? (const int32_t*)h->s_gid.p : nullptr;
   v.n = h->grid.n; v.n_query = h->grid.n_query; v.nx = h->grid.nx; v.ny = h->grid.ny;
   v.x0 = h->grid.x0; v.y0 = h->grid.y0; v.cell = h->grid.cell; v.inv_cell = h->grid.inv_cell;
   return v;
 }
 
 #ifdef __CUDACC__
+// id used for ordering / output columns of the point at cell-order position j
+__device__ __forceinline__ int pg_id_of(const pg_grid_view& g, int j, int local_idx) {
+  return g.s_gid ? g.s_gid[j] : local_idx;
+}
+
 // Visit the (2R+1)^2 block of cells around (cx, cy) as 2R+1 contiguous runs of the cell-ordered
 // point array (cells are row-major, so one grid row of the block is one run).
 template <class F>

@@ -1,7 +1,10 @@
-// K3: single-pass exclusive scan with decoupled look-back (int32), used for cell_start and every
-// CSR row_ptr. One tile of 4096 items per CTA; tiles are handed out by an atomic ticket so a CTA
-// only ever waits on tiles that are already running. Descriptor words carry an epoch tag, so the
-// descriptor array never has to be cleared between scans.
+// K3: single-pass exclusive scan (int32) used for cell_start and every CSR row_ptr.
+// Decoupled look-back organised for short chains: tiles of 4096 items are handed out by an atomic
+// ticket (so a tile only ever waits on tiles that are already running); every tile publishes its
+// aggregate at once, then sums the aggregates of the earlier tiles of its GROUP (256 tiles) directly,
+// one descriptor per thread - a single L2 round trip - and adds the inclusive prefix published by the
+// last tile of the previous group. 1M items = 245 tiles = one group: no serial chain at all.
+// Descriptor words carry an epoch tag, so nothing has to be cleared between scans.
 #include "pg_common.cuh"
 
 namespace {
@@ -9,11 +12,10 @@ namespace {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_GROUP = SCAN_THREADS;  // tiles per group: one predecessor per thread
 
-constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
-
-__device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, uint64_t state, int32_t value) {
-  return ((uint64_t)epoch << 34) | (state << 32) | (uint32_t)value;
+__device__ __forceinline__ uint64_t pack_desc(uint32_t epoch, int32_t value) {
+  return ((uint64_t)epoch << 32) | (uint32_t)value;
 }
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
   uint64_t v;
@@ -24,12 +26,13 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// agg[tile]: aggregate of one tile; gpre[group]: inclusive prefix up to the end of a group
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n,
-                     uint64_t* desc, unsigned int* ticket, uint32_t epoch, int num_tiles) {
+scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n, uint64_t* agg, uint64_t* gpre,
+            unsigned int* ticket, uint32_t epoch, int num_tiles, int32_t* total_copy) {
   __shared__ int s_tile;
   __shared__ int s_warp_sum[SCAN_THREADS / PG_WARP];
-  __shared__ int s_prefix;
+  __shared__ int s_red[SCAN_THREADS / PG_WARP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     int t = (int)atomicAdd(ticket, 1u);
@@ -55,7 +58,6 @@ scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, 
   int tsum = 0;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) { int x = v[i]; v[i] = tsum; tsum += x; }
-  // warp inclusive scan of thread sums
   int incl = tsum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -72,41 +74,37 @@ scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, 
     tile_sum += s;
   }
   const int thread_off = warp_off + incl - tsum;
+  if (tid == 0) st_relaxed_u64(&agg[tile], pack_desc(epoch, tile_sum));
 
-  if (warp == 0) {
-    int running = 0;
-    if (tile == 0) {
-      if (lane == 0) st_relaxed_u64(&desc[0], pack_desc(epoch, ST_PREFIX, tile_sum));
-    } else {
-      if (lane == 0) st_relaxed_u64(&desc[tile], pack_desc(epoch, ST_AGG, tile_sum));
-      int look = tile - 1;
-      while (true) {
-        const int idx = look - lane;
-        uint64_t w = pack_desc(epoch, ST_PREFIX, 0);  // virtual tile -1: prefix 0
-        if (idx >= 0) {
-          do {
-            w = ld_relaxed_u64(&desc[idx]);
-          } while ((uint32_t)(w >> 34) != epoch || ((w >> 32) & 3) == 0);
-        }
-        const bool is_prefix = ((w >> 32) & 3) == ST_PREFIX;
-        const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-        const int first = pm ? (__ffs(pm) - 1) : 32;
-        int contrib = (lane <= first) ? (int32_t)(uint32_t)w : 0;
+  // prefix of this tile = prefix of the previous group + aggregates of the earlier tiles of my group
+  const int group = tile / SCAN_GROUP, first = group * SCAN_GROUP;
+  int contrib = 0;
+  const int pred = first + tid;
+  if (pred < tile) {
+    uint64_t w;
+    do { w = ld_relaxed_u64(&agg[pred]); } while ((uint32_t)(w >> 32) != epoch);
+    contrib = (int32_t)(uint32_t)w;
+  }
+  if (tid == SCAN_THREADS - 1 && group > 0) {   // this lane never has a predecessor (pred >= first + 255 >= tile)
+    uint64_t w;
+    do { w = ld_relaxed_u64(&gpre[group - 1]); } while ((uint32_t)(w >> 32) != epoch);
+    contrib = (int32_t)(uint32_t)w;
+  }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-        running += contrib;
-        if (pm) break;
-        look -= 32;
-      }
-      if (lane == 0) st_relaxed_u64(&desc[tile], pack_desc(epoch, ST_PREFIX, running + tile_sum));
-    }
-    if (lane == 0) {
-      s_prefix = running;
-      if (tile == num_tiles - 1) out[n] = running + tile_sum;
+  for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+  if (lane == 0) s_red[warp] = contrib;
+  __syncthreads();
+  int prefix = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / PG_WARP; ++w) prefix += s_red[w];
+  if (tid == 0) {
+    if (tile == first + SCAN_GROUP - 1) st_relaxed_u64(&gpre[group], pack_desc(epoch, prefix + tile_sum));
+    if (tile == num_tiles - 1) {
+      out[n] = prefix + tile_sum;
+      if (total_copy) *total_copy = prefix + tile_sum;
     }
   }
-  __syncthreads();
-  const int off = s_prefix + thread_off;
+  const int off = prefix + thread_off;
   if (base + SCAN_ITEMS <= n) {
     int4* p = reinterpret_cast<int4*>(out + base);
 #pragma unroll
@@ -119,34 +117,39 @@ scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, 
   }
 }
 
-__global__ void scan_empty_kernel(int32_t* out) { out[0] = 0; }
+__global__ void scan_empty_kernel(int32_t* out, int32_t* total_copy) {
+  out[0] = 0;
+  if (total_copy) *total_copy = 0;
+}
 
 }  // namespace
 
-int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s) {
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy) {
   if (n < 0) return pg_set_error(h, PG_ERR_INVALID, "scan: n < 0");
   if (n == 0) {
-    PG_LAUNCH(h, s, "scan_empty_kernel", scan_empty_kernel<<<1, 1, 0, s>>>(out));
+    PG_LAUNCH(h, s, "scan_empty_kernel", scan_empty_kernel<<<1, 1, 0, s>>>(out, total_copy));
     PG_LAUNCH_CHECK(h);
     return PG_OK;
   }
   if (((uintptr_t)in & 15) || ((uintptr_t)out & 15))
     return pg_set_error(h, PG_ERR_INVALID, "scan: in/out must be 16-byte aligned");
   const int num_tiles = pg_div_up(n, SCAN_TILE);
-  const size_t need = 256 + (size_t)num_tiles * sizeof(uint64_t);
+  const int num_groups = pg_div_up(num_tiles, SCAN_GROUP);
+  const size_t need = 256 + (size_t)(num_tiles + num_groups + 2) * sizeof(uint64_t);
   if (need > h->scan_state.cap) {
     int rc = pg_reserve(h, h->scan_state, need);
     if (rc) return rc;
     PG_CUDA(h, cudaMemsetAsync(h->scan_state.p, 0, h->scan_state.cap, s));
   }
   h->scan_epoch += 1;
-  if (h->scan_epoch >= (1u << 30)) {  // epoch field is 30 bits wide: start over on a clean slate
+  if (h->scan_epoch == 0xffffffffu) {  // epoch 0 means "never written": start over on a clean slate
     PG_CUDA(h, cudaMemsetAsync(h->scan_state.p, 0, h->scan_state.cap, s));
     h->scan_epoch = 1;
   }
   unsigned int* ticket = (unsigned int*)h->scan_state.p;
-  uint64_t* desc = (uint64_t*)((char*)h->scan_state.p + 256);
-  PG_LAUNCH(h, s, "scan_lookback_kernel", scan_lookback_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, desc, ticket, h->scan_epoch, num_tiles));
+  uint64_t* agg = (uint64_t*)((char*)h->scan_state.p + 256);
+  uint64_t* gpre = agg + num_tiles;
+  PG_LAUNCH(h, s, "scan_kernel", scan_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, agg, gpre, ticket, h->scan_epoch, num_tiles, total_copy));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -155,5 +158,5 @@ extern "C" int pg_exclusive_scan_i32(pg_handle* h, const int32_t* in, int32_t* o
   if (!h) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = (cudaStream_t)stream;
-  return pg_scan_i32(h, in, out, n, (cudaStream_t)stream);
+  return pg_scan_i32(h, in, out, n, (cudaStream_t)stream, nullptr);
 }
