@@ -27,14 +27,13 @@ struct pg_handle {
   int device = 0;
   std::string err;
   // grow-only workspace
-  pg_buf cell_count;   // int32 [C+1] histogram
+  pg_buf cell_count;   // int32 [C+1] histogram; all zero between builds (the scan clears what it reads)
+  bool cell_count_clean = false;
   pg_buf cell_start;   // int32 [3 pad | 0 | C+1]: scan output lands one slot late, the scatter's cursor
                        // atomics turn it into the start-of-cell array in place (see pg_grid.cu)
   pg_buf cell_of;      // scratch (K7 staging columns)
   pg_buf rank;         // scratch (K7 staging weights)
-  pg_buf s_xy;         // double2 [N]   points in cell order
-  pg_buf s_meta;       // int2 [N]      {local idx, type}
-  pg_buf s_gid;        // int32 [N]     global ids in cell order (only when gid was given)
+  pg_buf s_rec;        // pg_rec [N]    points in cell order, one 32-byte sector each (see pg_query.cuh)
   pg_buf row_count;    // int32 [N+1]   per-row counts before the scan
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
@@ -80,7 +79,19 @@ struct pg_kernel_scope {
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory
-#define PG_MISC_BYTES 256
+#define PG_MISC_ACC 256       // pg_stats_acc: degree-statistics accumulators kept in their reset state
+#define PG_MISC_ACC_HIST 512  // int32 [PG_ACC_HIST_MAX] histogram accumulators (all zero between launches)
+#define PG_ACC_HIST_MAX 1024
+#define PG_MISC_BYTES (PG_MISC_ACC_HIST + 4 * PG_ACC_HIST_MAX)
+
+// accumulators behind the fused degree statistics: every CTA adds its share, the last CTA to finish
+// copies them to the caller's pg_degree_stats / hist and puts them back into the reset state, so no
+// separate init / finish launches are needed.
+struct pg_stats_acc {
+  int32_t min_degree, max_degree;
+  unsigned long long sum_degree, sumsq_degree, n_nodes;
+  unsigned int done;  // CTAs finished
+};
 
 int pg_set_error(pg_handle* h, int code, const char* fmt, ...);
 int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
@@ -102,7 +113,9 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
 
 // internal scan entry (pg_scan.cu): out[0..n] exclusive prefix of in[0..n), out[n] = total
 // total_copy (optional): a second device location that also receives the total
-int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy = nullptr);
+// clear_in: zero in[0..n) while reading it (the buffer must then be writable)
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy = nullptr,
+                bool clear_in = false);
 
 static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -8,7 +8,7 @@
 // B[c+1] = start(c) + count(c) = start(c+1), i.e. B has become the start-of-cell array itself - no
 // per-point rank / cell arrays and no cursor copy.
 #include <cmath>
-#include "pg_common.cuh"
+#include "pg_query.cuh"
 
 namespace {
 
@@ -63,20 +63,21 @@ histogram_kernel(const double2* __restrict__ xy, int n, double x0, double y0, do
   atomicAdd(&cell_count[c], 1);
 }
 
-// K4: counting-sort scatter into cell order, carrying {local idx, type} (+ gid when given).
+// K4: counting-sort scatter into cell order: one 32-byte record per point, written as one full sector.
 // cursor = B + 1: cursor[c] starts as start(c) and ends as start(c+1).
 __global__ void __launch_bounds__(TPB)
 scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
                int n, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
-               double2* __restrict__ s_xy, int2* __restrict__ s_meta, int32_t* __restrict__ s_gid) {
+               pg_rec* __restrict__ rec) {
   const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const double2 p = xy[i];
+  const int t = type ? type[i] : 0;
+  const int id = gid ? gid[i] : i;
   const int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
   const int dst = atomicAdd(&cursor[c], 1);
-  s_xy[dst] = p;
-  s_meta[dst] = make_int2(i, type ? type[i] : 0);
-  if (gid) s_gid[dst] = gid[i];
+  const int tshift = (t >= 1 && t <= PG_PACKED_TYPES) ? (t - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
+  pg_st_rec(rec + dst, p.x, p.y, i, id, t, tshift);
 }
 
 }  // namespace
@@ -133,28 +134,34 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   g.x0 = b[0]; g.y0 = b[1]; g.cell = cell; g.inv_cell = 1.0 / cell; g.has_gid = gid != nullptr;
 
   int rc;
-  if ((rc = pg_reserve(h, h->cell_count, (cells + 4) * sizeof(int32_t)))) return rc;
+  const size_t cc_need = (cells + 4) * sizeof(int32_t);
+  if (cc_need > h->cell_count.cap) h->cell_count_clean = false;
+  if ((rc = pg_reserve(h, h->cell_count, cc_need))) return rc;
   const size_t cs_need = (cells + 8) * sizeof(int32_t);
   if (cs_need > h->cell_start.cap) {
     if ((rc = pg_reserve(h, h->cell_start, cs_need))) return rc;
     PG_CUDA(h, cudaMemsetAsync(h->cell_start.p, 0, 16, s));  // B[0] = 0 (and the alignment pad) once per allocation
   }
-  if ((rc = pg_reserve(h, h->s_xy, (size_t)(n + 1) * sizeof(double2)))) return rc;
-  if ((rc = pg_reserve(h, h->s_meta, (size_t)(n + 1) * sizeof(int2)))) return rc;
-  if (gid && (rc = pg_reserve(h, h->s_gid, (size_t)(n + 1) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->s_rec, (size_t)(n + 1) * sizeof(pg_rec)))) return rc;
   int32_t* B = (int32_t*)h->cell_start.p + 3;  // B[0] = 0, B + 1 is 16-byte aligned for the scan
 
-  PG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, (cells + 1) * sizeof(int32_t), s));
+  // the histogram is all zero between builds: the scan below clears every counter it reads
+  if (!h->cell_count_clean) {
+    PG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, h->cell_count.cap, s));
+    h->cell_count_clean = true;
+  }
   if (n > 0) {
     PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
         (const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p));
     PG_LAUNCH_CHECK(h);
   }
-  if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, B + 1, (int32_t)cells, s))) return rc;
+  if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, B + 1, (int32_t)cells, s, nullptr, true))) {
+    h->cell_count_clean = false;
+    return rc;
+  }
   if (n > 0) {
     PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
-        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (double2*)h->s_xy.p,
-        (int2*)h->s_meta.p, gid ? (int32_t*)h->s_gid.p : nullptr));
+        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p));
     PG_LAUNCH_CHECK(h);
   }
   g.built = true;

@@ -85,6 +85,12 @@ int pg_create(int device, pg_handle** out) {
   int rc = pg_reserve(h, h->misc, PG_MISC_BYTES);
   if (rc == PG_OK) {
     e = cudaMemset(h->misc.p, 0, PG_MISC_BYTES);
+    if (e == cudaSuccess) {  // reset state of the statistics accumulators: min = INT_MAX, max = -1, sums 0
+      pg_stats_acc acc{};
+      acc.min_degree = 0x7fffffff;
+      acc.max_degree = -1;
+      e = cudaMemcpy((char*)h->misc.p + PG_MISC_ACC, &acc, sizeof(acc), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) rc = pg_set_error(nullptr, PG_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
   } else {
     g_create_error = h->err;
@@ -102,7 +108,7 @@ int pg_destroy(pg_handle* h) {
   if (!h) return PG_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  pg_buf* bufs[] = {&h->cell_count, &h->cell_start, &h->cell_of, &h->rank,      &h->s_xy,      &h->s_meta,    &h->s_gid,
+  pg_buf* bufs[] = {&h->cell_count, &h->cell_start, &h->cell_of, &h->rank,      &h->s_rec,
                     &h->row_count,  &h->scan_state, &h->misc,    &h->sym_extra, &h->sym_cursor, &h->sym_recip};
   for (pg_buf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -116,7 +122,7 @@ const char* pg_last_error(pg_handle* h) { return h ? h->err.c_str() : g_create_e
 
 int64_t pg_workspace_bytes(pg_handle* h) {
   if (!h) return 0;
-  pg_buf* bufs[] = {&h->cell_count, &h->cell_start, &h->cell_of, &h->rank,      &h->s_xy,      &h->s_meta,    &h->s_gid,
+  pg_buf* bufs[] = {&h->cell_count, &h->cell_start, &h->cell_of, &h->rank,      &h->s_rec,
                     &h->row_count,  &h->scan_state, &h->misc,    &h->sym_extra, &h->sym_cursor, &h->sym_recip};
   int64_t t = 0;
   for (pg_buf* b : bufs) t += (int64_t)b->cap;

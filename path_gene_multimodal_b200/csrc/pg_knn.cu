@@ -54,9 +54,9 @@ knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restr
            float* __restrict__ dist32, double x_lo, double x_hi, int32_t* halo_ok) {
   const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= g.n) return;
-  const int2 me = g.s_meta[p];
-  if (me.x >= g.n_query) return;
-  const double2 q = g.s_xy[p];
+  const pg_rec me = pg_ld_rec(g.rec + p);
+  if (me.row >= g.n_query) return;
+  const double2 q = make_double2(me.x, me.y);
   const int cx = pg_cell_coord(q.x, g.x0, g.inv_cell, g.nx);
   const int cy = pg_cell_coord(q.y, g.y0, g.inv_cell, g.ny);
   topk<KMAX> top;
@@ -65,10 +65,10 @@ knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restr
   int wid = top.id[0];
   auto scan = [&](int b, int e) {
     for (int j = b; j < e; ++j) {
-      const double2 c = g.s_xy[j];
+      const pg_rec c = pg_ld_rec(g.rec + j);
       const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
       if (d2 <= wd2 && j != p) {
-        const int cid = g.s_gid ? g.s_gid[j] : g.s_meta[j].x;
+        const int cid = c.id;
         if (d2 < wd2 || cid < wid) {
           top.insert(d2, cid, k);
           wd2 = top.worst_d2(k);
@@ -94,7 +94,7 @@ knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restr
     ++R;
     pg_visit_ring(g, cx, cy, R, scan);
   }
-  const int64_t o = (int64_t)me.x * k;
+  const int64_t o = (int64_t)me.row * k;
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
     if (s < k) {

@@ -2,11 +2,24 @@
 #pragma once
 #include "pg_common.cuh"
 
+// One point of the cell-ordered array = one 32-byte DRAM sector: the counting-sort scatter writes it
+// with a single 256-bit store (a full sector, so L2 never has to fetch the old contents) and a query
+// reads coordinates, ids and type of a candidate with a single 256-bit load.
+struct __align__(32) pg_rec {
+  double x, y;
+  int32_t row;     // index of the point in the caller's arrays (its output row; >= n_query: halo point)
+  int32_t id;      // id used for ordering / output columns: gid[row] when gids were given, else row
+  int32_t type;    // cell type id as given
+  int32_t tshift;  // bit offset of the type's 12-bit field in the packed neighbour-type counter
+};
+
+#define PG_TYPE_BITS 12
+#define PG_PACKED_TYPES 5
+#define PG_TYPE_OTHER_SHIFT 60  // types outside 1..5 land in the 4 spare top bits (never read)
+
 struct pg_grid_view {
   const int32_t* __restrict__ cell_start;
-  const double2* __restrict__ s_xy;
-  const int2* __restrict__ s_meta;  // {local idx, type}
-  const int32_t* __restrict__ s_gid;  // global ids in cell order, or NULL when ids are the local indices
+  const pg_rec* __restrict__ rec;
   int32_t n, n_query, nx, ny;
   double x0, y0, cell, inv_cell;
 };
@@ -14,19 +27,32 @@ struct pg_grid_view {
 static inline pg_grid_view pg_make_view(const pg_handle* h) {
   pg_grid_view v;
   v.cell_start = (const int32_t*)h->cell_start.p + 3;  // see pg_grid.cu: B[c] = first point of cell c
-  v.s_xy = (const double2*)h->s_xy.p;
-  v.s_meta = (const int2*)h->s_meta.p;
-  v.s_gid = h->grid.has_gid ? (const int32_t*)h->s_gid.p : nullptr;
+  v.rec = (const pg_rec*)h->s_rec.p;
   v.n = h->grid.n; v.n_query = h->grid.n_query; v.nx = h->grid.nx; v.ny = h->grid.ny;
   v.x0 = h->grid.x0; v.y0 = h->grid.y0; v.cell = h->grid.cell; v.inv_cell = h->grid.inv_cell;
   return v;
 }
 
 #ifdef __CUDACC__
-// id used for ordering / output columns of the point at cell-order position j
-__device__ __forceinline__ int pg_id_of(const pg_grid_view& g, int j, int local_idx) {
-  return g.s_gid ? g.s_gid[j] : local_idx;
+// 256-bit global load / store (LDG.E.256 / STG.E.256 on sm_100a)
+__device__ __forceinline__ pg_rec pg_ld_rec(const pg_rec* p) {
+  unsigned long long a, b, c, d;
+  // .nc: the records are read-only for the lifetime of every query kernel; not volatile so loads can be batched
+  asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  pg_rec r;
+  r.x = __longlong_as_double((long long)a);
+  r.y = __longlong_as_double((long long)b);
+  r.row = (int32_t)(uint32_t)c; r.id = (int32_t)(uint32_t)(c >> 32);
+  r.type = (int32_t)(uint32_t)d; r.tshift = (int32_t)(uint32_t)(d >> 32);
+  return r;
 }
+__device__ __forceinline__ void pg_st_rec(pg_rec* p, double x, double y, int row, int id, int type, int tshift) {
+  const unsigned long long a = (unsigned long long)__double_as_longlong(x), b = (unsigned long long)__double_as_longlong(y);
+  const unsigned long long c = (unsigned long long)(uint32_t)row | ((unsigned long long)(uint32_t)id << 32);
+  const unsigned long long d = (unsigned long long)(uint32_t)type | ((unsigned long long)(uint32_t)tshift << 32);
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ double2 pg_ld_xy(const pg_rec* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // Visit the (2R+1)^2 block of cells around (cx, cy) as 2R+1 contiguous runs of the cell-ordered
 // point array (cells are row-major, so one grid row of the block is one run).

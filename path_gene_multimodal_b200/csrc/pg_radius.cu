@@ -4,306 +4,279 @@
 // loop), :3021 (edge_index), :3041-3042 (np.linalg.norm distances, float32 edge_attr); composition /
 // degree per SURVEY A.5. Acceptance test is d2 <= r*r in float64 with d2 = fl(fl(dx*dx)+fl(dy*dy)).
 //
-// Work split: one CTA per run of W consecutive cells of a grid row. The three cell rows around the
-// run (W+2 cells each, three contiguous runs of the cell-ordered point array) are staged in shared
-// memory with coalesced loads; then each thread takes one query point of the run and walks its own
-// 3x3 block out of shared memory in ONE merged, branch-free loop (accept flag folded into the counters,
-// per-type counts in 12-bit fields of one 64-bit word). A run whose neighbourhood does not fit the
-// staging buffer, a ring radius > 1 or more than 5 types fall back to walking global memory.
+// Work split: one thread per point, in cell order, so the 32 lanes of a warp sit in the same or adjacent
+// cells and their candidate records (one 32-byte sector each, read with one 256-bit load) hit in L1.
+// With the usual cell ~ r the 3x3 block of a point is three contiguous runs of the cell-ordered array;
+// they are walked as ONE merged loop (a branch-free index map) so a warp iterates max-over-lanes of the
+// block population once instead of three times. The count pass keeps the per-type neighbour counts in
+// 12-bit fields of one 64-bit register (the field offset is precomputed in the record); degree statistics
+// are reduced per warp, then per CTA, then added to accumulators in the handle, and the last CTA to finish
+// publishes them - no init / finish launches. The fill pass collects a row's accepted (id, position) pairs
+// in shared memory (slot-major, conflict-free), sorts the handful of entries by id and writes the row.
 #include <cmath>
 #include "pg_query.cuh"
 
 namespace {
 
-constexpr int TPB = 128;
-constexpr int FILL_CAP = 32;
-constexpr int HIST_SMEM_MAX = 512;
-constexpr int STAGE_CAP = 1024;  // candidates staged per CTA (24 B each)
-constexpr int MAX_W = 256;       // query cells per CTA
-constexpr int TYPE_BITS = 12;    // packed per-type counters; STAGE_CAP < 2^12 so a field cannot overflow
-constexpr int PACKED_TYPES = 5;
+constexpr int TPB_COUNT = 256;
+constexpr int TPB_FILL = 128;
+constexpr int FILL_CAP = 16;         // row entries kept per thread in shared memory (2 x 4 B x CAP x TPB_FILL = 16 KB)
+constexpr int FIELD_MAX = (1 << PG_TYPE_BITS) - 1;
 
-// per-thread degree statistics -> one set of atomics per CTA
-__device__ __forceinline__ void reduce_degree_stats(int mn, int mx, long long sum, long long sq, int cnt,
-                                                    pg_degree_stats* stats) {
-  __shared__ int s_mn[TPB / 32], s_mx[TPB / 32], s_cnt[TPB / 32];
-  __shared__ long long s_sum[TPB / 32], s_sq[TPB / 32];
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    sq += __shfl_xor_sync(0xffffffffu, sq, d);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; s_sum[warp] = sum; s_sq[warp] = sq; s_cnt[warp] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < TPB / 32; ++w) {
-      mn = min(mn, s_mn[w]); mx = max(mx, s_mx[w]); sum += s_sum[w]; sq += s_sq[w]; cnt += s_cnt[w];
+// Calls f(position) for every candidate of the (2R+1)^2 block around (cx, cy) and flush() at least once
+// every FIELD_MAX candidates (and once at the end).
+template <bool MERGED, class F, class FL>
+__device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx, int cy, F&& f, FL&& flush) {
+  if (MERGED) {  // R == 1: three runs, one loop
+    const int xa = max(cx - 1, 0), xe = min(cx + 1, g.nx - 1) + 1;
+    const int32_t* c1 = g.cell_start + (int64_t)cy * g.nx;
+    const int b1 = c1[xa], e1 = c1[xe];
+    int b0 = 0, e0 = 0, b2 = 0, e2 = 0;
+    if (cy > 0) { b0 = c1[xa - g.nx]; e0 = c1[xe - g.nx]; }
+    if (cy + 1 < g.ny) { b2 = c1[xa + g.nx]; e2 = c1[xe + g.nx]; }
+    const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
+    const int off1 = b1 - n0, off2 = b2 - n01;
+    for (int t0 = 0; t0 < tot; t0 += FIELD_MAX) {
+      const int t1 = min(tot, t0 + FIELD_MAX);
+      for (int t = t0; t < t1; ++t) f(t + (t < n0 ? b0 : (t < n01 ? off1 : off2)));
+      flush();
     }
-    if (cnt > 0) {
-      atomicMin(&stats->min_degree, mn);
-      atomicMax(&stats->max_degree, mx);
-      atomicAdd((unsigned long long*)&stats->sum_degree, (unsigned long long)sum);
-      atomicAdd((unsigned long long*)&stats->sumsq_degree, (unsigned long long)sq);
-      atomicAdd((unsigned long long*)&stats->n_nodes, (unsigned long long)cnt);
+  } else {
+    pg_visit_block(g, cx, cy, R, [&](int b, int e) {
+      for (int j0 = b; j0 < e; j0 += FIELD_MAX) {
+        const int j1 = min(e, j0 + FIELD_MAX);
+        for (int j = j0; j < j1; ++j) f(j);
+        flush();
+      }
+    });
+  }
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Count pass: CSR row count (all neighbours, or only id_j > id_i when `upper`) and, fused over all
+// neighbours: degree, per-type neighbour counts, degree statistics and histogram.
+// hist_mode 0: no histogram; 1: shared-memory bins -> accumulators -> published by the last CTA;
+// 2: hist_len > PG_ACC_HIST_MAX, bins added straight into the caller's (pre-zeroed) array.
+template <bool MERGED, bool WIDE_TYPES>
+__global__ void __launch_bounds__(TPB_COUNT)
+radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __restrict__ row_count,
+                    int32_t* __restrict__ degree, int32_t* __restrict__ nbr_count, int n_types,
+                    pg_stats_acc* acc, int32_t* acc_hist, pg_degree_stats* stats, int32_t* hist, int hist_len,
+                    int hist_mode) {
+  __shared__ int s_hist[PG_ACC_HIST_MAX];
+  __shared__ int s_mn, s_mx, s_cnt, s_last;
+  __shared__ unsigned long long s_sum, s_sq;
+  const int tid = threadIdx.x;
+  if (hist_mode == 1)
+    for (int i = tid; i < hist_len; i += TPB_COUNT) s_hist[i] = 0;
+  if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_cnt = 0; s_sum = 0; s_sq = 0; s_last = 0; }
+  __syncthreads();
+
+  const int q = blockIdx.x * TPB_COUNT + tid;
+  const pg_rec me = pg_ld_rec(g.rec + min(q, g.n - 1));
+  const bool active = q < g.n && me.row < g.n_query;  // halo points own no row
+  int deg = 0, up = 0;
+  if (active) {
+    const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
+    const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
+    unsigned long long pk = 0;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    walk_block<MERGED>(g, R, cx, cy,
+      [&](int j) {
+        const pg_rec c = pg_ld_rec(g.rec + j);
+        const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+        const int a = (d2 <= r2) & (j != q);
+        deg += a;
+        up += a & (c.id > me.id);
+        pk += (unsigned long long)a << c.tshift;
+      },
+      [&]() {
+        c0 += (int)(pk & FIELD_MAX); c1 += (int)((pk >> PG_TYPE_BITS) & FIELD_MAX);
+        c2 += (int)((pk >> (2 * PG_TYPE_BITS)) & FIELD_MAX); c3 += (int)((pk >> (3 * PG_TYPE_BITS)) & FIELD_MAX);
+        c4 += (int)((pk >> (4 * PG_TYPE_BITS)) & FIELD_MAX);
+        pk = 0;
+      });
+    row_count[me.row] = upper ? up : deg;
+    if (degree) degree[me.row] = deg;
+    if (nbr_count) {
+      int32_t* o = nbr_count + (int64_t)me.row * n_types;
+      if (!WIDE_TYPES) {
+        o[0] = c0;
+        if (n_types > 1) o[1] = c1;
+        if (n_types > 2) o[2] = c2;
+        if (n_types > 3) o[3] = c3;
+        if (n_types > 4) o[4] = c4;
+      } else {  // more than PG_PACKED_TYPES types: a second walk with counters in local memory (rare)
+        int tc[PG_MAX_TYPES];
+#pragma unroll
+        for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] = 0;
+        walk_block<MERGED>(g, R, cx, cy,
+          [&](int j) {
+            const pg_rec c = pg_ld_rec(g.rec + j);
+            const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+            if (d2 <= r2 && j != q && c.type >= 1 && c.type <= n_types) tc[c.type - 1] += 1;
+          },
+          [&]() {});
+        for (int t = 0; t < n_types; ++t) o[t] = tc[t];
+      }
+    }
+    if (hist_mode == 1) atomicAdd(&s_hist[min(deg, hist_len - 1)], 1);
+    else if (hist_mode == 2) atomicAdd(&hist[min(deg, hist_len - 1)], 1);
+  }
+  if (!stats && hist_mode != 1) return;  // block-uniform
+
+  // ---- degree statistics: warp -> CTA -> accumulators in the handle
+  const int wmn = __reduce_min_sync(0xffffffffu, active ? deg : 0x7fffffff);
+  const int wmx = __reduce_max_sync(0xffffffffu, active ? deg : -1);
+  const int wcnt = __reduce_add_sync(0xffffffffu, active ? 1 : 0);
+  const long long wsum = warp_sum_ll(active ? (long long)deg : 0ll);
+  const long long wsq = warp_sum_ll(active ? (long long)deg * deg : 0ll);
+  if ((tid & 31) == 0 && wcnt > 0) {
+    atomicMin(&s_mn, wmn); atomicMax(&s_mx, wmx); atomicAdd(&s_cnt, wcnt);
+    atomicAdd(&s_sum, (unsigned long long)wsum); atomicAdd(&s_sq, (unsigned long long)wsq);
+  }
+  __syncthreads();
+  if (tid == 0 && s_cnt > 0) {
+    atomicMin(&acc->min_degree, s_mn); atomicMax(&acc->max_degree, s_mx);
+    atomicAdd(&acc->sum_degree, s_sum); atomicAdd(&acc->sumsq_degree, s_sq);
+    atomicAdd(&acc->n_nodes, (unsigned long long)s_cnt);
+  }
+  if (hist_mode == 1)
+    for (int i = tid; i < hist_len; i += TPB_COUNT) {
+      const int c = s_hist[i];
+      if (c) atomicAdd(&acc_hist[i], c);
+    }
+  // ---- the last CTA to get here publishes the totals and puts the accumulators back into their reset state
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&acc->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (hist_mode == 1)
+    for (int i = tid; i < hist_len; i += TPB_COUNT) hist[i] = atomicExch(&acc_hist[i], 0);
+  if (tid == 0) {
+    const int mn = atomicExch(&acc->min_degree, 0x7fffffff), mx = atomicExch(&acc->max_degree, -1);
+    const unsigned long long sm = atomicExch(&acc->sum_degree, 0ull), sq = atomicExch(&acc->sumsq_degree, 0ull);
+    const unsigned long long nn = atomicExch(&acc->n_nodes, 0ull);
+    atomicExch(&acc->done, 0u);
+    if (stats) {
+      stats->min_degree = nn ? mn : 0; stats->max_degree = nn ? mx : 0;
+      stats->sum_degree = (long long)sm; stats->sumsq_degree = (long long)sq; stats->n_nodes = (long long)nn;
     }
   }
 }
 
-// stats block + histogram cleared by one tiny launch (replaces memset + init)
-__global__ void prep_stats_kernel(pg_degree_stats* stats, int32_t* hist, int hist_len, int empty) {
+// nothing to query: the statistics of an empty graph
+__global__ void empty_stats_kernel(pg_degree_stats* stats, int32_t* hist, int hist_len) {
   if (stats && threadIdx.x == 0) {
-    stats->min_degree = empty ? 0 : 0x7fffffff;
-    stats->max_degree = empty ? 0 : -1;
-    stats->sum_degree = 0; stats->sumsq_degree = 0; stats->n_nodes = 0;
+    stats->min_degree = 0; stats->max_degree = 0; stats->sum_degree = 0; stats->sumsq_degree = 0; stats->n_nodes = 0;
   }
   if (hist)
     for (int i = threadIdx.x; i < hist_len; i += blockDim.x) hist[i] = 0;
 }
 
-// Geometry of one CTA's run of cells and its staged neighbourhood.
-struct run_geom {
-  int y, c0, c1, xa, ncell;  // query cells [c0, c1) of row y; candidate cells [xa, xa + ncell)
-  int q0, q1;                // query points (cell-order positions)
-  int base[3], first[3];     // shared-memory base and first global position of each staged row
-  int total;
+struct fill_out {
+  int32_t* __restrict__ col;
+  float* __restrict__ dist32;
+  double* __restrict__ dist64;
+  long long* __restrict__ edges;
+  long long* __restrict__ edge_index;
+  float* __restrict__ edge_attr;
+  long long n_edges;
 };
 
-struct stage_smem {
-  double2 xy[STAGE_CAP];
-  int2 ia[STAGE_CAP];            // {id, aux}
-  int cs[3][MAX_W + 4];          // cell_start of the three rows over the candidate cells (+1)
-};
+__device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int my_id, int key, double d2) {
+  const double d = sqrt(d2);
+  o.col[pos] = key;
+  if (o.dist32) o.dist32[pos] = (float)d;
+  if (o.dist64) o.dist64[pos] = d;
+  if (o.edges) *reinterpret_cast<longlong2*>(o.edges + 2 * pos) = make_longlong2(my_id, key);
+  if (o.edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
+    o.edge_index[pos] = my_id; o.edge_index[o.n_edges + pos] = key;
+    o.edge_index[2 * o.n_edges + pos] = key; o.edge_index[3 * o.n_edges + pos] = my_id;
+  }
+  if (o.edge_attr) { o.edge_attr[pos] = (float)d; o.edge_attr[o.n_edges + pos] = (float)d; }  // ipynb:3041-3042
+}
 
-// Loads the cell_start slices, derives the geometry and (when it fits) stages the candidates.
-// aux_mode 0: aux = bit shift of the packed type counter; 1: aux unused.
-__device__ __forceinline__ bool stage_run(const pg_grid_view& g, int W, int nbx, int n_types, int aux_mode,
-                                          stage_smem& sm, run_geom& rg) {
+// Fill pass. A row of up to FILL_CAP entries (known from row_ptr before the walk) takes one walk:
+// accepted (id, position) pairs are appended to the thread's column of two shared-memory arrays, sorted
+// by id there, and written out with the distance recomputed from the (L1-resident) record. Longer rows
+// are emitted in chunks of FILL_CAP: each walk keeps the FILL_CAP smallest ids above the last one written.
+template <bool MERGED>
+__global__ void __launch_bounds__(TPB_FILL)
+radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* __restrict__ row_ptr, fill_out o,
+                   long long capacity, int32_t* overflow) {
+  __shared__ int s_key[FILL_CAP][TPB_FILL];
+  __shared__ int s_pos[FILL_CAP][TPB_FILL];
   const int tid = threadIdx.x;
-  rg.y = blockIdx.x / nbx;
-  rg.c0 = (blockIdx.x - rg.y * nbx) * W;
-  rg.c1 = min(rg.c0 + W, g.nx);
-  rg.xa = max(rg.c0 - 1, 0);
-  const int xb = min(rg.c1, g.nx - 1);
-  rg.ncell = xb - rg.xa + 1;
-  const int stride = rg.ncell + 1;
-  for (int i = tid; i < 3 * stride; i += TPB) {
-    const int r = i / stride, c = i - r * stride;
-    const int yy = rg.y - 1 + r;
-    sm.cs[r][c] = (yy >= 0 && yy < g.ny) ? g.cell_start[yy * g.nx + rg.xa + c] : 0;
-  }
-  __syncthreads();
-  rg.q0 = sm.cs[1][rg.c0 - rg.xa];
-  rg.q1 = sm.cs[1][rg.c1 - rg.xa];
-  int acc = 0;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    rg.first[r] = sm.cs[r][0];
-    rg.base[r] = acc;
-    acc += sm.cs[r][rg.ncell] - sm.cs[r][0];
-  }
-  rg.total = acc;
-  if (rg.q1 == rg.q0 || acc > STAGE_CAP) return false;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int cnt = sm.cs[r][rg.ncell] - rg.first[r];
-    for (int t = tid; t < cnt; t += TPB) {
-      const int j = rg.first[r] + t;
-      const int2 m = g.s_meta[j];
-      sm.xy[rg.base[r] + t] = g.s_xy[j];
-      int aux = 0;
-      if (aux_mode == 0) aux = (m.y >= 1 && m.y <= n_types) ? (m.y - 1) * TYPE_BITS : 60;
-      sm.ia[rg.base[r] + t] = make_int2(pg_id_of(g, j, m.x), aux);
-    }
-  }
-  __syncthreads();
-  return true;
-}
+  const int q = blockIdx.x * TPB_FILL + tid;
+  if (q >= g.n) return;
+  const pg_rec me = pg_ld_rec(g.rec + q);
+  if (me.row >= g.n_query) return;
+  const int base = row_ptr[me.row];
+  const int cnt = row_ptr[me.row + 1] - base;
+  if (cnt <= 0) return;
+  if ((long long)base + cnt > capacity) { atomicExch(overflow, 1); return; }
+  const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
+  const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
 
-// shared-memory sub-ranges of the 3x3 block of cell cx inside the staged rows
-__device__ __forceinline__ void block_ranges(const stage_smem& sm, const run_geom& rg, int cx, int nx,
-                                             int& s0, int& n0, int& s1, int& n1, int& s2, int& n2) {
-  const int i0 = max(cx - 1, rg.xa) - rg.xa, i1 = min(cx + 1, nx - 1) - rg.xa + 1;
-  const int a0 = sm.cs[0][i0], a1 = sm.cs[1][i0], a2 = sm.cs[2][i0];
-  n0 = sm.cs[0][i1] - a0; n1 = sm.cs[1][i1] - a1; n2 = sm.cs[2][i1] - a2;
-  s0 = rg.base[0] + a0 - rg.first[0];
-  s1 = rg.base[1] + a1 - rg.first[1];
-  s2 = rg.base[2] + a2 - rg.first[2];
-}
-
-// Count pass: CSR row count (all neighbours, or only id_j > id_i when `upper`) and, fused over all
-// neighbours: degree, per-type neighbour counts, degree statistics and histogram.
-__global__ void __launch_bounds__(TPB)
-radius_count_kernel(pg_grid_view g, double r2, int R, int W, int nbx, int upper, int32_t* __restrict__ row_count,
-                    int32_t* __restrict__ degree, int32_t* __restrict__ nbr_count, int n_types,
-                    pg_degree_stats* stats, int32_t* hist, int hist_len) {
-  __shared__ stage_smem sm;
-  __shared__ int s_hist[HIST_SMEM_MAX];
-  const bool use_smem_hist = hist != nullptr && hist_len <= HIST_SMEM_MAX;
-  if (use_smem_hist)
-    for (int i = threadIdx.x; i < hist_len; i += TPB) s_hist[i] = 0;
-  run_geom rg;
-  const bool fast = R == 1 && n_types <= PACKED_TYPES;
-  const bool staged = stage_run(g, W, nbx, n_types, 0, sm, rg) && fast;   // block-uniform
-  if (rg.q1 == rg.q0) return;                                             // block-uniform: empty run
-
-  int st_mn = 0x7fffffff, st_mx = -1, st_cnt = 0;
-  long long st_sum = 0, st_sq = 0;
-  for (int q = rg.q0 + threadIdx.x; q < rg.q1; q += TPB) {
-    const int2 me = g.s_meta[q];
-    if (me.x >= g.n_query) continue;  // halo point: no row
-    const int my_id = pg_id_of(g, q, me.x);
-    int deg = 0, up = 0;
-    if (staged) {
-      const int slot = rg.base[1] + q - rg.first[1];
-      const double2 p = sm.xy[slot];
-      const int cx = pg_cell_coord(p.x, g.x0, g.inv_cell, g.nx);
-      int s0, n0, s1, n1, s2, n2;
-      block_ranges(sm, rg, cx, g.nx, s0, n0, s1, n1, s2, n2);
-      const int n01 = n0 + n1, tot = n01 + n2;
-      const int off1 = s1 - n0, off2 = s2 - n01;
-      unsigned long long pk = 0;
-      for (int t = 0; t < tot; ++t) {
-        const int idx = t + (t < n0 ? s0 : (t < n01 ? off1 : off2));
-        const double2 c = sm.xy[idx];
-        const int2 ia = sm.ia[idx];
-        const double d2 = pg_dist2(p.x, p.y, c.x, c.y);
-        const int acc = (d2 <= r2) & (idx != slot);
-        deg += acc;
-        up += acc & (ia.x > my_id);
-        pk += (unsigned long long)acc << ia.y;
-      }
-      if (nbr_count) {
-#pragma unroll
-        for (int t = 0; t < PACKED_TYPES; ++t)
-          if (t < n_types) nbr_count[(int64_t)me.x * n_types + t] = (int)((pk >> (TYPE_BITS * t)) & ((1u << TYPE_BITS) - 1));
-      }
-    } else {
-      const double2 p = g.s_xy[q];
-      const int cx = pg_cell_coord(p.x, g.x0, g.inv_cell, g.nx);
-      int tc[PG_MAX_TYPES];
-#pragma unroll
-      for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] = 0;
-      pg_visit_block(g, cx, rg.y, R, [&](int b, int e) {
-        for (int j = b; j < e; ++j) {
-          const double2 c = g.s_xy[j];
-          const double d2 = pg_dist2(p.x, p.y, c.x, c.y);
-          if (d2 <= r2 && j != q) {
-            const int2 m = g.s_meta[j];
-            ++deg;
-            up += (pg_id_of(g, j, m.x) > my_id);
-#pragma unroll
-            for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] += (m.y == t + 1);
-          }
+  if (cnt <= FILL_CAP) {
+    int m = 0;
+    walk_block<MERGED>(g, R, cx, cy,
+      [&](int j) {
+        const pg_rec c = pg_ld_rec(g.rec + j);
+        const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+        if (d2 <= r2 && j != q && (!upper || c.id > me.id) && m < FILL_CAP) {
+          s_key[m][tid] = c.id; s_pos[m][tid] = j; ++m;
         }
-      });
-      if (nbr_count) {
-#pragma unroll
-        for (int t = 0; t < PG_MAX_TYPES; ++t)
-          if (t < n_types) nbr_count[(int64_t)me.x * n_types + t] = tc[t];
-      }
+      },
+      [&]() {});
+    for (int a = 1; a < m; ++a) {  // insertion sort of a handful of entries, own column only
+      const int k = s_key[a][tid], p = s_pos[a][tid];
+      int s = a;
+      while (s > 0 && s_key[s - 1][tid] > k) { s_key[s][tid] = s_key[s - 1][tid]; s_pos[s][tid] = s_pos[s - 1][tid]; --s; }
+      s_key[s][tid] = k; s_pos[s][tid] = p;
     }
-    row_count[me.x] = upper ? up : deg;
-    if (degree) degree[me.x] = deg;
-    if (hist) {
-      const int bin = min(deg, hist_len - 1);
-      if (use_smem_hist) atomicAdd(&s_hist[bin], 1); else atomicAdd(&hist[bin], 1);
+    for (int t = 0; t < m; ++t) {
+      const double2 c = pg_ld_xy(g.rec + s_pos[t][tid]);
+      emit_entry(o, (long long)base + t, me.id, s_key[t][tid], pg_dist2(me.x, me.y, c.x, c.y));
     }
-    st_mn = min(st_mn, deg); st_mx = max(st_mx, deg); st_sum += deg; st_sq += (long long)deg * deg; ++st_cnt;
+    return;
   }
-  if (stats) reduce_degree_stats(st_mn, st_mx, st_sum, st_sq, st_cnt, stats);
-  if (use_smem_hist) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < hist_len; i += TPB) {
-      const int c = s_hist[i];
-      if (c) atomicAdd(&hist[i], c);
-    }
-  }
-}
 
-// Fill pass. Same staging; a row is emitted in ascending column (id) order in chunks of FILL_CAP:
-// each pass keeps the FILL_CAP smallest accepted ids above the last one written, so ordinary rows
-// take one walk and heavy rows take ceil(count / FILL_CAP) walks without extra memory.
-__global__ void __launch_bounds__(TPB)
-radius_fill_kernel(pg_grid_view g, double r2, int R, int W, int nbx, int upper, const int32_t* __restrict__ row_ptr,
-                   int32_t* __restrict__ col, float* __restrict__ dist32, double* __restrict__ dist64,
-                   long long* __restrict__ edges, long long* __restrict__ edge_index,
-                   float* __restrict__ edge_attr, long long n_edges, long long capacity, int32_t* overflow) {
-  __shared__ stage_smem sm;
-  run_geom rg;
-  const bool staged = stage_run(g, W, nbx, 0, 1, sm, rg) && R == 1;
-  if (rg.q1 == rg.q0) return;
-  for (int q = rg.q0 + threadIdx.x; q < rg.q1; q += TPB) {
-    const int2 me = g.s_meta[q];
-    if (me.x >= g.n_query) continue;
-    const int base = row_ptr[me.x];
-    const int cnt = row_ptr[me.x + 1] - base;
-    if (cnt <= 0) continue;
-    if ((long long)base + cnt > capacity) { atomicExch(overflow, 1); continue; }
-    const int my_id = pg_id_of(g, q, me.x);
-    const double2 p = g.s_xy[q];
-    const int cx = pg_cell_coord(p.x, g.x0, g.inv_cell, g.nx);
-    int s0 = 0, n0 = 0, s1 = 0, n1 = 0, s2 = 0, n2 = 0, slot = 0;
-    if (staged) {
-      slot = rg.base[1] + q - rg.first[1];
-      block_ranges(sm, rg, cx, g.nx, s0, n0, s1, n1, s2, n2);
-    }
-    pg_sorted_chunk<FILL_CAP> buf;
-    int emitted = 0;
-    int last = upper ? my_id : -1;
-    while (emitted < cnt) {
-      buf.reset(last);
-      if (staged) {
-        const int n01 = n0 + n1, tot = n01 + n2;
-        const int off1 = s1 - n0, off2 = s2 - n01;
-        for (int t = 0; t < tot; ++t) {
-          const int idx = t + (t < n0 ? s0 : (t < n01 ? off1 : off2));
-          const double2 c = sm.xy[idx];
-          const double d2 = pg_dist2(p.x, p.y, c.x, c.y);
-          if (d2 <= r2 && idx != slot) buf.push(sm.ia[idx].x, d2);
+  int emitted = 0;
+  int last = upper ? me.id : -1;
+  while (emitted < cnt) {
+    int m = 0;
+    walk_block<MERGED>(g, R, cx, cy,
+      [&](int j) {
+        const pg_rec c = pg_ld_rec(g.rec + j);
+        const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+        if (!(d2 <= r2) || j == q || c.id <= last) return;
+        if (m == FILL_CAP) {
+          if (c.id >= s_key[FILL_CAP - 1][tid]) return;
+          m = FILL_CAP - 1;
         }
-      } else {
-        pg_visit_block(g, cx, rg.y, R, [&](int b, int e) {
-          for (int j = b; j < e; ++j) {
-            const double2 c = g.s_xy[j];
-            const double d2 = pg_dist2(p.x, p.y, c.x, c.y);
-            if (d2 <= r2 && j != q) buf.push(pg_id_of(g, j, g.s_meta[j].x), d2);
-          }
-        });
-      }
-      if (buf.m == 0) break;  // cannot happen when row_ptr came from the matching count pass
-      for (int t = 0; t < buf.m; ++t) {
-        const long long o = (long long)base + emitted + t;
-        const double d = sqrt(buf.val[t]);
-        col[o] = buf.key[t];
-        if (dist32) dist32[o] = (float)d;
-        if (dist64) dist64[o] = d;
-        if (edges) { edges[2 * o] = my_id; edges[2 * o + 1] = buf.key[t]; }
-        if (edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
-          edge_index[o] = my_id; edge_index[n_edges + o] = buf.key[t];
-          edge_index[2 * n_edges + o] = buf.key[t]; edge_index[3 * n_edges + o] = my_id;
-        }
-        if (edge_attr) { edge_attr[o] = (float)d; edge_attr[n_edges + o] = (float)d; }  // ipynb:3041-3042
-      }
-      emitted += buf.m;
-      last = buf.key[buf.m - 1];
+        int s = m;
+        while (s > 0 && s_key[s - 1][tid] > c.id) { s_key[s][tid] = s_key[s - 1][tid]; s_pos[s][tid] = s_pos[s - 1][tid]; --s; }
+        s_key[s][tid] = c.id; s_pos[s][tid] = j;
+        ++m;
+      },
+      [&]() {});
+    if (m == 0) break;  // cannot happen when row_ptr came from the matching count pass
+    for (int t = 0; t < m; ++t) {
+      const double2 c = pg_ld_xy(g.rec + s_pos[t][tid]);
+      emit_entry(o, (long long)base + emitted + t, me.id, s_key[t][tid], pg_dist2(me.x, me.y, c.x, c.y));
     }
+    emitted += m;
+    last = s_key[m - 1][tid];
   }
-}
-
-// cells per CTA: about one query point per thread, bounded by the staging buffer
-static inline int pick_run_width(const pg_grid& gr) {
-  const double cells = (double)gr.nx * (double)gr.ny;
-  const double lambda = gr.n > 0 ? (double)gr.n / cells : 1.0;   // points per cell
-  int w = (int)std::floor(TPB / std::max(lambda, 1e-3));
-  const int by_stage = (int)std::floor(STAGE_CAP / (3.0 * 2.5 * std::max(lambda, 1e-3))) - 2;  // 2.5x headroom
-  w = std::min(w, by_stage);
-  w = std::max(1, std::min(w, MAX_W));
-  return std::min(w, std::max(gr.nx, 1));
 }
 
 static inline int ring_radius(double r, const pg_grid& gr) {
@@ -336,15 +309,31 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   if ((rc = pg_reserve(h, h->row_count, ((size_t)nq + 4) * sizeof(int32_t)))) return rc;
   h->radius_r = r;
   h->radius_flags = flags;
-  if (stats || hist)
-    PG_LAUNCH(h, s, "prep_stats_kernel", prep_stats_kernel<<<1, 256, 0, s>>>(stats, hist, hist ? hist_len : 0, nq == 0));
   if (gr.n > 0 && nq > 0) {
     pg_grid_view v = pg_make_view(h);
-    const int W = pick_run_width(gr);
-    const int nbx = pg_div_up(gr.nx, W);
-    PG_LAUNCH(h, s, "radius_count_kernel", radius_count_kernel<<<nbx * gr.ny, TPB, 0, s>>>(
-        v, r * r, ring_radius(r, gr), W, nbx, flags == PG_RADIUS_UPPER, (int32_t*)h->row_count.p, degree, nbr_count,
-        nbr_count ? n_types : 1, stats, hist, hist_len));
+    const int R = ring_radius(r, gr);
+    const int upper = flags == PG_RADIUS_UPPER;
+    const int nt = nbr_count ? n_types : 1;
+    int hist_mode = 0;
+    if (hist) {
+      hist_mode = hist_len <= PG_ACC_HIST_MAX ? 1 : 2;
+      if (hist_mode == 2) PG_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)hist_len * sizeof(int32_t), s));
+    }
+    pg_stats_acc* acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
+    int32_t* acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
+    const int blocks = pg_div_up(gr.n, TPB_COUNT);
+    const bool wide = nbr_count && n_types > PG_PACKED_TYPES;
+#define PG_COUNT_LAUNCH(M, W)                                                                                   \
+  PG_LAUNCH(h, s, "radius_count_kernel", radius_count_kernel<M, W><<<blocks, TPB_COUNT, 0, s>>>(                \
+      v, r * r, R, upper, (int32_t*)h->row_count.p, degree, nbr_count, nt, acc, acc_hist, stats, hist, hist_len, hist_mode))
+    if (R == 1 && !wide) PG_COUNT_LAUNCH(true, false);
+    else if (R == 1) PG_COUNT_LAUNCH(true, true);
+    else if (!wide) PG_COUNT_LAUNCH(false, false);
+    else PG_COUNT_LAUNCH(false, true);
+#undef PG_COUNT_LAUNCH
+    PG_LAUNCH_CHECK(h);
+  } else if (stats || hist) {
+    PG_LAUNCH(h, s, "empty_stats_kernel", empty_stats_kernel<<<1, 256, 0, s>>>(stats, hist, hist ? hist_len : 0));
     PG_LAUNCH_CHECK(h);
   }
   return pg_scan_i32(h, (const int32_t*)h->row_count.p, row_ptr, nq, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS));
@@ -373,15 +362,20 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   PG_REQUIRE(h, capacity == 0 || col != nullptr, "pg_radius_fill: col is NULL");
   PG_REQUIRE(h, !(edge_index || edge_attr) || (h->radius_flags == PG_RADIUS_UPPER && n_edges >= 0 && n_edges <= capacity),
              "pg_radius_fill: edge_index / edge_attr need the UPPER count pass and 0 <= n_edges <= capacity");
+  PG_REQUIRE(h, ((uintptr_t)edges_i64 & 15) == 0, "pg_radius_fill: edges must be 16-byte aligned");
   const pg_grid& gr = h->grid;
   if (gr.n == 0 || gr.n_query == 0) return PG_OK;
   pg_grid_view v = pg_make_view(h);
-  const int W = pick_run_width(gr);
-  const int nbx = pg_div_up(gr.nx, W);
-  PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<<<nbx * gr.ny, TPB, 0, s>>>(
-      v, h->radius_r * h->radius_r, ring_radius(h->radius_r, gr), W, nbx, h->radius_flags == PG_RADIUS_UPPER, row_ptr, col,
-      dist32, dist64, (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges, (long long)capacity,
-      (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW)));
+  const int R = ring_radius(h->radius_r, gr);
+  const int upper = h->radius_flags == PG_RADIUS_UPPER;
+  fill_out o{col, dist32, dist64, (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges};
+  int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
+  const int blocks = pg_div_up(gr.n, TPB_FILL);
+  const double r2 = h->radius_r * h->radius_r;
+  if (R == 1)
+    PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<true><<<blocks, TPB_FILL, 0, s>>>(v, r2, R, upper, row_ptr, o, (long long)capacity, ovf));
+  else
+    PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<false><<<blocks, TPB_FILL, 0, s>>>(v, r2, R, upper, row_ptr, o, (long long)capacity, ovf));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

@@ -26,9 +26,12 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// agg[tile]: aggregate of one tile; gpre[group]: inclusive prefix up to the end of a group
+// agg[tile]: aggregate of one tile; gpre[group]: inclusive prefix up to the end of a group.
+// CLEAR: the input is zeroed as it is read (the cell histogram is handed back clean for the next build,
+// which saves a memset node per build).
+template <bool CLEAR>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n, uint64_t* agg, uint64_t* gpre,
+scan_kernel(int32_t* in, int32_t* __restrict__ out, int32_t n, uint64_t* agg, uint64_t* gpre,
             unsigned int* ticket, uint32_t epoch, int num_tiles, int32_t* total_copy) {
   __shared__ int s_tile;
   __shared__ int s_warp_sum[SCAN_THREADS / PG_WARP];
@@ -45,15 +48,22 @@ scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n
 
   int v[SCAN_ITEMS];
   if (base + SCAN_ITEMS <= n) {
-    const int4* p = reinterpret_cast<const int4*>(in + base);
+    int4* p = reinterpret_cast<int4*>(in + base);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS / 4; ++i) {
-      int4 q = __ldg(p + i);
+      int4 q = p[i];
       v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+    if (CLEAR) {
+#pragma unroll
+      for (int i = 0; i < SCAN_ITEMS / 4; ++i) p[i] = make_int4(0, 0, 0, 0);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      v[i] = (base + i < n) ? in[base + i] : 0;
+      if (CLEAR && base + i < n) in[base + i] = 0;
+    }
   }
   int tsum = 0;
 #pragma unroll
@@ -124,7 +134,8 @@ __global__ void scan_empty_kernel(int32_t* out, int32_t* total_copy) {
 
 }  // namespace
 
-int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy) {
+int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy,
+                bool clear_in) {
   if (n < 0) return pg_set_error(h, PG_ERR_INVALID, "scan: n < 0");
   if (n == 0) {
     PG_LAUNCH(h, s, "scan_empty_kernel", scan_empty_kernel<<<1, 1, 0, s>>>(out, total_copy));
@@ -149,7 +160,10 @@ int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaSt
   unsigned int* ticket = (unsigned int*)h->scan_state.p;
   uint64_t* agg = (uint64_t*)((char*)h->scan_state.p + 256);
   uint64_t* gpre = agg + num_tiles;
-  PG_LAUNCH(h, s, "scan_kernel", scan_kernel<<<num_tiles, SCAN_THREADS, 0, s>>>(in, out, n, agg, gpre, ticket, h->scan_epoch, num_tiles, total_copy));
+  if (clear_in)
+    PG_LAUNCH(h, s, "scan_kernel", scan_kernel<true><<<num_tiles, SCAN_THREADS, 0, s>>>(const_cast<int32_t*>(in), out, n, agg, gpre, ticket, h->scan_epoch, num_tiles, total_copy));
+  else
+    PG_LAUNCH(h, s, "scan_kernel", scan_kernel<false><<<num_tiles, SCAN_THREADS, 0, s>>>(const_cast<int32_t*>(in), out, n, agg, gpre, ticket, h->scan_epoch, num_tiles, total_copy));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -158,5 +172,5 @@ extern "C" int pg_exclusive_scan_i32(pg_handle* h, const int32_t* in, int32_t* o
   if (!h) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = (cudaStream_t)stream;
-  return pg_scan_i32(h, in, out, n, (cudaStream_t)stream, nullptr);
+  return pg_scan_i32(h, in, out, n, (cudaStream_t)stream, nullptr, false);
 }
