@@ -34,6 +34,22 @@ struct pg_handle {
   pg_buf cell_of;      // scratch (K7 staging columns)
   pg_buf rank;         // scratch (K7 staging weights)
   pg_buf s_rec;        // pg_rec [N]    points in cell order, one 32-byte sector each (see pg_query.cuh)
+  pg_buf s_pos;        // int32 [N]     cell-order position of point i (inverse of the counting sort)
+  pg_buf s_gid;        // int32 [N]     copy of the caller's gids (only when given), for the fill pass
+  // radius graph: the count pass leaves its results in cell order (one 32-byte pg_row_meta per point plus a
+  // temporary CSR of 16-byte entries); the row scan and the fill pass gather from them in row order
+  pg_buf tmp_meta;     // pg_row_meta [N]
+  pg_buf tmp_ent;      // pg_tmp_ent [tmp_cap]
+  pg_buf row_tmp_off;  // int32 [n_query] offset of row i's entries in tmp_ent
+  int64_t tmp_cap = 0;        // entries tmp_ent can hold
+  int64_t tmp_need_hint = 0;  // entries a past count pass needed (grow-only sizing)
+  bool tmp_may_overflow = false;
+  struct {             // arguments of the last count pass, kept so that pg_radius_total can redo it if tmp_ent was too small
+    bool valid = false;
+    double r = 0; int32_t flags = 0; int32_t* row_ptr = nullptr; int32_t* degree = nullptr; int32_t* nbr_count = nullptr;
+    int32_t n_types = 0; pg_degree_stats* stats = nullptr; int32_t* hist = nullptr; int32_t hist_len = 0;
+    cudaStream_t stream = nullptr;
+  } last_count;
   pg_buf row_count;    // int32 [N+1]   per-row counts before the scan
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
@@ -78,7 +94,8 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
-#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory
+#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 tmp entries needed
+#define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent (zero between count passes)
 #define PG_MISC_ACC 256       // pg_stats_acc: degree-statistics accumulators kept in their reset state
 #define PG_MISC_ACC_HIST 512  // int32 [PG_ACC_HIST_MAX] histogram accumulators (all zero between launches)
 #define PG_ACC_HIST_MAX 1024
@@ -114,8 +131,16 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
 // internal scan entry (pg_scan.cu): out[0..n] exclusive prefix of in[0..n), out[n] = total
 // total_copy (optional): a second device location that also receives the total
 // clear_in: zero in[0..n) while reading it (the buffer must then be writable)
+// publish: degree statistics to hand to the caller from the scan's first CTA (see pg_radius.cu)
+struct pg_scan_publish {
+  pg_stats_acc* acc = nullptr;
+  int32_t* acc_hist = nullptr;
+  pg_degree_stats* stats = nullptr;
+  int32_t* hist = nullptr;  // NULL: no histogram to publish
+  int32_t hist_len = 0;
+};
 int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaStream_t s, int32_t* total_copy = nullptr,
-                bool clear_in = false);
+                bool clear_in = false, const pg_scan_publish* publish = nullptr);
 
 static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

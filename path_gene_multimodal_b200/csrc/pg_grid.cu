@@ -68,7 +68,7 @@ histogram_kernel(const double2* __restrict__ xy, int n, double x0, double y0, do
 __global__ void __launch_bounds__(TPB)
 scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
                int n, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
-               pg_rec* __restrict__ rec) {
+               pg_rec* __restrict__ rec, int32_t* __restrict__ pos, int32_t* __restrict__ gid_copy) {
   const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const double2 p = xy[i];
@@ -78,6 +78,8 @@ scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type,
   const int dst = atomicAdd(&cursor[c], 1);
   const int tshift = (t >= 1 && t <= PG_PACKED_TYPES) ? (t - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
   pg_st_rec(rec + dst, p.x, p.y, i, id, t, tshift);
+  pos[i] = dst;
+  if (gid) gid_copy[i] = id;
 }
 
 }  // namespace
@@ -143,6 +145,9 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     PG_CUDA(h, cudaMemsetAsync(h->cell_start.p, 0, 16, s));  // B[0] = 0 (and the alignment pad) once per allocation
   }
   if ((rc = pg_reserve(h, h->s_rec, (size_t)(n + 1) * sizeof(pg_rec)))) return rc;
+  if ((rc = pg_reserve(h, h->s_pos, (size_t)(n + 4) * sizeof(int32_t)))) return rc;
+  if (gid && (rc = pg_reserve(h, h->s_gid, (size_t)(n + 4) * sizeof(int32_t)))) return rc;
+  h->last_count.valid = false;
   int32_t* B = (int32_t*)h->cell_start.p + 3;  // B[0] = 0, B + 1 is 16-byte aligned for the scan
 
   // the histogram is all zero between builds: the scan below clears every counter it reads
@@ -161,7 +166,8 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   }
   if (n > 0) {
     PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
-        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p));
+        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p,
+        (int32_t*)h->s_pos.p, gid ? (int32_t*)h->s_gid.p : nullptr));
     PG_LAUNCH_CHECK(h);
   }
   g.built = true;

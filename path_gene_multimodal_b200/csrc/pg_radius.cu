@@ -10,8 +10,8 @@
 // they are walked as ONE merged loop (a branch-free index map) so a warp iterates max-over-lanes of the
 // block population once instead of three times. The count pass keeps the per-type neighbour counts in
 // 12-bit fields of one 64-bit register (the field offset is precomputed in the record); degree statistics
-// are reduced per warp, then per CTA, then added to accumulators in the handle, and the last CTA to finish
-// publishes them - no init / finish launches. The fill pass collects a row's accepted (id, position) pairs
+// are reduced per warp, then per CTA (no barrier), then added to accumulators in the handle which the row_ptr
+// scan that follows publishes and resets - no init / finish launches. The fill pass collects a row's accepted (id, position) pairs
 // in shared memory (slot-major, conflict-free), sorts the handful of entries by id and writes the row.
 #include <cmath>
 #include "pg_query.cuh"
@@ -23,10 +23,12 @@ constexpr int TPB_FILL = 128;
 constexpr int FILL_CAP = 16;         // row entries kept per thread in shared memory (2 x 4 B x CAP x TPB_FILL = 16 KB)
 constexpr int FIELD_MAX = (1 << PG_TYPE_BITS) - 1;
 
-// Calls f(position) for every candidate of the (2R+1)^2 block around (cx, cy) and flush() at least once
-// every FIELD_MAX candidates (and once at the end).
+// Calls f(position, record) for every candidate of the (2R+1)^2 block around (cx, cy) and flush() at least
+// once every FIELD_MAX candidates (and once at the end). Records are fetched four at a time so that four
+// 256-bit loads are in flight per thread; the slots past the end of a run are pointed at `self`, the
+// caller's own position, which every f rejects anyway (a point is not its own neighbour).
 template <bool MERGED, class F, class FL>
-__device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx, int cy, F&& f, FL&& flush) {
+__device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx, int cy, int self, F&& f, FL&& flush) {
   if (MERGED) {  // R == 1: three runs, one loop
     const int xa = max(cx - 1, 0), xe = min(cx + 1, g.nx - 1) + 1;
     const int32_t* c1 = g.cell_start + (int64_t)cy * g.nx;
@@ -36,16 +38,27 @@ __device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx,
     if (cy + 1 < g.ny) { b2 = c1[xa + g.nx]; e2 = c1[xe + g.nx]; }
     const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
     const int off1 = b1 - n0, off2 = b2 - n01;
-    for (int t0 = 0; t0 < tot; t0 += FIELD_MAX) {
-      const int t1 = min(tot, t0 + FIELD_MAX);
-      for (int t = t0; t < t1; ++t) f(t + (t < n0 ? b0 : (t < n01 ? off1 : off2)));
+    auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b0 : (t < n01 ? off1 : off2)) : self; };
+    for (int t0 = 0; t0 < tot; t0 += FIELD_MAX - 3) {  // FIELD_MAX - 3 is a multiple of 4
+      const int t1 = min(tot, t0 + FIELD_MAX - 3);
+      for (int t = t0; t < t1; t += 4) {
+        const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+        const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
+        const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
+        f(j0, r0); f(j1, r1); f(j2, r2); f(j3, r3);
+      }
       flush();
     }
   } else {
     pg_visit_block(g, cx, cy, R, [&](int b, int e) {
-      for (int j0 = b; j0 < e; j0 += FIELD_MAX) {
-        const int j1 = min(e, j0 + FIELD_MAX);
-        for (int j = j0; j < j1; ++j) f(j);
+      for (int j0 = b; j0 < e; j0 += FIELD_MAX - 3) {
+        const int j1 = min(e, j0 + FIELD_MAX - 3);
+        for (int j = j0; j < j1; j += 4) {
+          const int p0 = j, p1 = j + 1 < j1 ? j + 1 : self, p2 = j + 2 < j1 ? j + 2 : self, p3 = j + 3 < j1 ? j + 3 : self;
+          const pg_rec r0 = pg_ld_rec(g.rec + p0), r1 = pg_ld_rec(g.rec + p1);
+          const pg_rec r2 = pg_ld_rec(g.rec + p2), r3 = pg_ld_rec(g.rec + p3);
+          f(p0, r0); f(p1, r1); f(p2, r2); f(p3, r3);
+        }
         flush();
       }
     });
@@ -60,21 +73,20 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 
 // Count pass: CSR row count (all neighbours, or only id_j > id_i when `upper`) and, fused over all
 // neighbours: degree, per-type neighbour counts, degree statistics and histogram.
-// hist_mode 0: no histogram; 1: shared-memory bins -> accumulators -> published by the last CTA;
+// hist_mode 0: no histogram; 1: shared-memory bins -> accumulators -> published by the scan that follows;
 // 2: hist_len > PG_ACC_HIST_MAX, bins added straight into the caller's (pre-zeroed) array.
 template <bool MERGED, bool WIDE_TYPES>
 __global__ void __launch_bounds__(TPB_COUNT)
 radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __restrict__ row_count,
                     int32_t* __restrict__ degree, int32_t* __restrict__ nbr_count, int n_types,
-                    pg_stats_acc* acc, int32_t* acc_hist, pg_degree_stats* stats, int32_t* hist, int hist_len,
-                    int hist_mode) {
+                    pg_stats_acc* acc, int32_t* acc_hist, bool stats, int32_t* hist, int hist_len, int hist_mode) {
   __shared__ int s_hist[PG_ACC_HIST_MAX];
-  __shared__ int s_mn, s_mx, s_cnt, s_last;
+  __shared__ int s_mn, s_mx, s_cnt, s_arrived;
   __shared__ unsigned long long s_sum, s_sq;
   const int tid = threadIdx.x;
   if (hist_mode == 1)
     for (int i = tid; i < hist_len; i += TPB_COUNT) s_hist[i] = 0;
-  if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_cnt = 0; s_sum = 0; s_sq = 0; s_last = 0; }
+  if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_cnt = 0; s_sum = 0; s_sq = 0; s_arrived = 0; }
   __syncthreads();
 
   const int q = blockIdx.x * TPB_COUNT + tid;
@@ -86,9 +98,8 @@ radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __rest
     const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
     unsigned long long pk = 0;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-    walk_block<MERGED>(g, R, cx, cy,
-      [&](int j) {
-        const pg_rec c = pg_ld_rec(g.rec + j);
+    walk_block<MERGED>(g, R, cx, cy, q,
+      [&](int j, const pg_rec& c) {
         const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
         const int a = (d2 <= r2) & (j != q);
         deg += a;
@@ -115,9 +126,8 @@ radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __rest
         int tc[PG_MAX_TYPES];
 #pragma unroll
         for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] = 0;
-        walk_block<MERGED>(g, R, cx, cy,
-          [&](int j) {
-            const pg_rec c = pg_ld_rec(g.rec + j);
+        walk_block<MERGED>(g, R, cx, cy, q,
+          [&](int j, const pg_rec& c) {
             const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
             if (d2 <= r2 && j != q && c.type >= 1 && c.type <= n_types) tc[c.type - 1] += 1;
           },
@@ -128,48 +138,37 @@ radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __rest
     if (hist_mode == 1) atomicAdd(&s_hist[min(deg, hist_len - 1)], 1);
     else if (hist_mode == 2) atomicAdd(&hist[min(deg, hist_len - 1)], 1);
   }
-  if (!stats && hist_mode != 1) return;  // block-uniform
+  if (!stats && hist_mode != 1) return;  // grid-uniform
 
-  // ---- degree statistics: warp -> CTA -> accumulators in the handle
+  // ---- degree statistics: warp -> CTA (shared-memory atomics, no barrier: the last warp to arrive
+  // forwards the CTA's totals) -> accumulators in the handle. The scan that follows publishes them.
   const int wmn = __reduce_min_sync(0xffffffffu, active ? deg : 0x7fffffff);
   const int wmx = __reduce_max_sync(0xffffffffu, active ? deg : -1);
   const int wcnt = __reduce_add_sync(0xffffffffu, active ? 1 : 0);
   const long long wsum = warp_sum_ll(active ? (long long)deg : 0ll);
   const long long wsq = warp_sum_ll(active ? (long long)deg * deg : 0ll);
-  if ((tid & 31) == 0 && wcnt > 0) {
-    atomicMin(&s_mn, wmn); atomicMax(&s_mx, wmx); atomicAdd(&s_cnt, wcnt);
-    atomicAdd(&s_sum, (unsigned long long)wsum); atomicAdd(&s_sq, (unsigned long long)wsq);
+  int last_warp = 0;
+  if ((tid & 31) == 0) {
+    if (wcnt > 0) {
+      atomicMin(&s_mn, wmn); atomicMax(&s_mx, wmx); atomicAdd(&s_cnt, wcnt);
+      atomicAdd(&s_sum, (unsigned long long)wsum); atomicAdd(&s_sq, (unsigned long long)wsq);
+    }
+    __threadfence_block();
+    last_warp = atomicAdd(&s_arrived, 1) == TPB_COUNT / 32 - 1;
   }
-  __syncthreads();
-  if (tid == 0 && s_cnt > 0) {
-    atomicMin(&acc->min_degree, s_mn); atomicMax(&acc->max_degree, s_mx);
-    atomicAdd(&acc->sum_degree, s_sum); atomicAdd(&acc->sumsq_degree, s_sq);
-    atomicAdd(&acc->n_nodes, (unsigned long long)s_cnt);
+  if (!__shfl_sync(0xffffffffu, last_warp, 0)) return;
+  __threadfence_block();
+  if ((tid & 31) == 0 && *(volatile int*)&s_cnt > 0) {
+    atomicMin(&acc->min_degree, *(volatile int*)&s_mn); atomicMax(&acc->max_degree, *(volatile int*)&s_mx);
+    atomicAdd(&acc->sum_degree, *(volatile unsigned long long*)&s_sum);
+    atomicAdd(&acc->sumsq_degree, *(volatile unsigned long long*)&s_sq);
+    atomicAdd(&acc->n_nodes, (unsigned long long)*(volatile int*)&s_cnt);
   }
   if (hist_mode == 1)
-    for (int i = tid; i < hist_len; i += TPB_COUNT) {
-      const int c = s_hist[i];
+    for (int i = tid & 31; i < hist_len; i += 32) {
+      const int c = *(volatile int*)&s_hist[i];
       if (c) atomicAdd(&acc_hist[i], c);
     }
-  // ---- the last CTA to get here publishes the totals and puts the accumulators back into their reset state
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(&acc->done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (hist_mode == 1)
-    for (int i = tid; i < hist_len; i += TPB_COUNT) hist[i] = atomicExch(&acc_hist[i], 0);
-  if (tid == 0) {
-    const int mn = atomicExch(&acc->min_degree, 0x7fffffff), mx = atomicExch(&acc->max_degree, -1);
-    const unsigned long long sm = atomicExch(&acc->sum_degree, 0ull), sq = atomicExch(&acc->sumsq_degree, 0ull);
-    const unsigned long long nn = atomicExch(&acc->n_nodes, 0ull);
-    atomicExch(&acc->done, 0u);
-    if (stats) {
-      stats->min_degree = nn ? mn : 0; stats->max_degree = nn ? mx : 0;
-      stats->sum_degree = (long long)sm; stats->sumsq_degree = (long long)sq; stats->n_nodes = (long long)nn;
-    }
-  }
 }
 
 // nothing to query: the statistics of an empty graph
@@ -228,9 +227,8 @@ radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* _
 
   if (cnt <= FILL_CAP) {
     int m = 0;
-    walk_block<MERGED>(g, R, cx, cy,
-      [&](int j) {
-        const pg_rec c = pg_ld_rec(g.rec + j);
+    walk_block<MERGED>(g, R, cx, cy, q,
+      [&](int j, const pg_rec& c) {
         const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
         if (d2 <= r2 && j != q && (!upper || c.id > me.id) && m < FILL_CAP) {
           s_key[m][tid] = c.id; s_pos[m][tid] = j; ++m;
@@ -254,9 +252,8 @@ radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* _
   int last = upper ? me.id : -1;
   while (emitted < cnt) {
     int m = 0;
-    walk_block<MERGED>(g, R, cx, cy,
-      [&](int j) {
-        const pg_rec c = pg_ld_rec(g.rec + j);
+    walk_block<MERGED>(g, R, cx, cy, q,
+      [&](int j, const pg_rec& c) {
         const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
         if (!(d2 <= r2) || j == q || c.id <= last) return;
         if (m == FILL_CAP) {
@@ -309,7 +306,10 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   if ((rc = pg_reserve(h, h->row_count, ((size_t)nq + 4) * sizeof(int32_t)))) return rc;
   h->radius_r = r;
   h->radius_flags = flags;
+  bool launched = false;
+  int hist_mode_used = 0;
   if (gr.n > 0 && nq > 0) {
+    launched = true;
     pg_grid_view v = pg_make_view(h);
     const int R = ring_radius(r, gr);
     const int upper = flags == PG_RADIUS_UPPER;
@@ -319,13 +319,14 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
       hist_mode = hist_len <= PG_ACC_HIST_MAX ? 1 : 2;
       if (hist_mode == 2) PG_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)hist_len * sizeof(int32_t), s));
     }
+    hist_mode_used = hist_mode;
     pg_stats_acc* acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
     int32_t* acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
     const int blocks = pg_div_up(gr.n, TPB_COUNT);
     const bool wide = nbr_count && n_types > PG_PACKED_TYPES;
 #define PG_COUNT_LAUNCH(M, W)                                                                                   \
   PG_LAUNCH(h, s, "radius_count_kernel", radius_count_kernel<M, W><<<blocks, TPB_COUNT, 0, s>>>(                \
-      v, r * r, R, upper, (int32_t*)h->row_count.p, degree, nbr_count, nt, acc, acc_hist, stats, hist, hist_len, hist_mode))
+      v, r * r, R, upper, (int32_t*)h->row_count.p, degree, nbr_count, nt, acc, acc_hist, stats != nullptr, hist, hist_len, hist_mode))
     if (R == 1 && !wide) PG_COUNT_LAUNCH(true, false);
     else if (R == 1) PG_COUNT_LAUNCH(true, true);
     else if (!wide) PG_COUNT_LAUNCH(false, false);
@@ -336,7 +337,16 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
     PG_LAUNCH(h, s, "empty_stats_kernel", empty_stats_kernel<<<1, 256, 0, s>>>(stats, hist, hist ? hist_len : 0));
     PG_LAUNCH_CHECK(h);
   }
-  return pg_scan_i32(h, (const int32_t*)h->row_count.p, row_ptr, nq, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS));
+  pg_scan_publish pub;
+  if (launched && (stats || hist_mode_used == 1)) {
+    pub.acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
+    pub.acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
+    pub.stats = stats;
+    pub.hist = hist_mode_used == 1 ? hist : nullptr;
+    pub.hist_len = hist_len;
+  }
+  return pg_scan_i32(h, (const int32_t*)h->row_count.p, row_ptr, nq, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS), false,
+                     pub.acc ? &pub : nullptr);
 }
 
 int pg_radius_total(pg_handle* h, int64_t* total) {
