@@ -129,6 +129,9 @@ int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64, float* dis
 int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree,
                     int32_t* nbr_count, int32_t n_types, pg_degree_stats* stats, int32_t* hist,
                     int32_t hist_len, pg_stream stream);
+/* optional, before pg_radius_count: announces how many entries the count pass will have to hold (the caller's
+ * output capacity), so that a sequence enqueued without ever asking for the total cannot run out of scratch */
+int pg_radius_reserve(pg_handle* h, int64_t entries);
 /* synchronises `stream`, returns row_ptr[n_query] of the last count pass */
 int pg_radius_total(pg_handle* h, int64_t* total);
 /* fill pass: col int32 [capacity] ascending per row, dist32 / dist64 (either may be NULL),

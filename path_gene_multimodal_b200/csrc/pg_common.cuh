@@ -18,7 +18,8 @@ struct pg_buf {
 struct pg_grid {
   bool built = false;
   int32_t n = 0, n_query = 0;
-  int32_t nx = 0, ny = 0;
+  int32_t nx = 0, ny = 0;  // logical cell columns / rows
+  int32_t nys = 0;         // strips of PG_STRIP rows (rows are padded up to nys * PG_STRIP; the padding cells are empty)
   double x0 = 0, y0 = 0, cell = 0, inv_cell = 0;
   bool has_gid = false;
 };
@@ -36,21 +37,23 @@ struct pg_handle {
   pg_buf s_rec;        // pg_rec [N]    points in cell order, one 32-byte sector each (see pg_query.cuh)
   pg_buf s_pos;        // int32 [N]     cell-order position of point i (inverse of the counting sort)
   pg_buf s_gid;        // int32 [N]     copy of the caller's gids (only when given), for the fill pass
-  // radius graph: the count pass leaves its results in cell order (one 32-byte pg_row_meta per point plus a
-  // temporary CSR of 16-byte entries); the row scan and the fill pass gather from them in row order
-  pg_buf tmp_meta;     // pg_row_meta [N]
-  pg_buf tmp_ent;      // pg_tmp_ent [tmp_cap]
-  pg_buf row_tmp_off;  // int32 [n_query] offset of row i's entries in tmp_ent
+  // radius graph (pg_radius.cu): the walk leaves one 32-byte pg_pt_meta per point IN CELL ORDER (coalesced) and
+  // parks the accepted entries of each row in tmp_ent; the row pass un-permutes the meta records into row order
+  // (row_ptr scan, degree, type counts, statistics, row_off); the fill pass gathers the parked entries.
+  pg_buf pt_meta;      // pg_pt_meta [N]
+  pg_buf tmp_ent;      // pg_tmp_ent [tmp_cap]: one fixed region per walk CTA, then a shared overflow region
+  pg_buf row_off;      // int32 [n_query] offset of row i's entries in tmp_ent (-1: never parked)
   int64_t tmp_cap = 0;        // entries tmp_ent can hold
-  int64_t tmp_need_hint = 0;  // entries a past count pass needed (grow-only sizing)
-  bool tmp_may_overflow = false;
-  struct {             // arguments of the last count pass, kept so that pg_radius_total can redo it if tmp_ent was too small
+  int32_t tmp_cta_cap = 0;    // entries in one CTA's region
+  int64_t tmp_ovf_base = 0;   // first entry of the overflow region
+  int64_t tmp_hint = 0;       // entries a past count pass produced in total (sizes the CTA regions)
+  int64_t tmp_ovf_hint = 0;   // entries the overflow region must hold (a past pass's need / the caller's capacity)
+  struct {             // arguments of the last count pass, kept so that it can be redone if tmp_ent was too small
     bool valid = false;
     double r = 0; int32_t flags = 0; int32_t* row_ptr = nullptr; int32_t* degree = nullptr; int32_t* nbr_count = nullptr;
     int32_t n_types = 0; pg_degree_stats* stats = nullptr; int32_t* hist = nullptr; int32_t hist_len = 0;
-    cudaStream_t stream = nullptr;
   } last_count;
-  pg_buf row_count;    // int32 [N+1]   per-row counts before the scan
+  pg_buf row_count;    // int32 [N+1]   per-row counts before the scan (K7)
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
   pg_buf sym_extra;    // int32 [N] reverse-only in-degree
@@ -94,8 +97,8 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
-#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 tmp entries needed
-#define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent (zero between count passes)
+#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
+#define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])
 #define PG_MISC_ACC 256       // pg_stats_acc: degree-statistics accumulators kept in their reset state
 #define PG_MISC_ACC_HIST 512  // int32 [PG_ACC_HIST_MAX] histogram accumulators (all zero between launches)
 #define PG_ACC_HIST_MAX 1024
@@ -133,7 +136,7 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
 // clear_in: zero in[0..n) while reading it (the buffer must then be writable)
 // publish: degree statistics to hand to the caller from the scan's first CTA (see pg_radius.cu)
 struct pg_scan_publish {
-  pg_stats_acc* acc = nullptr;
+  pg_stats_acc* acc = nullptr;   // NULL: no statistics to publish
   int32_t* acc_hist = nullptr;
   pg_degree_stats* stats = nullptr;
   int32_t* hist = nullptr;  // NULL: no histogram to publish
@@ -144,7 +147,19 @@ int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaSt
 
 static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Cell order. Cells are numbered strip by strip (a strip = PG_STRIP grid rows), column-major inside a strip:
+//   c = ((cy / PG_STRIP) * nx + cx) * PG_STRIP + cy % PG_STRIP.
+// Consecutive cells - and so consecutive points of the cell-ordered array - sweep a strip column by column,
+// which keeps the neighbourhoods of a warp's / CTA's points in a compact, roughly square patch (L1 reuse),
+// and the rows cy-1..cy+1 of one column are one contiguous run of the array unless they cross a strip edge.
+#define PG_STRIP_LOG 5
+#define PG_STRIP (1 << PG_STRIP_LOG)
+
 #ifdef __CUDACC__
+__host__ __device__ __forceinline__ int pg_cell_index(int nx, int cx, int cy) {
+  return ((((cy >> PG_STRIP_LOG) * nx) + cx) << PG_STRIP_LOG) + (cy & (PG_STRIP - 1));
+}
+
 // cell coordinate along one axis: identical expression everywhere a point is binned.
 __device__ __forceinline__ int pg_cell_coord(double v, double v0, double inv_cell, int n_cells) {
   double t = __dmul_rn(__dsub_rn(v, v0), inv_cell);

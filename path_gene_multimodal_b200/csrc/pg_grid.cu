@@ -2,6 +2,9 @@
 // (pg_scan.cu), counting-sort scatter. Plays the role of the cKDTree build at
 // /root/reference/hovernet_tile_inference.ipynb:1818 (KNN.from_array) and :2964 (cKDTree(coords)).
 //
+// Cells are numbered strip by strip, column-major inside a strip (pg_common.cuh: pg_cell_index), so the
+// cell-ordered array keeps spatial neighbours close in memory along BOTH axes.
+//
 // Passes over the points: (1) histogram with fire-and-forget atomics (nothing written per point),
 // (2) scatter that re-derives the cell and claims its slot with one atomicAdd on the scanned array.
 // The scan writes start(c) into B[c+1] (B[0] = 0 stays put); after the scatter's cursor increments
@@ -52,34 +55,87 @@ __global__ void init_bounds_kernel(unsigned long long* keys) {
   keys[2] = keys[3] = 0ull;
 }
 
-// K2: one thread per point, reduction atomics (no return value, nothing else written)
+// K2: PTS points per thread (independent 256-bit loads in flight, one wave of CTAs for 1M points), reduction
+// atomics (no return value, nothing else written)
+constexpr int PTS = 4;
+__device__ __forceinline__ void ld_xy2(const double2* p, double2& a, double2& b) {
+  unsigned long long x0, y0, x1, y1;
+  asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(y0), "=l"(x1), "=l"(y1) : "l"(p));
+  a = make_double2(__longlong_as_double((long long)x0), __longlong_as_double((long long)y0));
+  b = make_double2(__longlong_as_double((long long)x1), __longlong_as_double((long long)y1));
+}
+
+// the PTS points of thread t of CTA b are b*TPB*PTS + k*TPB*2 + t*2 + {0,1} (k < PTS/2): pairs, so that a warp's
+// 256-bit loads are contiguous
+__device__ __forceinline__ void load_points(const double2* __restrict__ xy, int n, bool aligned32, int base, double2 (&p)[PTS]) {
+#pragma unroll
+  for (int k = 0; k < PTS / 2; ++k) {
+    const int i = base + k * TPB * 2;
+    if (aligned32 && i + 1 < n) {
+      ld_xy2(xy + i, p[2 * k], p[2 * k + 1]);
+    } else {
+      if (i < n) p[2 * k] = xy[i];
+      if (i + 1 < n) p[2 * k + 1] = xy[i + 1];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB)
-histogram_kernel(const double2* __restrict__ xy, int n, double x0, double y0, double inv_cell, int nx, int ny,
+histogram_kernel(const double2* __restrict__ xy, int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny,
                  int32_t* __restrict__ cell_count) {
-  const int i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  const double2 p = xy[i];
-  const int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
-  atomicAdd(&cell_count[c], 1);
+  const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
+  double2 p[PTS];
+  load_points(xy, n, aligned32, base, p);
+#pragma unroll
+  for (int k = 0; k < PTS; ++k) {
+    const int i = base + (k >> 1) * TPB * 2 + (k & 1);
+    if (i < n) {
+      const int c = pg_cell_index(nx, pg_cell_coord(p[k].x, x0, inv_cell, nx), pg_cell_coord(p[k].y, y0, inv_cell, ny));
+      atomicAdd(&cell_count[c], 1);
+    }
+  }
 }
 
 // K4: counting-sort scatter into cell order: one 32-byte record per point, written as one full sector.
-// cursor = B + 1: cursor[c] starts as start(c) and ends as start(c+1).
+// cursor = B + 1: cursor[c] starts as start(c) and ends as start(c+1). PTS points per thread, as in K2.
 __global__ void __launch_bounds__(TPB)
 scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
-               int n, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
+               int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
                pg_rec* __restrict__ rec, int32_t* __restrict__ pos, int32_t* __restrict__ gid_copy) {
-  const int i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  const double2 p = xy[i];
-  const int t = type ? type[i] : 0;
-  const int id = gid ? gid[i] : i;
-  const int c = pg_cell_coord(p.y, y0, inv_cell, ny) * nx + pg_cell_coord(p.x, x0, inv_cell, nx);
-  const int dst = atomicAdd(&cursor[c], 1);
-  const int tshift = (t >= 1 && t <= PG_PACKED_TYPES) ? (t - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
-  pg_st_rec(rec + dst, p.x, p.y, i, id, t, tshift);
-  pos[i] = dst;
-  if (gid) gid_copy[i] = id;
+  const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // sentinel behind the last record: infinitely far from everything (the queries pad their loads with it)
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    pg_st_rec(rec + n, inf, inf, 0x7fffffff, -1, 0, PG_TYPE_OTHER_SHIFT);
+  }
+  double2 p[PTS];
+  int t[PTS], id[PTS], dst[PTS];
+  load_points(xy, n, aligned32, base, p);
+#pragma unroll
+  for (int k = 0; k < PTS; ++k) {
+    const int i = base + (k >> 1) * TPB * 2 + (k & 1);
+    t[k] = (type && i < n) ? type[i] : 0;
+    id[k] = i < n ? (gid ? gid[i] : i) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < PTS; ++k) {
+    const int i = base + (k >> 1) * TPB * 2 + (k & 1);
+    dst[k] = 0;
+    if (i < n) {
+      const int c = pg_cell_index(nx, pg_cell_coord(p[k].x, x0, inv_cell, nx), pg_cell_coord(p[k].y, y0, inv_cell, ny));
+      dst[k] = atomicAdd(&cursor[c], 1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PTS; ++k) {
+    const int i = base + (k >> 1) * TPB * 2 + (k & 1);
+    if (i < n) {
+      const int tshift = (t[k] >= 1 && t[k] <= PG_PACKED_TYPES) ? (t[k] - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
+      pg_st_rec(rec + dst[k], p[k].x, p[k].y, i, id[k], t[k], tshift);
+      pos[i] = dst[k];
+      if (gid) gid_copy[i] = id[k];
+    }
+  }
 }
 
 }  // namespace
@@ -123,16 +179,20 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   // derive their ring radius from the actual cell size), never changes results.
   const double max_cells = std::min((double)(1 << 28), std::max(8.0 * (double)n, (double)(1 << 20)));
   double cell = cell_size;
-  int64_t nx, ny;
+  int64_t nx, ny, nys;
   while (true) {
-    nx = (int64_t)std::floor((b[2] - b[0]) / cell) + 1;
-    ny = (int64_t)std::floor((b[3] - b[1]) / cell) + 1;
-    if ((double)nx * (double)ny <= max_cells) break;
+    const double fx = std::floor((b[2] - b[0]) / cell) + 1, fy = std::floor((b[3] - b[1]) / cell) + 1;
+    const double fys = std::ceil(fy / PG_STRIP);
+    // rows are padded to whole strips: the padded count may reach 4 x the cap for thin grids (< 2^30 either way)
+    if (fx * fy <= max_cells && fx * fys * PG_STRIP <= 4.0 * max_cells) {
+      nx = (int64_t)fx; ny = (int64_t)fy; nys = (int64_t)fys;
+      break;
+    }
     cell *= 2.0;
   }
-  const int64_t cells = nx * ny;
+  const int64_t cells = nx * nys * PG_STRIP;
   pg_grid& g = h->grid;
-  g.n = n; g.n_query = n_query; g.nx = (int)nx; g.ny = (int)ny;
+  g.n = n; g.n_query = n_query; g.nx = (int)nx; g.ny = (int)ny; g.nys = (int)nys;
   g.x0 = b[0]; g.y0 = b[1]; g.cell = cell; g.inv_cell = 1.0 / cell; g.has_gid = gid != nullptr;
 
   int rc;
@@ -144,10 +204,11 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     if ((rc = pg_reserve(h, h->cell_start, cs_need))) return rc;
     PG_CUDA(h, cudaMemsetAsync(h->cell_start.p, 0, 16, s));  // B[0] = 0 (and the alignment pad) once per allocation
   }
-  if ((rc = pg_reserve(h, h->s_rec, (size_t)(n + 1) * sizeof(pg_rec)))) return rc;
-  if ((rc = pg_reserve(h, h->s_pos, (size_t)(n + 4) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->s_rec, (size_t)(n + 2) * sizeof(pg_rec)))) return rc;
+  if ((rc = pg_reserve(h, h->s_pos, (size_t)(n + 8) * sizeof(int32_t)))) return rc;
   if (gid && (rc = pg_reserve(h, h->s_gid, (size_t)(n + 4) * sizeof(int32_t)))) return rc;
   h->last_count.valid = false;
+  const bool aligned32 = ((uintptr_t)xy & 31) == 0;
   int32_t* B = (int32_t*)h->cell_start.p + 3;  // B[0] = 0, B + 1 is 16-byte aligned for the scan
 
   // the histogram is all zero between builds: the scan below clears every counter it reads
@@ -156,8 +217,8 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     h->cell_count_clean = true;
   }
   if (n > 0) {
-    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
-        (const double2*)xy, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p));
+    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB * PTS), TPB, 0, s>>>(
+        (const double2*)xy, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p));
     PG_LAUNCH_CHECK(h);
   }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, B + 1, (int32_t)cells, s, nullptr, true))) {
@@ -165,8 +226,8 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     return rc;
   }
   if (n > 0) {
-    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
-        (const double2*)xy, type, gid, n, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p,
+    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB * PTS), TPB, 0, s>>>(
+        (const double2*)xy, type, gid, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p,
         (int32_t*)h->s_pos.p, gid ? (int32_t*)h->s_gid.p : nullptr));
     PG_LAUNCH_CHECK(h);
   }

@@ -20,7 +20,7 @@ struct __align__(32) pg_rec {
 struct pg_grid_view {
   const int32_t* __restrict__ cell_start;
   const pg_rec* __restrict__ rec;
-  int32_t n, n_query, nx, ny;
+  int32_t n, n_query, nx, ny, nys;
   double x0, y0, cell, inv_cell;
 };
 
@@ -28,7 +28,7 @@ static inline pg_grid_view pg_make_view(const pg_handle* h) {
   pg_grid_view v;
   v.cell_start = (const int32_t*)h->cell_start.p + 3;  // see pg_grid.cu: B[c] = first point of cell c
   v.rec = (const pg_rec*)h->s_rec.p;
-  v.n = h->grid.n; v.n_query = h->grid.n_query; v.nx = h->grid.nx; v.ny = h->grid.ny;
+  v.n = h->grid.n; v.n_query = h->grid.n_query; v.nx = h->grid.nx; v.ny = h->grid.ny; v.nys = h->grid.nys;
   v.x0 = h->grid.x0; v.y0 = h->grid.y0; v.cell = h->grid.cell; v.inv_cell = h->grid.inv_cell;
   return v;
 }
@@ -54,30 +54,37 @@ __device__ __forceinline__ void pg_st_rec(pg_rec* p, double x, double y, int row
 }
 __device__ __forceinline__ double2 pg_ld_xy(const pg_rec* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// Visit the (2R+1)^2 block of cells around (cx, cy) as 2R+1 contiguous runs of the cell-ordered
-// point array (cells are row-major, so one grid row of the block is one run).
+// Rows ya..yb (inclusive, inside the grid) of column x as contiguous runs of the cell-ordered array: one run
+// per strip touched (see the cell order in pg_common.cuh).
+template <class F>
+__device__ __forceinline__ void pg_visit_column(const pg_grid_view& g, int x, int ya, int yb, F&& f) {
+  for (int s = ya >> PG_STRIP_LOG; s <= (yb >> PG_STRIP_LOG); ++s) {
+    const int s0 = s << PG_STRIP_LOG;
+    const int la = max(ya, s0) - s0, lb = min(yb, s0 + PG_STRIP - 1) - s0;
+    const int32_t* c = g.cell_start + (((int64_t)s * g.nx + x) << PG_STRIP_LOG);
+    f(c[la], c[lb + 1]);
+  }
+}
+
+// Visit the (2R+1)^2 block of cells around (cx, cy).
 template <class F>
 __device__ __forceinline__ void pg_visit_block(const pg_grid_view& g, int cx, int cy, int R, F&& f) {
   const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
   const int ya = max(cy - R, 0), yb = min(cy + R, g.ny - 1);
-  for (int y = ya; y <= yb; ++y) {
-    const int row = y * g.nx;
-    f(g.cell_start[row + xa], g.cell_start[row + xb + 1]);
-  }
+  for (int x = xa; x <= xb; ++x) pg_visit_column(g, x, ya, yb, f);
 }
 
 // Visit only the ring at Chebyshev distance exactly R (R >= 1) around (cx, cy).
 template <class F>
 __device__ __forceinline__ void pg_visit_ring(const pg_grid_view& g, int cx, int cy, int R, F&& f) {
-  const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
-  if (cy - R >= 0) { const int row = (cy - R) * g.nx; f(g.cell_start[row + xa], g.cell_start[row + xb + 1]); }
-  if (cy + R < g.ny) { const int row = (cy + R) * g.nx; f(g.cell_start[row + xa], g.cell_start[row + xb + 1]); }
-  const int ya = max(cy - R + 1, 0), yb = min(cy + R - 1, g.ny - 1);
-  const bool left = cx - R >= 0, right = cx + R < g.nx;
-  for (int y = ya; y <= yb; ++y) {
-    const int row = y * g.nx;
-    if (left) f(g.cell_start[row + cx - R], g.cell_start[row + cx - R + 1]);
-    if (right) f(g.cell_start[row + cx + R], g.cell_start[row + cx + R + 1]);
+  const int ya = max(cy - R, 0), yb = min(cy + R, g.ny - 1);
+  if (cx - R >= 0) pg_visit_column(g, cx - R, ya, yb, f);
+  if (cx + R < g.nx) pg_visit_column(g, cx + R, ya, yb, f);
+  const int xa = max(cx - R + 1, 0), xb = min(cx + R - 1, g.nx - 1);
+  const bool top = cy - R >= 0, bottom = cy + R < g.ny;
+  for (int x = xa; x <= xb; ++x) {
+    if (top) { const int c = pg_cell_index(g.nx, x, cy - R); f(g.cell_start[c], g.cell_start[c + 1]); }
+    if (bottom) { const int c = pg_cell_index(g.nx, x, cy + R); f(g.cell_start[c], g.cell_start[c + 1]); }
   }
 }
 

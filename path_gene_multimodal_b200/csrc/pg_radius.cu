@@ -1,63 +1,134 @@
-// K6 radius graph (two-pass count / scan / fill CSR) with K8 (neighbour-type histogram + degree
-// statistics) fused into the count pass.
+// K6 radius graph with K8 (neighbour-type histogram + degree statistics) fused in.
 // Reference: /root/reference/hovernet_tile_inference.ipynb:2964-2975 (cKDTree.query_ball_tree, i<j edge
 // loop), :3021 (edge_index), :3041-3042 (np.linalg.norm distances, float32 edge_attr); composition /
 // degree per SURVEY A.5. Acceptance test is d2 <= r*r in float64 with d2 = fl(fl(dx*dx)+fl(dy*dy)).
 //
-// Work split: one thread per point, in cell order, so the 32 lanes of a warp sit in the same or adjacent
-// cells and their candidate records (one 32-byte sector each, read with one 256-bit load) hit in L1.
-// With the usual cell ~ r the 3x3 block of a point is three contiguous runs of the cell-ordered array;
-// they are walked as ONE merged loop (a branch-free index map) so a warp iterates max-over-lanes of the
-// block population once instead of three times. The count pass keeps the per-type neighbour counts in
-// 12-bit fields of one 64-bit register (the field offset is precomputed in the record); degree statistics
-// are reduced per warp, then per CTA (no barrier), then added to accumulators in the handle which the row_ptr
-// scan that follows publishes and resets - no init / finish launches. The fill pass collects a row's accepted (id, position) pairs
-// in shared memory (slot-major, conflict-free), sorts the handful of entries by id and writes the row.
+// The CSR is built count -> scan -> fill, but every neighbourhood is walked only ONCE and all scattered
+// traffic is confined to two single-instruction gathers:
+//   walk   (pg_radius_count, kernel 1) one thread per point in CELL order. Cells are strip-ordered
+//          (pg_common.cuh), so the lanes of a warp / the threads of a CTA sit in a compact patch and their
+//          candidate records (one 32-byte sector each, one 256-bit load) hit in L1. With cell ~ r the 3x3 block
+//          of a point is three contiguous runs (one per cell column), walked as ONE merged loop with four loads
+//          in flight; the points on a strip edge add a short second loop over the three cells across the edge.
+//          Loads past the end of a run are pointed at a sentinel record at infinity, and a point meets itself
+//          like any other candidate (undone once after the loop), so the loop body has no special cases.
+//          Per point it leaves ONE 32-byte pg_pt_meta {degree, entries, offset, 5 type counts} at its cell-order
+//          position (a full-sector coalesced store) and parks the row's accepted (id, d2) entries - staged in a
+//          small shared-memory slab - in the CTA's own region of a temporary array (space claimed with a
+//          shared-memory atomic per warp; a shared overflow region takes what does not fit).
+//   rows   (pg_radius_count, kernel 2) one thread per ROW: follows pos[row] to the point's meta record (the one
+//          scattered access, a single 256-bit load) and writes row_ptr (decoupled look-back scan of the entry
+//          counts), degree, nbr_count and row_off coalesced; the degree statistics / histogram are reduced
+//          here too (CTA -> accumulators; the last CTA publishes them and re-arms the accumulators).
+//   gather (pg_radius_fill) warp-flattened over 32 rows: lane p of the warp's contiguous output range finds its
+//          row by a 5-step shuffle search, reads one parked entry, ranks it among the row's entries by counting
+//          smaller ids (rows are short; ids are distinct) and writes col / dist / edges fully coalesced.
 #include <cmath>
+#include <cstring>
+#include <algorithm>
 #include "pg_query.cuh"
+#include "pg_scan.cuh"
 
 namespace {
 
-constexpr int TPB_COUNT = 256;
-constexpr int TPB_FILL = 128;
-constexpr int FILL_CAP = 16;         // row entries kept per thread in shared memory (2 x 4 B x CAP x TPB_FILL = 16 KB)
+constexpr int TPB_WALK = 128;
+constexpr int SLAB = 8;              // row entries staged per thread in shared memory (12 B x SLAB x TPB_WALK = 12 KB)
+constexpr int TPB_ROWS = 256;
+constexpr int ROWS_ITEMS = 4;
+constexpr int ROWS_TILE = TPB_ROWS * ROWS_ITEMS;
+constexpr int TPB_GATHER = 256;
 constexpr int FIELD_MAX = (1 << PG_TYPE_BITS) - 1;
 
-// Calls f(position, record) for every candidate of the (2R+1)^2 block around (cx, cy) and flush() at least
-// once every FIELD_MAX candidates (and once at the end). Records are fetched four at a time so that four
-// 256-bit loads are in flight per thread; the slots past the end of a run are pointed at `self`, the
-// caller's own position, which every f rejects anyway (a point is not its own neighbour).
-template <bool MERGED, class F, class FL>
-__device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx, int cy, int self, F&& f, FL&& flush) {
-  if (MERGED) {  // R == 1: three runs, one loop
-    const int xa = max(cx - 1, 0), xe = min(cx + 1, g.nx - 1) + 1;
-    const int32_t* c1 = g.cell_start + (int64_t)cy * g.nx;
-    const int b1 = c1[xa], e1 = c1[xe];
-    int b0 = 0, e0 = 0, b2 = 0, e2 = 0;
-    if (cy > 0) { b0 = c1[xa - g.nx]; e0 = c1[xe - g.nx]; }
-    if (cy + 1 < g.ny) { b2 = c1[xa + g.nx]; e2 = c1[xe + g.nx]; }
-    const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
-    const int off1 = b1 - n0, off2 = b2 - n01;
-    auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b0 : (t < n01 ? off1 : off2)) : self; };
-    for (int t0 = 0; t0 < tot; t0 += FIELD_MAX - 3) {  // FIELD_MAX - 3 is a multiple of 4
-      const int t1 = min(tot, t0 + FIELD_MAX - 3);
-      for (int t = t0; t < t1; t += 4) {
-        const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
-        const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
-        const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
-        f(j0, r0); f(j1, r1); f(j2, r2); f(j3, r3);
+struct __align__(16) pg_tmp_ent {
+  double d2;
+  int32_t id;
+  int32_t pad;
+};
+
+struct __align__(32) pg_pt_meta {
+  int32_t deg, cnt, off;
+  int32_t c[PG_PACKED_TYPES];
+};
+static_assert(sizeof(pg_pt_meta) == 32, "pg_pt_meta must be one sector");
+
+__device__ __forceinline__ void st_meta(pg_pt_meta* p, const pg_pt_meta& m) {
+  const unsigned long long a = (unsigned long long)(uint32_t)m.deg | ((unsigned long long)(uint32_t)m.cnt << 32);
+  const unsigned long long b = (unsigned long long)(uint32_t)m.off | ((unsigned long long)(uint32_t)m.c[0] << 32);
+  const unsigned long long c = (unsigned long long)(uint32_t)m.c[1] | ((unsigned long long)(uint32_t)m.c[2] << 32);
+  const unsigned long long d = (unsigned long long)(uint32_t)m.c[3] | ((unsigned long long)(uint32_t)m.c[4] << 32);
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ pg_pt_meta ld_meta(const pg_pt_meta* p) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  pg_pt_meta m;
+  m.deg = (int32_t)(uint32_t)a; m.cnt = (int32_t)(uint32_t)(a >> 32);
+  m.off = (int32_t)(uint32_t)b; m.c[0] = (int32_t)(uint32_t)(b >> 32);
+  m.c[1] = (int32_t)(uint32_t)c; m.c[2] = (int32_t)(uint32_t)(c >> 32);
+  m.c[3] = (int32_t)(uint32_t)d; m.c[4] = (int32_t)(uint32_t)(d >> 32);
+  return m;
+}
+
+// Merged walk over three runs [b0,e0) [b1,e1) [b2,e2) of the record array: f(record) for every slot; the
+// slots past the end read the sentinel record at `pad` (infinitely far away, rejected by every f).
+// flush() at least once every FIELD_MAX slots and once at the end.
+template <class F, class FL>
+__device__ __forceinline__ void walk_runs3(const pg_rec* __restrict__ rec, int b0, int e0, int b1, int e1, int b2, int e2,
+                                           int pad, F&& f, FL&& flush) {
+  const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
+  const int off1 = b1 - n0, off2 = b2 - n01;
+  auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b0 : (t < n01 ? off1 : off2)) : pad; };
+  for (int t0 = 0; t0 < tot; t0 += FIELD_MAX - 3) {  // FIELD_MAX - 3 is a multiple of 4
+    const int t1 = min(tot, t0 + FIELD_MAX - 3);
+    for (int t = t0; t < t1; t += 4) {
+      const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+      const pg_rec r0 = pg_ld_rec(rec + j0), r1 = pg_ld_rec(rec + j1);
+      const pg_rec r2 = pg_ld_rec(rec + j2), r3 = pg_ld_rec(rec + j3);
+      f(r0); f(r1); f(r2); f(r3);
+    }
+    flush();
+  }
+}
+
+// Every candidate of the (2R+1)^2 block around (cx, cy), the query point itself included.
+template <bool FAST, class F, class FL>
+__device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx, int cy, F&& f, FL&& flush) {
+  const int pad = g.n;  // the sentinel record
+  if (FAST) {           // R == 1
+    const int sy = cy >> PG_STRIP_LOG, ly = cy & (PG_STRIP - 1);
+    const bool has_l = cx > 0, has_r = cx + 1 < g.nx;
+    // pass 0: rows ly-1..ly+1 of the columns cx-1..cx+1 inside this strip (column x+1 starts PG_STRIP cells
+    // after column x); pass 1 (strip-edge points only): the one row across the edge, in the adjacent strip
+    int edge = -1;
+    if (ly == 0 && sy > 0) edge = (((sy - 1) * g.nx + cx) << PG_STRIP_LOG) + PG_STRIP - 1;
+    else if (ly == PG_STRIP - 1 && sy + 1 < g.nys) edge = ((sy + 1) * g.nx + cx) << PG_STRIP_LOG;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int32_t* c;
+      int lo, hi;
+      if (pass == 0) {
+        c = g.cell_start + ((sy * g.nx + cx) << PG_STRIP_LOG);
+        lo = max(ly - 1, 0); hi = min(ly + 1, PG_STRIP - 1) + 1;
+      } else {
+        if (edge < 0) break;
+        c = g.cell_start + edge;
+        lo = 0; hi = 1;
       }
-      flush();
+      const int b1 = c[lo], e1 = c[hi];
+      int b0 = 0, e0 = 0, b2 = 0, e2 = 0;
+      if (has_l) { b0 = c[lo - PG_STRIP]; e0 = c[hi - PG_STRIP]; }
+      if (has_r) { b2 = c[lo + PG_STRIP]; e2 = c[hi + PG_STRIP]; }
+      walk_runs3(g.rec, b0, e0, b1, e1, b2, e2, pad, f, flush);
     }
   } else {
     pg_visit_block(g, cx, cy, R, [&](int b, int e) {
       for (int j0 = b; j0 < e; j0 += FIELD_MAX - 3) {
         const int j1 = min(e, j0 + FIELD_MAX - 3);
         for (int j = j0; j < j1; j += 4) {
-          const int p0 = j, p1 = j + 1 < j1 ? j + 1 : self, p2 = j + 2 < j1 ? j + 2 : self, p3 = j + 3 < j1 ? j + 3 : self;
-          const pg_rec r0 = pg_ld_rec(g.rec + p0), r1 = pg_ld_rec(g.rec + p1);
+          const int p1 = j + 1 < j1 ? j + 1 : pad, p2 = j + 2 < j1 ? j + 2 : pad, p3 = j + 3 < j1 ? j + 3 : pad;
+          const pg_rec r0 = pg_ld_rec(g.rec + j), r1 = pg_ld_rec(g.rec + p1);
           const pg_rec r2 = pg_ld_rec(g.rec + p2), r3 = pg_ld_rec(g.rec + p3);
-          f(p0, r0); f(p1, r1); f(p2, r2); f(p3, r3);
+          f(r0); f(r1); f(r2); f(r3);
         }
         flush();
       }
@@ -65,116 +136,302 @@ __device__ __forceinline__ void walk_block(const pg_grid_view& g, int R, int cx,
   }
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
+struct walk_out {
+  pg_pt_meta* __restrict__ meta;
+  pg_tmp_ent* __restrict__ tmp;
+  int cta_cap;                       // entries in one CTA's region of tmp
+  unsigned long long ovf_base;       // first entry of the overflow region
+  unsigned long long ovf_cap;        // entries in the overflow region
+  unsigned long long* ovf_cursor;
+  int32_t* __restrict__ nbr_count;   // only the WIDE_TYPES variant writes the type counts itself
+  int n_types;
+};
 
-// Count pass: CSR row count (all neighbours, or only id_j > id_i when `upper`) and, fused over all
-// neighbours: degree, per-type neighbour counts, degree statistics and histogram.
-// hist_mode 0: no histogram; 1: shared-memory bins -> accumulators -> published by the scan that follows;
-// 2: hist_len > PG_ACC_HIST_MAX, bins added straight into the caller's (pre-zeroed) array.
-template <bool MERGED, bool WIDE_TYPES>
-__global__ void __launch_bounds__(TPB_COUNT)
-radius_count_kernel(pg_grid_view g, double r2, int R, int upper, int32_t* __restrict__ row_count,
-                    int32_t* __restrict__ degree, int32_t* __restrict__ nbr_count, int n_types,
-                    pg_stats_acc* acc, int32_t* acc_hist, bool stats, int32_t* hist, int hist_len, int hist_mode) {
-  __shared__ int s_hist[PG_ACC_HIST_MAX];
-  __shared__ int s_mn, s_mx, s_cnt, s_arrived;
-  __shared__ unsigned long long s_sum, s_sq;
-  const int tid = threadIdx.x;
-  if (hist_mode == 1)
-    for (int i = tid; i < hist_len; i += TPB_COUNT) s_hist[i] = 0;
-  if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_cnt = 0; s_sum = 0; s_sq = 0; s_arrived = 0; }
+// Entries kept: all neighbours (UPPER = false) or only id_j > id_i; degree and type counts are over all neighbours.
+template <bool FAST, bool UPPER, bool WIDE_TYPES>
+__global__ void __launch_bounds__(TPB_WALK, 8)
+radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
+  __shared__ double s_d2[SLAB][TPB_WALK];
+  __shared__ int s_key[SLAB][TPB_WALK];
+  __shared__ int s_alloc;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_alloc = 0;
   __syncthreads();
 
-  const int q = blockIdx.x * TPB_COUNT + tid;
+  const int q = blockIdx.x * TPB_WALK + tid;
   const pg_rec me = pg_ld_rec(g.rec + min(q, g.n - 1));
   const bool active = q < g.n && me.row < g.n_query;  // halo points own no row
-  int deg = 0, up = 0;
+  int cnt = 0, cx = 0, cy = 0;
+  pg_pt_meta m;
+  m.deg = 0; m.cnt = 0; m.off = -1;
+#pragma unroll
+  for (int t = 0; t < PG_PACKED_TYPES; ++t) m.c[t] = 0;
   if (active) {
-    const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
-    const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
+    cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
+    cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
     unsigned long long pk = 0;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-    walk_block<MERGED>(g, R, cx, cy, q,
-      [&](int j, const pg_rec& c) {
+    int deg = 0;
+    walk_block<FAST>(g, R, cx, cy,
+      [&](const pg_rec& c) {
         const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
-        const int a = (d2 <= r2) & (j != q);
+        const bool a = d2 <= r2;
         deg += a;
-        up += a & (c.id > me.id);
         pk += (unsigned long long)a << c.tshift;
+        if (a && (UPPER ? c.id > me.id : c.id != me.id)) {
+          if (cnt < SLAB) { s_key[cnt][tid] = c.id; s_d2[cnt][tid] = d2; }
+          ++cnt;
+        }
       },
       [&]() {
-        c0 += (int)(pk & FIELD_MAX); c1 += (int)((pk >> PG_TYPE_BITS) & FIELD_MAX);
-        c2 += (int)((pk >> (2 * PG_TYPE_BITS)) & FIELD_MAX); c3 += (int)((pk >> (3 * PG_TYPE_BITS)) & FIELD_MAX);
-        c4 += (int)((pk >> (4 * PG_TYPE_BITS)) & FIELD_MAX);
+#pragma unroll
+        for (int t = 0; t < PG_PACKED_TYPES; ++t) m.c[t] += (int)((pk >> (t * PG_TYPE_BITS)) & FIELD_MAX);
         pk = 0;
       });
-    row_count[me.row] = upper ? up : deg;
-    if (degree) degree[me.row] = deg;
-    if (nbr_count) {
-      int32_t* o = nbr_count + (int64_t)me.row * n_types;
-      if (!WIDE_TYPES) {
-        o[0] = c0;
-        if (n_types > 1) o[1] = c1;
-        if (n_types > 2) o[2] = c2;
-        if (n_types > 3) o[3] = c3;
-        if (n_types > 4) o[4] = c4;
-      } else {  // more than PG_PACKED_TYPES types: a second walk with counters in local memory (rare)
-        int tc[PG_MAX_TYPES];
+    // the point met itself (d2 = 0 unless a coordinate is not finite): take it out again
+    const int self = pg_dist2(me.x, me.y, me.x, me.y) <= r2;
+    m.deg = deg - self;
+    const unsigned long long own = (unsigned long long)self << me.tshift;
 #pragma unroll
-        for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] = 0;
-        walk_block<MERGED>(g, R, cx, cy, q,
-          [&](int j, const pg_rec& c) {
-            const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
-            if (d2 <= r2 && j != q && c.type >= 1 && c.type <= n_types) tc[c.type - 1] += 1;
-          },
-          [&]() {});
-        for (int t = 0; t < n_types; ++t) o[t] = tc[t];
-      }
+    for (int t = 0; t < PG_PACKED_TYPES; ++t) m.c[t] -= (int)((own >> (t * PG_TYPE_BITS)) & FIELD_MAX);
+    m.cnt = cnt;
+    if (WIDE_TYPES) {  // more than PG_PACKED_TYPES types: a second walk with counters in local memory (rare)
+      int tc[PG_MAX_TYPES];
+#pragma unroll
+      for (int t = 0; t < PG_MAX_TYPES; ++t) tc[t] = 0;
+      walk_block<FAST>(g, R, cx, cy,
+        [&](const pg_rec& c) {
+          const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+          if (d2 <= r2 && c.id != me.id && c.type >= 1 && c.type <= o.n_types) tc[c.type - 1] += 1;
+        },
+        [&]() {});
+      for (int t = 0; t < o.n_types; ++t) o.nbr_count[(int64_t)me.row * o.n_types + t] = tc[t];
     }
-    if (hist_mode == 1) atomicAdd(&s_hist[min(deg, hist_len - 1)], 1);
-    else if (hist_mode == 2) atomicAdd(&hist[min(deg, hist_len - 1)], 1);
   }
-  if (!stats && hist_mode != 1) return;  // grid-uniform
 
-  // ---- degree statistics: warp -> CTA (shared-memory atomics, no barrier: the last warp to arrive
-  // forwards the CTA's totals) -> accumulators in the handle. The scan that follows publishes them.
-  const int wmn = __reduce_min_sync(0xffffffffu, active ? deg : 0x7fffffff);
-  const int wmx = __reduce_max_sync(0xffffffffu, active ? deg : -1);
-  const int wcnt = __reduce_add_sync(0xffffffffu, active ? 1 : 0);
-  const long long wsum = warp_sum_ll(active ? (long long)deg : 0ll);
-  const long long wsq = warp_sum_ll(active ? (long long)deg * deg : 0ll);
-  int last_warp = 0;
-  if ((tid & 31) == 0) {
-    if (wcnt > 0) {
-      atomicMin(&s_mn, wmn); atomicMax(&s_mx, wmx); atomicAdd(&s_cnt, wcnt);
-      atomicAdd(&s_sum, (unsigned long long)wsum); atomicAdd(&s_sq, (unsigned long long)wsq);
-    }
-    __threadfence_block();
-    last_warp = atomicAdd(&s_arrived, 1) == TPB_COUNT / 32 - 1;
+  // ---- park the row's entries: the warp claims space in the CTA's region with one shared-memory atomic
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
   }
-  if (!__shfl_sync(0xffffffffu, last_warp, 0)) return;
-  __threadfence_block();
-  if ((tid & 31) == 0 && *(volatile int*)&s_cnt > 0) {
-    atomicMin(&acc->min_degree, *(volatile int*)&s_mn); atomicMax(&acc->max_degree, *(volatile int*)&s_mx);
-    atomicAdd(&acc->sum_degree, *(volatile unsigned long long*)&s_sum);
-    atomicAdd(&acc->sumsq_degree, *(volatile unsigned long long*)&s_sq);
-    atomicAdd(&acc->n_nodes, (unsigned long long)*(volatile int*)&s_cnt);
-  }
-  if (hist_mode == 1)
-    for (int i = tid & 31; i < hist_len; i += 32) {
-      const int c = *(volatile int*)&s_hist[i];
-      if (c) atomicAdd(&acc_hist[i], c);
+  const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+  long long wbase = -1;
+  if (lane == 0 && wtot > 0) {
+    const int loc = atomicAdd(&s_alloc, wtot);
+    if (loc + wtot <= o.cta_cap) {
+      wbase = (long long)blockIdx.x * o.cta_cap + loc;
+    } else {  // the CTA's region is full: shared overflow region (the cursor keeps counting past its end)
+      const unsigned long long at = atomicAdd(o.ovf_cursor, (unsigned long long)wtot);
+      if (at + (unsigned long long)wtot <= o.ovf_cap) wbase = (long long)(o.ovf_base + at);
     }
+  }
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  if (!active) return;
+  if (wbase >= 0 && cnt > 0) {
+    const long long off = wbase + (incl - cnt);
+    m.off = (int)off;
+    pg_tmp_ent* dst = o.tmp + off;
+    if (cnt <= SLAB) {
+      for (int t = 0; t < cnt; ++t) {
+        pg_tmp_ent e; e.d2 = s_d2[t][tid]; e.id = s_key[t][tid]; e.pad = 0;
+        dst[t] = e;
+      }
+    } else {  // long row: walk this point again and park the entries as they come
+      int k = 0;
+      walk_block<FAST>(g, R, cx, cy,
+        [&](const pg_rec& c) {
+          const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+          if (d2 <= r2 && (UPPER ? c.id > me.id : c.id != me.id) && k < cnt) {
+            pg_tmp_ent e; e.d2 = d2; e.id = c.id; e.pad = 0;
+            dst[k++] = e;
+          }
+        },
+        [&]() {});
+    }
+  }
+  st_meta(o.meta + q, m);
 }
 
-// nothing to query: the statistics of an empty graph
-__global__ void empty_stats_kernel(pg_degree_stats* stats, int32_t* hist, int hist_len) {
-  if (stats && threadIdx.x == 0) {
-    stats->min_degree = 0; stats->max_degree = 0; stats->sum_degree = 0; stats->sumsq_degree = 0; stats->n_nodes = 0;
+struct rows_out {
+  int32_t* __restrict__ row_ptr;
+  int32_t* __restrict__ degree;
+  int32_t* __restrict__ nbr_count;   // NULL when not wanted or when the walk wrote it (wide types)
+  int32_t* __restrict__ row_off;
+  int n_types;
+  pg_degree_stats* stats;
+  int32_t* hist;
+  int hist_len, hist_mode;           // 0 none, 1 shared-memory bins -> accumulators, 2 straight into hist (pre-zeroed)
+  pg_stats_acc* acc;
+  int32_t* acc_hist;
+  int32_t* total_copy;
+  unsigned long long* ovf_cursor;    // retired here: *ovf_needed = *ovf_cursor; *ovf_cursor = 0
+  unsigned long long* ovf_needed;
+};
+
+// The row pass: meta records -> row order. Tiles of ROWS_TILE rows, decoupled look-back over the entry counts
+// (tile = blockIdx.x: CTAs are dispatched in index order, so a tile only waits on tiles that are running or done).
+// The statistics are reduced between publishing the tile's aggregate and reading the predecessors', i.e. inside
+// the look-back wait.
+__global__ void __launch_bounds__(TPB_ROWS)
+radius_rows_kernel(int n_query, const int32_t* __restrict__ pos, const pg_pt_meta* __restrict__ meta, pg_scan_state st, rows_out o) {
+  using TS = pg_tile_scan<TPB_ROWS>;
+  __shared__ typename TS::smem_t sm;
+  __shared__ int s_hist[PG_ACC_HIST_MAX];
+  __shared__ int s_mn, s_mx, s_last;
+  __shared__ unsigned long long s_sum, s_sq;
+  const int tid = threadIdx.x;
+  const bool want_stats = o.stats != nullptr || o.hist_mode != 0;
+  const int tile = blockIdx.x;
+  const int row0 = tile * ROWS_TILE + tid * ROWS_ITEMS;
+  const bool full = row0 + ROWS_ITEMS <= n_query;
+
+  pg_pt_meta m[ROWS_ITEMS];
+  int p[ROWS_ITEMS];
+  if (full) {
+    const int4 pp = *reinterpret_cast<const int4*>(pos + row0);
+    p[0] = pp.x; p[1] = pp.y; p[2] = pp.z; p[3] = pp.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS_ITEMS; ++i) p[i] = row0 + i < n_query ? pos[row0 + i] : -1;
+  }
+  if (o.hist_mode == 1)
+    for (int i = tid; i < o.hist_len; i += TPB_ROWS) s_hist[i] = 0;
+  if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_sum = 0; s_sq = 0; }
+#pragma unroll
+  for (int i = 0; i < ROWS_ITEMS; ++i) {
+    if (p[i] >= 0) m[i] = ld_meta(meta + p[i]);
+    else { m[i].deg = 0; m[i].cnt = 0; m[i].off = -1; }
+  }
+  int v[ROWS_ITEMS], tsum = 0;
+#pragma unroll
+  for (int i = 0; i < ROWS_ITEMS; ++i) { v[i] = tsum; tsum += m[i].cnt; }
+  int tile_sum;
+  const int thread_off = TS::local_scan(sm, st, tile, tsum, &tile_sum);  // barrier inside: the shared accumulators are ready
+
+  // ---- everything that does not need the tile's prefix: row_off, degree, type counts, statistics
+  if (full) {
+    *reinterpret_cast<int4*>(o.row_off + row0) = make_int4(m[0].off, m[1].off, m[2].off, m[3].off);
+    if (o.degree) *reinterpret_cast<int4*>(o.degree + row0) = make_int4(m[0].deg, m[1].deg, m[2].deg, m[3].deg);
+    if (o.nbr_count) {
+      if (o.n_types == PG_PACKED_TYPES) {  // 4 rows x 5 counts = 80 contiguous, 16-byte aligned bytes
+        int4* d = reinterpret_cast<int4*>(o.nbr_count + (int64_t)row0 * PG_PACKED_TYPES);
+        d[0] = make_int4(m[0].c[0], m[0].c[1], m[0].c[2], m[0].c[3]);
+        d[1] = make_int4(m[0].c[4], m[1].c[0], m[1].c[1], m[1].c[2]);
+        d[2] = make_int4(m[1].c[3], m[1].c[4], m[2].c[0], m[2].c[1]);
+        d[3] = make_int4(m[2].c[2], m[2].c[3], m[2].c[4], m[3].c[0]);
+        d[4] = make_int4(m[3].c[1], m[3].c[2], m[3].c[3], m[3].c[4]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < ROWS_ITEMS; ++i)
+#pragma unroll
+          for (int t = 0; t < PG_PACKED_TYPES; ++t)
+            if (t < o.n_types) o.nbr_count[(int64_t)(row0 + i) * o.n_types + t] = m[i].c[t];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS_ITEMS; ++i) {
+      const int row = row0 + i;
+      if (row < n_query) {
+        o.row_off[row] = m[i].off;
+        if (o.degree) o.degree[row] = m[i].deg;
+        if (o.nbr_count)
+#pragma unroll
+          for (int t = 0; t < PG_PACKED_TYPES; ++t)
+            if (t < o.n_types) o.nbr_count[(int64_t)row * o.n_types + t] = m[i].c[t];
+      }
+    }
+  }
+  if (want_stats) {  // thread -> warp -> CTA
+    int mn = 0x7fffffff, mx = -1;
+    long long sum = 0, sq = 0;
+#pragma unroll
+    for (int i = 0; i < ROWS_ITEMS; ++i) {
+      if (row0 + i < n_query) {
+        const int d = m[i].deg;
+        mn = min(mn, d); mx = max(mx, d); sum += d; sq += (long long)d * d;
+      }
+    }
+    if (o.hist_mode != 0) {
+      // degrees cluster on a few bins: one atomic per distinct bin of the warp instead of one per lane
+#pragma unroll
+      for (int i = 0; i < ROWS_ITEMS; ++i) {
+        const int bin = row0 + i < n_query ? min(m[i].deg, o.hist_len - 1) : -1;
+        const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (tid & 31) == __ffs(peers) - 1) {
+          if (o.hist_mode == 1) atomicAdd(&s_hist[bin], __popc(peers));
+          else atomicAdd(&o.hist[bin], __popc(peers));
+        }
+      }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, d); sq += __shfl_xor_sync(0xffffffffu, sq, d); }
+    if ((tid & 31) == 0) {
+      atomicMin(&s_mn, mn); atomicMax(&s_mx, mx);
+      atomicAdd(&s_sum, (unsigned long long)sum); atomicAdd(&s_sq, (unsigned long long)sq);
+    }
+  }
+
+  // ---- the prefix of the tile (barrier inside: the CTA's statistics are complete after it)
+  bool last;
+  int total;
+  const int base = thread_off + TS::look_back(sm, st, tile, tile_sum, &last, &total);
+  if (tid == 0 && last) {
+    o.row_ptr[n_query] = total;
+    if (o.total_copy) *o.total_copy = total;
+  }
+  if (full) {
+    *reinterpret_cast<int4*>(o.row_ptr + row0) = make_int4(v[0] + base, v[1] + base, v[2] + base, v[3] + base);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS_ITEMS; ++i)
+      if (row0 + i < n_query) o.row_ptr[row0 + i] = v[i] + base;
+  }
+
+  // ---- CTA -> accumulators; the last CTA to get here publishes them and re-arms the accumulators
+  if (want_stats) {
+    if (tid == 0) {
+      atomicMin(&o.acc->min_degree, s_mn); atomicMax(&o.acc->max_degree, s_mx);
+      atomicAdd(&o.acc->sum_degree, s_sum); atomicAdd(&o.acc->sumsq_degree, s_sq);
+    }
+    if (o.hist_mode == 1)
+      for (int i = tid; i < o.hist_len; i += TPB_ROWS)
+        if (s_hist[i]) atomicAdd(&o.acc_hist[i], s_hist[i]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&o.acc->done, 1u) == (unsigned int)st.num_tiles - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (o.hist_mode == 1)
+    for (int i = tid; i < o.hist_len; i += TPB_ROWS) {
+      o.hist[i] = *(volatile int32_t*)&o.acc_hist[i];
+      o.acc_hist[i] = 0;
+    }
+  if (tid == 0) {
+    volatile pg_stats_acc* a = o.acc;
+    if (o.stats) {
+      o.stats->min_degree = a->min_degree; o.stats->max_degree = a->max_degree;
+      o.stats->sum_degree = (long long)a->sum_degree; o.stats->sumsq_degree = (long long)a->sumsq_degree;
+      o.stats->n_nodes = n_query;
+    }
+    a->min_degree = 0x7fffffff; a->max_degree = -1; a->sum_degree = 0; a->sumsq_degree = 0; a->n_nodes = 0; a->done = 0;
+    if (o.ovf_cursor) { *o.ovf_needed = *(volatile unsigned long long*)o.ovf_cursor; *o.ovf_cursor = 0ull; }
+  }
+}
+
+// nothing to query: empty row_ptr and the statistics of an empty graph
+__global__ void empty_graph_kernel(int32_t* row_ptr, int32_t* total_copy, pg_degree_stats* stats, int32_t* hist, int hist_len,
+                                   unsigned long long* ovf_needed) {
+  if (threadIdx.x == 0) {
+    row_ptr[0] = 0;
+    *total_copy = 0;
+    *ovf_needed = 0;
+    if (stats) { stats->min_degree = 0; stats->max_degree = 0; stats->sum_degree = 0; stats->sumsq_degree = 0; stats->n_nodes = 0; }
   }
   if (hist)
     for (int i = threadIdx.x; i < hist_len; i += blockDim.x) hist[i] = 0;
@@ -203,76 +460,48 @@ __device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int
   if (o.edge_attr) { o.edge_attr[pos] = (float)d; o.edge_attr[o.n_edges + pos] = (float)d; }  // ipynb:3041-3042
 }
 
-// Fill pass. A row of up to FILL_CAP entries (known from row_ptr before the walk) takes one walk:
-// accepted (id, position) pairs are appended to the thread's column of two shared-memory arrays, sorted
-// by id there, and written out with the distance recomputed from the (L1-resident) record. Longer rows
-// are emitted in chunks of FILL_CAP: each walk keeps the FILL_CAP smallest ids above the last one written.
-template <bool MERGED>
-__global__ void __launch_bounds__(TPB_FILL)
-radius_fill_kernel(pg_grid_view g, double r2, int R, int upper, const int32_t* __restrict__ row_ptr, fill_out o,
-                   long long capacity, int32_t* overflow) {
-  __shared__ int s_key[FILL_CAP][TPB_FILL];
-  __shared__ int s_pos[FILL_CAP][TPB_FILL];
-  const int tid = threadIdx.x;
-  const int q = blockIdx.x * TPB_FILL + tid;
-  if (q >= g.n) return;
-  const pg_rec me = pg_ld_rec(g.rec + q);
-  if (me.row >= g.n_query) return;
-  const int base = row_ptr[me.row];
-  const int cnt = row_ptr[me.row + 1] - base;
-  if (cnt <= 0) return;
-  if ((long long)base + cnt > capacity) { atomicExch(overflow, 1); return; }
-  const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
-  const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
-
-  if (cnt <= FILL_CAP) {
-    int m = 0;
-    walk_block<MERGED>(g, R, cx, cy, q,
-      [&](int j, const pg_rec& c) {
-        const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
-        if (d2 <= r2 && j != q && (!upper || c.id > me.id) && m < FILL_CAP) {
-          s_key[m][tid] = c.id; s_pos[m][tid] = j; ++m;
-        }
-      },
-      [&]() {});
-    for (int a = 1; a < m; ++a) {  // insertion sort of a handful of entries, own column only
-      const int k = s_key[a][tid], p = s_pos[a][tid];
-      int s = a;
-      while (s > 0 && s_key[s - 1][tid] > k) { s_key[s][tid] = s_key[s - 1][tid]; s_pos[s][tid] = s_pos[s - 1][tid]; --s; }
-      s_key[s][tid] = k; s_pos[s][tid] = p;
+// The gather: one warp per 32 consecutive rows = one contiguous range of the outputs, one lane per output entry.
+__global__ void __launch_bounds__(TPB_GATHER)
+radius_gather_kernel(int n_query, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ row_off,
+                     const pg_tmp_ent* __restrict__ tmp, const int32_t* __restrict__ row_gid,
+                     fill_out o, long long capacity, int32_t* overflow) {
+  const int lane = threadIdx.x & 31;
+  const int r0 = ((blockIdx.x * TPB_GATHER + threadIdx.x) >> 5) << 5;
+  if (r0 >= n_query) return;  // warp-uniform
+  const int row = r0 + lane;
+  const bool has_row = row < n_query;
+  const int rp = row_ptr[min(row, n_query)];
+  const int off = has_row ? row_off[row] : -1;
+  const int id = has_row ? (row_gid ? row_gid[row] : row) : 0;
+  const int begin = __shfl_sync(0xffffffffu, rp, 0);
+  const int end = row_ptr[min(r0 + 32, n_query)];
+  const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+  const int my_cnt = (lane == 31 ? end : rp_next) - rp;
+  for (int p0 = begin; p0 < end; p0 += 32) {
+    const int p = p0 + lane;
+    int k = 0;  // the last row of the 32 that starts at or before p (empty rows share their start with the next row)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, rp, k + step);
+      if (v <= p) k += step;
     }
-    for (int t = 0; t < m; ++t) {
-      const double2 c = pg_ld_xy(g.rec + s_pos[t][tid]);
-      emit_entry(o, (long long)base + t, me.id, s_key[t][tid], pg_dist2(me.x, me.y, c.x, c.y));
+    const int roff = __shfl_sync(0xffffffffu, off, k);
+    const int rcnt = __shfl_sync(0xffffffffu, my_cnt, k);
+    const int rbase = __shfl_sync(0xffffffffu, rp, k);
+    const int rid = __shfl_sync(0xffffffffu, id, k);
+    if (p >= end) continue;
+    if ((long long)rbase + rcnt > capacity || roff < 0) {
+      atomicExch(overflow, 1);  // the row does not fit the caller's buffers (or never got parked): dropped, reported
+      continue;
     }
-    return;
-  }
-
-  int emitted = 0;
-  int last = upper ? me.id : -1;
-  while (emitted < cnt) {
-    int m = 0;
-    walk_block<MERGED>(g, R, cx, cy, q,
-      [&](int j, const pg_rec& c) {
-        const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
-        if (!(d2 <= r2) || j == q || c.id <= last) return;
-        if (m == FILL_CAP) {
-          if (c.id >= s_key[FILL_CAP - 1][tid]) return;
-          m = FILL_CAP - 1;
-        }
-        int s = m;
-        while (s > 0 && s_key[s - 1][tid] > c.id) { s_key[s][tid] = s_key[s - 1][tid]; s_pos[s][tid] = s_pos[s - 1][tid]; --s; }
-        s_key[s][tid] = c.id; s_pos[s][tid] = j;
-        ++m;
-      },
-      [&]() {});
-    if (m == 0) break;  // cannot happen when row_ptr came from the matching count pass
-    for (int t = 0; t < m; ++t) {
-      const double2 c = pg_ld_xy(g.rec + s_pos[t][tid]);
-      emit_entry(o, (long long)base + emitted + t, me.id, s_key[t][tid], pg_dist2(me.x, me.y, c.x, c.y));
+    const pg_tmp_ent* src = tmp + roff;
+    const pg_tmp_ent e = src[p - rbase];
+    int rank = 0;  // ids are distinct, so the place of an entry in its row is the number of smaller ids
+    for (int u = 0; u < rcnt; u += 4) {
+      const int i0 = src[u].id, i1 = src[min(u + 1, rcnt - 1)].id, i2 = src[min(u + 2, rcnt - 1)].id, i3 = src[min(u + 3, rcnt - 1)].id;
+      rank += (i0 < e.id) + (u + 1 < rcnt && i1 < e.id) + (u + 2 < rcnt && i2 < e.id) + (u + 3 < rcnt && i3 < e.id);
     }
-    emitted += m;
-    last = s_key[m - 1][tid];
+    emit_entry(o, (long long)rbase + rank, rid, e.id, e.d2);
   }
 }
 
@@ -283,9 +512,95 @@ static inline int ring_radius(double r, const pg_grid& gr) {
   return R < 1 ? 1 : R;
 }
 
+// sizes tmp_ent for the pass described by h->last_count: one region per walk CTA + the overflow region
+int size_tmp(pg_handle* h) {
+  const pg_grid& gr = h->grid;
+  const int64_t n_cta = pg_div_up(std::max(gr.n, 1), TPB_WALK);
+  // per point: twice what a past pass produced on average, else a first guess
+  const double per_point = h->tmp_hint > 0 && gr.n_query > 0 ? 2.0 * (double)h->tmp_hint / gr.n_query
+                                                               : (h->last_count.flags == PG_RADIUS_UPPER ? 4.0 : 8.0);
+  int64_t cta_cap = (int64_t)std::ceil(std::min(per_point, 64.0) * TPB_WALK);
+  cta_cap = (cta_cap + 7) & ~(int64_t)7;
+  const int64_t ovf = std::max<int64_t>(h->tmp_ovf_hint, gr.n_query / 8 + 4096);
+  const int64_t total = n_cta * cta_cap + ovf;
+  if (total > 0x7ffffff0) return pg_set_error(h, PG_ERR_CAPACITY, "radius graph: more than 2^31 parked entries");
+  int rc = pg_reserve(h, h->tmp_ent, (size_t)total * sizeof(pg_tmp_ent));
+  if (rc) return rc;
+  h->tmp_cta_cap = (int32_t)cta_cap;
+  h->tmp_ovf_base = n_cta * cta_cap;
+  h->tmp_cap = std::min<int64_t>((int64_t)(h->tmp_ent.cap / sizeof(pg_tmp_ent)), 0x7ffffff0);
+  return PG_OK;
+}
+
+// enqueue walk + row pass of the pass described by h->last_count
+int launch_count_pass(pg_handle* h, cudaStream_t s) {
+  const auto& a = h->last_count;
+  const pg_grid& gr = h->grid;
+  const int nq = gr.n_query;
+  unsigned long long* cursor = (unsigned long long*)((char*)h->misc.p + PG_MISC_TMPCUR);
+  int32_t* totals = (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS);
+  unsigned long long* needed = (unsigned long long*)(totals + 4);
+  if (gr.n == 0 || nq == 0) {
+    PG_LAUNCH(h, s, "empty_graph_kernel", empty_graph_kernel<<<1, 256, 0, s>>>(a.row_ptr, totals, a.stats, a.hist, a.hist ? a.hist_len : 0, needed));
+    PG_LAUNCH_CHECK(h);
+    return PG_OK;
+  }
+  pg_grid_view v = pg_make_view(h);
+  const int R = ring_radius(a.r, gr);
+  const bool upper = a.flags == PG_RADIUS_UPPER;
+  const bool wide = a.nbr_count && a.n_types > PG_PACKED_TYPES;
+  walk_out w;
+  w.meta = (pg_pt_meta*)h->pt_meta.p;
+  w.tmp = (pg_tmp_ent*)h->tmp_ent.p;
+  w.cta_cap = h->tmp_cta_cap;
+  w.ovf_base = (unsigned long long)h->tmp_ovf_base;
+  w.ovf_cap = (unsigned long long)(h->tmp_cap - h->tmp_ovf_base);
+  w.ovf_cursor = cursor;
+  w.nbr_count = a.nbr_count;
+  w.n_types = a.nbr_count ? a.n_types : 1;
+  const int blocks = pg_div_up(gr.n, TPB_WALK);
+#define PG_WALK_LAUNCH(F, U, W) \
+  PG_LAUNCH(h, s, "radius_walk_kernel", radius_walk_kernel<F, U, W><<<blocks, TPB_WALK, 0, s>>>(v, a.r * a.r, R, w))
+  if (wide) {
+    if (R == 1) { if (upper) PG_WALK_LAUNCH(true, true, true); else PG_WALK_LAUNCH(true, false, true); }
+    else { if (upper) PG_WALK_LAUNCH(false, true, true); else PG_WALK_LAUNCH(false, false, true); }
+  } else {
+    if (R == 1) { if (upper) PG_WALK_LAUNCH(true, true, false); else PG_WALK_LAUNCH(true, false, false); }
+    else { if (upper) PG_WALK_LAUNCH(false, true, false); else PG_WALK_LAUNCH(false, false, false); }
+  }
+#undef PG_WALK_LAUNCH
+  PG_LAUNCH_CHECK(h);
+
+  rows_out o;
+  o.row_ptr = a.row_ptr; o.degree = a.degree; o.nbr_count = wide ? nullptr : a.nbr_count;
+  o.row_off = (int32_t*)h->row_off.p;
+  o.n_types = a.nbr_count ? a.n_types : 1;
+  o.stats = a.stats; o.hist = a.hist; o.hist_len = a.hist_len;
+  o.hist_mode = a.hist ? (a.hist_len <= PG_ACC_HIST_MAX ? 1 : 2) : 0;
+  if (o.hist_mode == 2) PG_CUDA(h, cudaMemsetAsync(a.hist, 0, (size_t)a.hist_len * sizeof(int32_t), s));
+  o.acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
+  o.acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
+  o.total_copy = totals;
+  o.ovf_cursor = cursor; o.ovf_needed = needed;
+  const int tiles = pg_div_up(nq, ROWS_TILE);
+  pg_scan_state st;
+  int rc = pg_scan_prepare(h, tiles, TPB_ROWS, s, &st);
+  if (rc) return rc;
+  PG_LAUNCH(h, s, "radius_rows_kernel", radius_rows_kernel<<<tiles, TPB_ROWS, 0, s>>>(nq, (const int32_t*)h->s_pos.p, (const pg_pt_meta*)h->pt_meta.p, st, o));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int pg_radius_reserve(pg_handle* h, int64_t entries) {
+  if (!h) return PG_ERR_INVALID;
+  PG_REQUIRE(h, entries >= 0, "pg_radius_reserve: entries < 0");
+  if (entries > h->tmp_ovf_hint) h->tmp_ovf_hint = entries;
+  return PG_OK;
+}
 
 int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree,
                     int32_t* nbr_count, int32_t n_types, pg_degree_stats* stats, int32_t* hist,
@@ -294,69 +609,54 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = s;
+  h->last_count.valid = false;
   if (!h->grid.built) return pg_set_error(h, PG_ERR_STATE, "pg_radius_count: call pg_grid_build first");
   PG_REQUIRE(h, r >= 0 && std::isfinite(r), "pg_radius_count: r must be finite and >= 0");
   PG_REQUIRE(h, row_ptr != nullptr, "pg_radius_count: row_ptr is NULL");
   PG_REQUIRE(h, flags == PG_RADIUS_SYMMETRIC || flags == PG_RADIUS_UPPER, "pg_radius_count: bad flags %d", flags);
   PG_REQUIRE(h, !nbr_count || (n_types >= 1 && n_types <= PG_MAX_TYPES), "pg_radius_count: n_types must be in 1..%d", PG_MAX_TYPES);
   PG_REQUIRE(h, !hist || hist_len >= 1, "pg_radius_count: hist_len must be >= 1");
+  PG_REQUIRE(h, ((uintptr_t)row_ptr & 15) == 0 && ((uintptr_t)degree & 15) == 0 && ((uintptr_t)nbr_count & 15) == 0,
+             "pg_radius_count: row_ptr / degree / nbr_count must be 16-byte aligned");
   const pg_grid& gr = h->grid;
-  const int nq = gr.n_query;
   int rc;
-  if ((rc = pg_reserve(h, h->row_count, ((size_t)nq + 4) * sizeof(int32_t)))) return rc;
+  if ((rc = pg_reserve(h, h->pt_meta, ((size_t)gr.n + 1) * sizeof(pg_pt_meta)))) return rc;
+  if ((rc = pg_reserve(h, h->row_off, ((size_t)gr.n_query + 8) * sizeof(int32_t)))) return rc;
   h->radius_r = r;
   h->radius_flags = flags;
-  bool launched = false;
-  int hist_mode_used = 0;
-  if (gr.n > 0 && nq > 0) {
-    launched = true;
-    pg_grid_view v = pg_make_view(h);
-    const int R = ring_radius(r, gr);
-    const int upper = flags == PG_RADIUS_UPPER;
-    const int nt = nbr_count ? n_types : 1;
-    int hist_mode = 0;
-    if (hist) {
-      hist_mode = hist_len <= PG_ACC_HIST_MAX ? 1 : 2;
-      if (hist_mode == 2) PG_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)hist_len * sizeof(int32_t), s));
-    }
-    hist_mode_used = hist_mode;
-    pg_stats_acc* acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
-    int32_t* acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
-    const int blocks = pg_div_up(gr.n, TPB_COUNT);
-    const bool wide = nbr_count && n_types > PG_PACKED_TYPES;
-#define PG_COUNT_LAUNCH(M, W)                                                                                   \
-  PG_LAUNCH(h, s, "radius_count_kernel", radius_count_kernel<M, W><<<blocks, TPB_COUNT, 0, s>>>(                \
-      v, r * r, R, upper, (int32_t*)h->row_count.p, degree, nbr_count, nt, acc, acc_hist, stats != nullptr, hist, hist_len, hist_mode))
-    if (R == 1 && !wide) PG_COUNT_LAUNCH(true, false);
-    else if (R == 1) PG_COUNT_LAUNCH(true, true);
-    else if (!wide) PG_COUNT_LAUNCH(false, false);
-    else PG_COUNT_LAUNCH(false, true);
-#undef PG_COUNT_LAUNCH
-    PG_LAUNCH_CHECK(h);
-  } else if (stats || hist) {
-    PG_LAUNCH(h, s, "empty_stats_kernel", empty_stats_kernel<<<1, 256, 0, s>>>(stats, hist, hist ? hist_len : 0));
-    PG_LAUNCH_CHECK(h);
-  }
-  pg_scan_publish pub;
-  if (launched && (stats || hist_mode_used == 1)) {
-    pub.acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
-    pub.acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
-    pub.stats = stats;
-    pub.hist = hist_mode_used == 1 ? hist : nullptr;
-    pub.hist_len = hist_len;
-  }
-  return pg_scan_i32(h, (const int32_t*)h->row_count.p, row_ptr, nq, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS), false,
-                     pub.acc ? &pub : nullptr);
+  auto& a = h->last_count;
+  a.r = r; a.flags = flags; a.row_ptr = row_ptr; a.degree = degree; a.nbr_count = nbr_count; a.n_types = n_types;
+  a.stats = stats; a.hist = hist; a.hist_len = hist_len;
+  if ((rc = size_tmp(h))) return rc;
+  if ((rc = launch_count_pass(h, s))) return rc;
+  a.valid = true;
+  return PG_OK;
 }
 
 int pg_radius_total(pg_handle* h, int64_t* total) {
   if (!h || !total) return PG_ERR_INVALID;
   PG_CUDA(h, cudaSetDevice(h->device));
-  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[0], (char*)h->misc.p + PG_MISC_TOTALS, sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, h->last_stream));
-  PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
-  *total = h->pinned[0];
-  return PG_OK;
+  if (!h->last_count.valid) return pg_set_error(h, PG_ERR_STATE, "pg_radius_total: call pg_radius_count first");
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    PG_CUDA(h, cudaMemcpyAsync(&h->pinned[0], (char*)h->misc.p + PG_MISC_TOTALS, 8 * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, h->last_stream));
+    PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
+    int64_t needed;
+    memcpy(&needed, &h->pinned[4], sizeof(needed));
+    const int64_t produced = h->pinned[0];
+    if (produced > h->tmp_hint) h->tmp_hint = produced;
+    if (needed <= h->tmp_cap - h->tmp_ovf_base) {
+      *total = produced;
+      return PG_OK;
+    }
+    // the overflow region was too small: size it to what the pass needed (and the CTA regions to the new
+    // average) and redo the pass
+    h->tmp_ovf_hint = std::max(h->tmp_ovf_hint, needed + needed / 4);
+    int rc;
+    if ((rc = size_tmp(h))) return rc;
+    if ((rc = launch_count_pass(h, h->last_stream))) return rc;
+  }
+  return pg_set_error(h, PG_ERR_STATE, "pg_radius_total: the count pass did not settle");
 }
 
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
@@ -366,7 +666,8 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = s;
-  if (!h->grid.built) return pg_set_error(h, PG_ERR_STATE, "pg_radius_fill: call pg_grid_build / pg_radius_count first");
+  if (!h->grid.built || !h->last_count.valid)
+    return pg_set_error(h, PG_ERR_STATE, "pg_radius_fill: call pg_grid_build / pg_radius_count first");
   PG_REQUIRE(h, row_ptr != nullptr, "pg_radius_fill: row_ptr is NULL");
   PG_REQUIRE(h, capacity >= 0, "pg_radius_fill: capacity < 0");
   PG_REQUIRE(h, capacity == 0 || col != nullptr, "pg_radius_fill: col is NULL");
@@ -375,17 +676,12 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   PG_REQUIRE(h, ((uintptr_t)edges_i64 & 15) == 0, "pg_radius_fill: edges must be 16-byte aligned");
   const pg_grid& gr = h->grid;
   if (gr.n == 0 || gr.n_query == 0) return PG_OK;
-  pg_grid_view v = pg_make_view(h);
-  const int R = ring_radius(h->radius_r, gr);
-  const int upper = h->radius_flags == PG_RADIUS_UPPER;
   fill_out o{col, dist32, dist64, (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges};
   int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
-  const int blocks = pg_div_up(gr.n, TPB_FILL);
-  const double r2 = h->radius_r * h->radius_r;
-  if (R == 1)
-    PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<true><<<blocks, TPB_FILL, 0, s>>>(v, r2, R, upper, row_ptr, o, (long long)capacity, ovf));
-  else
-    PG_LAUNCH(h, s, "radius_fill_kernel", radius_fill_kernel<false><<<blocks, TPB_FILL, 0, s>>>(v, r2, R, upper, row_ptr, o, (long long)capacity, ovf));
+  const int blocks = pg_div_up(gr.n_query, TPB_GATHER);
+  PG_LAUNCH(h, s, "radius_gather_kernel", radius_gather_kernel<<<blocks, TPB_GATHER, 0, s>>>(
+      gr.n_query, row_ptr, (const int32_t*)h->row_off.p, (const pg_tmp_ent*)h->tmp_ent.p,
+      gr.has_gid ? (const int32_t*)h->s_gid.p : nullptr, o, (long long)capacity, ovf));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

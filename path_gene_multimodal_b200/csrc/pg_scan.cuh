@@ -55,6 +55,14 @@ struct pg_tile_scan {
   // item over the whole array. total (if the tile is the last one) receives the grand total.
   static __device__ __forceinline__ int thread_prefix(smem_t& sm, const pg_scan_state& st, int tile, int tsum,
                                                       bool* is_last_tile, int* grand_total) {
+    int tile_sum;
+    const int thread_off = local_scan(sm, st, tile, tsum, &tile_sum);
+    return thread_off + look_back(sm, st, tile, tile_sum, is_last_tile, grand_total);
+  }
+
+  // first half: scan inside the tile and publish the tile's aggregate at once; returns the exclusive prefix of
+  // the thread's first item inside the tile. Work placed between the two halves overlaps the look-back wait.
+  static __device__ __forceinline__ int local_scan(smem_t& sm, const pg_scan_state& st, int tile, int tsum, int* tile_sum_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int incl = tsum;
 #pragma unroll
@@ -71,10 +79,15 @@ struct pg_tile_scan {
       if (w < warp) warp_off += s;
       tile_sum += s;
     }
-    const int thread_off = warp_off + incl - tsum;
     if (tid == 0) pg_st_relaxed_u64(&st.agg[tile], pg_pack_desc(st.epoch, tile_sum));
+    *tile_sum_out = tile_sum;
+    return warp_off + incl - tsum;
+  }
 
-    // prefix of this tile = prefix of the previous group + aggregates of the earlier tiles of my group
+  // second half: prefix of this tile = prefix of the previous group + aggregates of the earlier tiles of my group
+  static __device__ __forceinline__ int look_back(smem_t& sm, const pg_scan_state& st, int tile, int tile_sum,
+                                                  bool* is_last_tile, int* grand_total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = tile / THREADS, first = group * THREADS;
     int contrib = 0;
     const int pred = first + tid;
@@ -98,7 +111,7 @@ struct pg_tile_scan {
     if (tid == 0 && tile == first + THREADS - 1) pg_st_relaxed_u64(&st.gpre[group], pg_pack_desc(st.epoch, prefix + tile_sum));
     *is_last_tile = tile == st.num_tiles - 1;
     *grand_total = prefix + tile_sum;
-    return prefix + thread_off;
+    return prefix;
   }
 };
 

@@ -241,6 +241,8 @@ class Engine:
         nbr = get("nbr_count", (nq, n_types), torch.int32) if compose else None
         st = get("stats", (4,), torch.int64) if stats else None
         hist = get("hist", (hist_len,), torch.int32) if (stats and hist_len) else None
+        if capacity is not None:
+            self._check(self.lib.pg_radius_reserve(self._h, int(capacity)))
         self._check(self.lib.pg_radius_count(self._h, float(r), 1 if upper else 0,
                                              self._p(row_ptr, torch.int32, "row_ptr"), self._p(degree, torch.int32, "degree"),
                                              self._p(nbr, torch.int32, "nbr_count"), int(n_types),
