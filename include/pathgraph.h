@@ -109,6 +109,11 @@ int pg_map_morph_f64(pg_handle* h, int32_t n, const int32_t* poly_off, const dou
  *   bounds  host f64[4] xmin,ymin,xmax,ymax (NULL = computed on the device; costs one sync) */
 int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, const int32_t* type,
                   const int32_t* gid, double cell_size, const double* bounds, pg_stream stream);
+/* Coordinates must be finite (cKDTree raises on NaN / inf). With bounds = NULL pg_grid_build itself reports it;
+ * with caller-given bounds the build is asynchronous, the histogram kernel flags the offending input and
+ * PG_ERR_INVALID comes from the next call that synchronises: pg_grid_check (synchronises the stream),
+ * pg_radius_total or pg_check_overflow. */
+int pg_grid_check(pg_handle* h);
 /* host-side view of the grid chosen: nx, ny, x0, y0, cell */
 int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0, double* cell);
 

@@ -58,6 +58,8 @@ def to_host_many(tensors: dict) -> dict:
 
 def as_int32(arr, name: str) -> np.ndarray:
     a = np.asarray(arr)
+    if a.dtype == np.int32:
+        return a
     if a.dtype.kind not in "iu":
         if a.dtype.kind == "f" and np.all(a == np.floor(a)):
             a = a.astype(np.int64)

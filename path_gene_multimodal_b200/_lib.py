@@ -61,6 +61,7 @@ SIGNATURES = {
     "pg_profile_count": (C.c_int, [vp]),
     "pg_profile_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "pg_check_overflow": (C.c_int, [vp]),
+    "pg_grid_check": (C.c_int, [vp]),
     "pg_knn_symmetrize_count": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp, vp]),
     "pg_knn_symmetrize_total": (C.c_int, [vp, C.POINTER(i64)]),
     "pg_knn_symmetrize_fill": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -28,8 +28,8 @@ def _prep(coords, types, eng):
         raise ValueError("coords must have shape (N, 2)")
     if c.shape[0] > _host.INT32_MAX:
         raise OverflowError("more than 2^31 points")
-    if c.size and not np.isfinite(c).all():
-        raise ValueError("coords must be finite")  # cKDTree raises on NaN / inf as well
+    # NaN / inf (cKDTree raises on them) are detected on the device by the histogram kernel and reported at the
+    # first synchronisation - no extra pass over the coordinates on the host
     d_xy = _host.to_device(c, np.float64, eng.device)
     d_t = None
     if types is not None:
@@ -65,12 +65,15 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
         raise ValueError(f"k={k} must be smaller than the number of points ({n})")
     with torch.cuda.device(eng.device):
         b = bounds if bounds is not None else _bounds(c)
+        if not np.isfinite(b).all():
+            raise ValueError("coords must be finite")
         if cell_size is None:
             cell_size = default_knn_cell(n, max(b[2] - b[0], 1e-9) * max(b[3] - b[1], 1e-9), k)
         eng.grid_build(d_xy, d_t, None, cell_size, b)
         kn = eng.knn(k, dist_dtype=torch.float64)
         out = {"knn_neighbors": _host.to_host(kn["knn_idx"]).astype(np.int64),
                "knn_neighbor_distances": _host.to_host(kn["dist"])}
+        eng.grid_check()
         if undirected:
             sym = eng.symmetrize(kn["knn_idx"], kn["dist"])
             up = eng.csr_upper(sym["row_ptr"], sym["col"], sym["w64"])

@@ -61,6 +61,7 @@ struct pg_handle {
   pg_buf sym_recip;    // uint8 [N*k]
   int32_t* pinned = nullptr;  // host-pinned: [0]=radius total [1]=sym total [2]=upper total [3]=overflow [4..]=scratch
   uint32_t scan_epoch = 0;
+  int32_t build_epoch = 0;    // pg_grid_build counter (tags PG_MISC_BADINPUT)
   pg_grid grid;
   double radius_r = 0;
   int32_t radius_flags = 0;
@@ -97,6 +98,7 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
+#define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
 #define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])
 #define PG_MISC_ACC 256       // pg_stats_acc: degree-statistics accumulators kept in their reset state
@@ -114,6 +116,8 @@ struct pg_stats_acc {
 };
 
 int pg_set_error(pg_handle* h, int code, const char* fmt, ...);
+// after a stream synchronisation that followed the copy of PG_MISC_BADINPUT into h->pinned[8]
+int pg_check_input_flag(pg_handle* h);
 int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
 
 #define PG_CUDA(h, expr)                                                                      \

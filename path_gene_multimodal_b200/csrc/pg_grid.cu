@@ -82,7 +82,7 @@ __device__ __forceinline__ void load_points(const double2* __restrict__ xy, int 
 
 __global__ void __launch_bounds__(TPB)
 histogram_kernel(const double2* __restrict__ xy, int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny,
-                 int32_t* __restrict__ cell_count) {
+                 int32_t* __restrict__ cell_count, int32_t* bad_input, int epoch) {
   const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
   double2 p[PTS];
   load_points(xy, n, aligned32, base, p);
@@ -92,6 +92,9 @@ histogram_kernel(const double2* __restrict__ xy, int n, bool aligned32, double x
     if (i < n) {
       const int c = pg_cell_index(nx, pg_cell_coord(p[k].x, x0, inv_cell, nx), pg_cell_coord(p[k].y, y0, inv_cell, ny));
       atomicAdd(&cell_count[c], 1);
+      // cKDTree refuses NaN / inf; here the build goes on (they land in a border cell) and the next call that
+      // synchronises reports it
+      if (!(isfinite(p[k].x) && isfinite(p[k].y))) *bad_input = epoch;
     }
   }
 }
@@ -149,6 +152,7 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = s;
   h->grid.built = false;
+  h->build_epoch = h->build_epoch == 0x7fffffff ? 1 : h->build_epoch + 1;
   PG_REQUIRE(h, n >= 0 && n_query >= 0 && n_query <= n, "pg_grid_build: need 0 <= n_query <= n (n=%d n_query=%d)", n, n_query);
   PG_REQUIRE(h, cell_size > 0 && std::isfinite(cell_size), "pg_grid_build: cell_size must be finite and > 0");
   PG_REQUIRE(h, n == 0 || xy != nullptr, "pg_grid_build: xy is NULL");
@@ -169,7 +173,7 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     PG_CUDA(h, cudaMemcpyAsync(hk, keys, sizeof(hk), cudaMemcpyDeviceToHost, s));
     PG_CUDA(h, cudaStreamSynchronize(s));
     if (hk[0] == ~0ull || hk[1] == ~0ull)
-      return pg_set_error(h, PG_ERR_INVALID, "pg_grid_build: every coordinate is NaN");
+      return pg_set_error(h, PG_ERR_INVALID, "pg_grid_build: coordinates must be finite (every coordinate is NaN)");
     for (int i = 0; i < 4; ++i) b[i] = key_dbl(hk[i]);
     if (!(std::isfinite(b[0]) && std::isfinite(b[1]) && std::isfinite(b[2]) && std::isfinite(b[3])))
       return pg_set_error(h, PG_ERR_INVALID, "pg_grid_build: coordinates must be finite");
@@ -218,7 +222,8 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   }
   if (n > 0) {
     PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB * PTS), TPB, 0, s>>>(
-        (const double2*)xy, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p));
+        (const double2*)xy, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p,
+        (int32_t*)((char*)h->misc.p + PG_MISC_BADINPUT), h->build_epoch));
     PG_LAUNCH_CHECK(h);
   }
   if ((rc = pg_scan_i32(h, (const int32_t*)h->cell_count.p, B + 1, (int32_t)cells, s, nullptr, true))) {
@@ -233,6 +238,14 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   }
   g.built = true;
   return PG_OK;
+}
+
+int pg_grid_check(pg_handle* h) {
+  if (!h) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[8], (char*)h->misc.p + PG_MISC_BADINPUT, sizeof(int32_t), cudaMemcpyDeviceToHost, h->last_stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  return pg_check_input_flag(h);
 }
 
 int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0, double* cell) {

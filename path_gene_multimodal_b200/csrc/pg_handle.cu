@@ -39,6 +39,12 @@ int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes) {
   return PG_OK;
 }
 
+int pg_check_input_flag(pg_handle* h) {
+  if (h->build_epoch != 0 && h->pinned[8] == h->build_epoch)
+    return pg_set_error(h, PG_ERR_INVALID, "coordinates must be finite (the last pg_grid_build met NaN or inf)");
+  return PG_OK;
+}
+
 static void pg_profile_clear(pg_handle* h) {
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   h->prof.clear();
@@ -159,8 +165,11 @@ int pg_check_overflow(pg_handle* h) {
   PG_CUDA(h, cudaSetDevice(h->device));
   int32_t* flag = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
   PG_CUDA(h, cudaMemcpyAsync(&h->pinned[3], flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->last_stream));
+  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[8], (char*)h->misc.p + PG_MISC_BADINPUT, sizeof(int32_t), cudaMemcpyDeviceToHost, h->last_stream));
   PG_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int32_t), h->last_stream));
   PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  int rc_in = pg_check_input_flag(h);
+  if (rc_in) return rc_in;
   if (h->pinned[3] != 0)
     return pg_set_error(h, PG_ERR_CAPACITY, "an output buffer was smaller than the result (capacity overflow)");
   return PG_OK;

@@ -640,7 +640,13 @@ int pg_radius_total(pg_handle* h, int64_t* total) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     PG_CUDA(h, cudaMemcpyAsync(&h->pinned[0], (char*)h->misc.p + PG_MISC_TOTALS, 8 * sizeof(int32_t),
                                cudaMemcpyDeviceToHost, h->last_stream));
+    PG_CUDA(h, cudaMemcpyAsync(&h->pinned[8], (char*)h->misc.p + PG_MISC_BADINPUT, sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, h->last_stream));
     PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
+    {
+      int rc_in = pg_check_input_flag(h);
+      if (rc_in) return rc_in;
+    }
     int64_t needed;
     memcpy(&needed, &h->pinned[4], sizeof(needed));
     const int64_t produced = h->pinned[0];

@@ -64,7 +64,10 @@ class Engine:
 
     def _check(self, rc: int):
         if rc != 0:
-            raise PathGraphError(rc, (self.lib.pg_last_error(self._h) or b"").decode())
+            msg = (self.lib.pg_last_error(self._h) or b"").decode()
+            if rc == _lib.PG_ERR_INVALID and "must be finite" in msg:
+                raise ValueError("coords must be finite")  # cKDTree raises ValueError on NaN / inf as well
+            raise PathGraphError(rc, msg)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -107,6 +110,10 @@ class Engine:
 
     def check_overflow(self):
         self._check(self.lib.pg_check_overflow(self._h))
+
+    def grid_check(self):
+        """Synchronise and raise if the last grid_build met a non-finite coordinate."""
+        self._check(self.lib.pg_grid_check(self._h))
 
     @staticmethod
     def decode_stats(stats_t: torch.Tensor, hist: torch.Tensor | None = None) -> dict:

@@ -129,3 +129,21 @@ def test_build_knn_graph_api(golden_graph):
     assert np.array_equal(nodes, on) and np.array_equal(sub, oe)
     with pytest.raises(ValueError):
         build_knn_graph(coords[:5], k=5)
+
+
+def test_non_finite_coordinates_raise(golden_graph):
+    """cKDTree raises ValueError on NaN / inf; here the histogram kernel flags them (no host pass over the data)."""
+    from path_gene_multimodal_b200 import build_knn_graph, build_radius_graph
+
+    coords = np.array(golden_graph["coords"], dtype=np.float64, copy=True)
+    for bad in (np.nan, np.inf):
+        c = coords.copy()
+        c[7, 1] = bad
+        for bounds in (None, (0.0, 0.0, 600.0, 600.0)):
+            with pytest.raises(ValueError, match="finite"):
+                build_radius_graph(c, r=40.0, bounds=bounds)
+            with pytest.raises(ValueError, match="finite"):
+                build_knn_graph(c, k=3, bounds=bounds)
+    # and the handle is usable again afterwards
+    g = build_radius_graph(coords, r=40.0)
+    assert np.array_equal(g["edges"], ograph.radius_graph(coords, 40.0)["edges"])
