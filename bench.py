@@ -5,8 +5,9 @@ a 1M-nucleus synthetic WSI (BASELINE.json configs[1], "C2"), per GPU, weak-scale
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one slide:
-  pg_grid_build (histogram, look-back scan, counting-sort scatter) -> pg_radius_count (fused
-  neighbour-type histogram + degree statistics) -> scan -> pg_radius_fill (edges i<j, float32 distances).
+  pg_grid_build (histogram, look-back scan, counting-sort scatter) -> pg_radius_count (one neighbourhood walk with
+  fused neighbour-type counts, then the row pass: row_ptr scan + degree statistics) -> pg_radius_fill (gather of
+  the parked entries: edges i<j, float32 distances).
 `value`    : inputs resident in HBM, device time from CUDA events, L2 flushed between steps.
 `e2e`      : the public call build_radius_graph(host coords, ...) -> host arrays (H2D + kernels + D2H).
 `roofline` : the dominant kernel, timed inside the library with CUDA events on its own stream.
@@ -163,10 +164,11 @@ def kernel_bytes(name, n, e_und, cells):
     """Compulsory bytes of one launch of each kernel (its own inputs read once + outputs written once)."""
     table = {
         "histogram_kernel": 16 * n + 4 * cells,                       # xy in; cell counters
-        "scatter_kernel": 16 * n + 4 * n + 4 * cells + 24 * n,        # xy, type, cursors in; sorted xy + meta out
-        "radius_count_kernel": 24 * n + 4 * cells + 4 * n + 4 * n + 4 * N_TYPES * n,  # sorted xy+meta, cell_start in; count, degree, nbr out
-        "radius_fill_kernel": 24 * n + 4 * cells + 8 * n + 4 * e_und + 4 * e_und + 16 * e_und,  # + row_ptr in; col, dist32, edges out
-        "scan_kernel": 8 * max(n, cells),
+        "scan_kernel": 8 * cells,                                     # counters in, cell starts out
+        "scatter_kernel": 16 * n + 4 * n + 4 * cells + 32 * n + 4 * n,  # xy, type, cursors in; 32-byte records + positions out
+        "radius_walk_kernel": 32 * n + 4 * cells + 32 * n + 16 * e_und,  # records, cell starts in; per-point meta + parked entries out
+        "radius_rows_kernel": 4 * n + 32 * n + 4 * n + 4 * n + 4 * N_TYPES * n + 4 * n,  # pos, meta in; row_ptr, degree, nbr_count, row_off out
+        "radius_gather_kernel": 8 * n + 16 * e_und + 4 * e_und + 4 * e_und + 16 * e_und,  # row_ptr, row_off, entries in; col, dist32, edges out
     }
     return table.get(name)
 

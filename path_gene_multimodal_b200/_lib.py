@@ -6,6 +6,7 @@ callers fail loudly; there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -82,7 +83,10 @@ def load_library(path: str | Path | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    if path is None and os.environ.get("PG_LIBPATH"):  # debugging aid: an alternative build of the same library
+        p = Path(os.environ["PG_LIBPATH"])
+    else:
+        p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise RuntimeError(
             f"{p} is missing: build the CUDA library first (python -m path_gene_multimodal_b200._build, "

@@ -120,6 +120,21 @@ int pg_set_error(pg_handle* h, int code, const char* fmt, ...);
 int pg_check_input_flag(pg_handle* h);
 int pg_reserve(pg_handle* h, pg_buf& b, size_t bytes);
 
+// Launch with programmatic dependent launch allowed: the grid may be scheduled while the kernel before it on the
+// stream is still draining; it must execute pg_pdl_wait() before its first global-memory access (every kernel
+// launched this way does so at its top), so only launch latency and the prologue overlap - no data hazard.
+int pg_pdl_mask();  // PG_PDL_MASK environment variable (debugging aid): bit i allows it for kernels launched with tag i
+template <class... KArgs, class... Args>
+static inline cudaError_t pg_launch_pdl(int tag, void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (pg_pdl_mask() >> tag) & 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define PG_CUDA(h, expr)                                                                      \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -160,6 +175,10 @@ static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 #define PG_STRIP (1 << PG_STRIP_LOG)
 
 #ifdef __CUDACC__
+// programmatic dependent launch: let the next kernel on the stream be scheduled / wait for the previous one
+__device__ __forceinline__ void pg_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __host__ __device__ __forceinline__ int pg_cell_index(int nx, int cx, int cy) {
   return ((((cy >> PG_STRIP_LOG) * nx) + cx) << PG_STRIP_LOG) + (cy & (PG_STRIP - 1));
 }

@@ -60,14 +60,15 @@ __global__ void init_bounds_kernel(unsigned long long* keys) {
 constexpr int PTS = 4;
 __device__ __forceinline__ void ld_xy2(const double2* p, double2& a, double2& b) {
   unsigned long long x0, y0, x1, y1;
-  asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(y0), "=l"(x1), "=l"(y1) : "l"(p));
+  // volatile + not .nc: stays behind pg_pdl_wait (the coordinates may come from the kernel before this one)
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(y0), "=l"(x1), "=l"(y1) : "l"(p) : "memory");
   a = make_double2(__longlong_as_double((long long)x0), __longlong_as_double((long long)y0));
   b = make_double2(__longlong_as_double((long long)x1), __longlong_as_double((long long)y1));
 }
 
 // the PTS points of thread t of CTA b are b*TPB*PTS + k*TPB*2 + t*2 + {0,1} (k < PTS/2): pairs, so that a warp's
 // 256-bit loads are contiguous
-__device__ __forceinline__ void load_points(const double2* __restrict__ xy, int n, bool aligned32, int base, double2 (&p)[PTS]) {
+__device__ __forceinline__ void load_points(const double2* xy, int n, bool aligned32, int base, double2 (&p)[PTS]) {
 #pragma unroll
   for (int k = 0; k < PTS / 2; ++k) {
     const int i = base + k * TPB * 2;
@@ -81,9 +82,11 @@ __device__ __forceinline__ void load_points(const double2* __restrict__ xy, int 
 }
 
 __global__ void __launch_bounds__(TPB)
-histogram_kernel(const double2* __restrict__ xy, int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny,
-                 int32_t* __restrict__ cell_count, int32_t* bad_input, int epoch) {
+histogram_kernel(const double2* xy, int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny,
+                 int32_t* cell_count, int32_t* bad_input, int epoch) {
   const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
+  pg_pdl_launch();
+  pg_pdl_wait();
   double2 p[PTS];
   load_points(xy, n, aligned32, base, p);
 #pragma unroll
@@ -102,10 +105,12 @@ histogram_kernel(const double2* __restrict__ xy, int n, bool aligned32, double x
 // K4: counting-sort scatter into cell order: one 32-byte record per point, written as one full sector.
 // cursor = B + 1: cursor[c] starts as start(c) and ends as start(c+1). PTS points per thread, as in K2.
 __global__ void __launch_bounds__(TPB)
-scatter_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
-               int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny, int32_t* __restrict__ cursor,
-               pg_rec* __restrict__ rec, int32_t* __restrict__ pos, int32_t* __restrict__ gid_copy) {
+scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
+               int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny, int32_t* cursor,
+               pg_rec* rec, int32_t* pos, int32_t* gid_copy) {
   const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
+  pg_pdl_launch();
+  pg_pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     // sentinel behind the last record: infinitely far from everything (the queries pad their loads with it)
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -221,7 +226,7 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     h->cell_count_clean = true;
   }
   if (n > 0) {
-    PG_LAUNCH(h, s, "histogram_kernel", histogram_kernel<<<pg_div_up(n, TPB * PTS), TPB, 0, s>>>(
+    PG_LAUNCH(h, s, "histogram_kernel", pg_launch_pdl(0, histogram_kernel, pg_div_up(n, TPB * PTS), TPB, s,
         (const double2*)xy, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, (int32_t*)h->cell_count.p,
         (int32_t*)((char*)h->misc.p + PG_MISC_BADINPUT), h->build_epoch));
     PG_LAUNCH_CHECK(h);
@@ -231,7 +236,7 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     return rc;
   }
   if (n > 0) {
-    PG_LAUNCH(h, s, "scatter_kernel", scatter_kernel<<<pg_div_up(n, TPB * PTS), TPB, 0, s>>>(
+    PG_LAUNCH(h, s, "scatter_kernel", pg_launch_pdl(2, scatter_kernel, pg_div_up(n, TPB * PTS), TPB, s,
         (const double2*)xy, type, gid, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p,
         (int32_t*)h->s_pos.p, gid ? (int32_t*)h->s_gid.p : nullptr));
     PG_LAUNCH_CHECK(h);

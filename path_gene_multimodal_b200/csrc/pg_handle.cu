@@ -1,9 +1,18 @@
 // Handle, error text and grow-only workspace of libpathgraph.so.
 #include <cstdarg>
+#include <cstdlib>
 #include <new>
 #include "pg_common.cuh"
 
 static std::string g_create_error;
+
+int pg_pdl_mask() {
+  static int mask = [] {
+    const char* e = getenv("PG_PDL_MASK");
+    return e ? (int)strtol(e, nullptr, 0) : 0x7fffffff;
+  }();
+  return mask;
+}
 
 int pg_set_error(pg_handle* h, int code, const char* fmt, ...) {
   char buf[1024];

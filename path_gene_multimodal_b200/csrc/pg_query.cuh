@@ -18,8 +18,8 @@ struct __align__(32) pg_rec {
 #define PG_TYPE_OTHER_SHIFT 60  // types outside 1..5 land in the 4 spare top bits (never read)
 
 struct pg_grid_view {
-  const int32_t* __restrict__ cell_start;
-  const pg_rec* __restrict__ rec;
+  const int32_t* cell_start;  // no __restrict__: const + restrict loads become LDG.CONSTANT (see pg_ld_rec)
+  const pg_rec* rec;
   int32_t n, n_query, nx, ny, nys;
   double x0, y0, cell, inv_cell;
 };
@@ -37,8 +37,21 @@ static inline pg_grid_view pg_make_view(const pg_handle* h) {
 // 256-bit global load / store (LDG.E.256 / STG.E.256 on sm_100a)
 __device__ __forceinline__ pg_rec pg_ld_rec(const pg_rec* p) {
   unsigned long long a, b, c, d;
-  // .nc: the records are read-only for the lifetime of every query kernel; not volatile so loads can be batched
-  asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  // NOT .nc: the query kernels may be scheduled (programmatic dependent launch) while the scatter that writes the
+  // records is still running, and ptxas hoists .nc loads above griddepcontrol.wait. Not volatile, so the loads of
+  // a batch can be issued back to back.
+  asm("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  pg_rec r;
+  r.x = __longlong_as_double((long long)a);
+  r.y = __longlong_as_double((long long)b);
+  r.row = (int32_t)(uint32_t)c; r.id = (int32_t)(uint32_t)(c >> 32);
+  r.type = (int32_t)(uint32_t)d; r.tshift = (int32_t)(uint32_t)(d >> 32);
+  return r;
+}
+// same load, but ordered after earlier volatile asm (pg_pdl_wait): for the first read of a kernel
+__device__ __forceinline__ pg_rec pg_ld_rec_ordered(const pg_rec* p) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
   pg_rec r;
   r.x = __longlong_as_double((long long)a);
   r.y = __longlong_as_double((long long)b);
@@ -52,7 +65,6 @@ __device__ __forceinline__ void pg_st_rec(pg_rec* p, double x, double y, int row
   const unsigned long long d = (unsigned long long)(uint32_t)type | ((unsigned long long)(uint32_t)tshift << 32);
   asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
-__device__ __forceinline__ double2 pg_ld_xy(const pg_rec* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // Rows ya..yb (inclusive, inside the grid) of column x as contiguous runs of the cell-ordered array: one run
 // per strip touched (see the cell order in pg_common.cuh).

@@ -73,7 +73,7 @@ __device__ __forceinline__ pg_pt_meta ld_meta(const pg_pt_meta* p) {
 // slots past the end read the sentinel record at `pad` (infinitely far away, rejected by every f).
 // flush() at least once every FIELD_MAX slots and once at the end.
 template <class F, class FL>
-__device__ __forceinline__ void walk_runs3(const pg_rec* __restrict__ rec, int b0, int e0, int b1, int e1, int b2, int e2,
+__device__ __forceinline__ void walk_runs3(const pg_rec* rec, int b0, int e0, int b1, int e1, int b2, int e2,
                                            int pad, F&& f, FL&& flush) {
   const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
   const int off1 = b1 - n0, off2 = b2 - n01;
@@ -156,10 +156,12 @@ radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
   __shared__ int s_alloc;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_alloc = 0;
+  pg_pdl_launch();
   __syncthreads();
+  pg_pdl_wait();
 
   const int q = blockIdx.x * TPB_WALK + tid;
-  const pg_rec me = pg_ld_rec(g.rec + min(q, g.n - 1));
+  const pg_rec me = pg_ld_rec_ordered(g.rec + min(q, g.n - 1));
   const bool active = q < g.n && me.row < g.n_query;  // halo points own no row
   int cnt = 0, cx = 0, cy = 0;
   pg_pt_meta m;
@@ -274,7 +276,7 @@ struct rows_out {
 // The statistics are reduced between publishing the tile's aggregate and reading the predecessors', i.e. inside
 // the look-back wait.
 __global__ void __launch_bounds__(TPB_ROWS)
-radius_rows_kernel(int n_query, const int32_t* __restrict__ pos, const pg_pt_meta* __restrict__ meta, pg_scan_state st, rows_out o) {
+radius_rows_kernel(int n_query, const int32_t* pos, const pg_pt_meta* meta, pg_scan_state st, rows_out o) {
   using TS = pg_tile_scan<TPB_ROWS>;
   __shared__ typename TS::smem_t sm;
   __shared__ int s_hist[PG_ACC_HIST_MAX];
@@ -285,6 +287,8 @@ radius_rows_kernel(int n_query, const int32_t* __restrict__ pos, const pg_pt_met
   const int tile = blockIdx.x;
   const int row0 = tile * ROWS_TILE + tid * ROWS_ITEMS;
   const bool full = row0 + ROWS_ITEMS <= n_query;
+  pg_pdl_launch();
+  pg_pdl_wait();
 
   pg_pt_meta m[ROWS_ITEMS];
   int p[ROWS_ITEMS];
@@ -462,11 +466,13 @@ __device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int
 
 // The gather: one warp per 32 consecutive rows = one contiguous range of the outputs, one lane per output entry.
 __global__ void __launch_bounds__(TPB_GATHER)
-radius_gather_kernel(int n_query, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ row_off,
-                     const pg_tmp_ent* __restrict__ tmp, const int32_t* __restrict__ row_gid,
+radius_gather_kernel(int n_query, const int32_t* row_ptr, const int32_t* row_off,
+                     const pg_tmp_ent* tmp, const int32_t* row_gid,
                      fill_out o, long long capacity, int32_t* overflow) {
   const int lane = threadIdx.x & 31;
   const int r0 = ((blockIdx.x * TPB_GATHER + threadIdx.x) >> 5) << 5;
+  pg_pdl_launch();
+  pg_pdl_wait();
   if (r0 >= n_query) return;  // warp-uniform
   const int row = r0 + lane;
   const bool has_row = row < n_query;
@@ -560,7 +566,7 @@ int launch_count_pass(pg_handle* h, cudaStream_t s) {
   w.n_types = a.nbr_count ? a.n_types : 1;
   const int blocks = pg_div_up(gr.n, TPB_WALK);
 #define PG_WALK_LAUNCH(F, U, W) \
-  PG_LAUNCH(h, s, "radius_walk_kernel", radius_walk_kernel<F, U, W><<<blocks, TPB_WALK, 0, s>>>(v, a.r * a.r, R, w))
+  PG_LAUNCH(h, s, "radius_walk_kernel", pg_launch_pdl(3, radius_walk_kernel<F, U, W>, blocks, TPB_WALK, s, v, a.r * a.r, R, w))
   if (wide) {
     if (R == 1) { if (upper) PG_WALK_LAUNCH(true, true, true); else PG_WALK_LAUNCH(true, false, true); }
     else { if (upper) PG_WALK_LAUNCH(false, true, true); else PG_WALK_LAUNCH(false, false, true); }
@@ -586,7 +592,7 @@ int launch_count_pass(pg_handle* h, cudaStream_t s) {
   pg_scan_state st;
   int rc = pg_scan_prepare(h, tiles, TPB_ROWS, s, &st);
   if (rc) return rc;
-  PG_LAUNCH(h, s, "radius_rows_kernel", radius_rows_kernel<<<tiles, TPB_ROWS, 0, s>>>(nq, (const int32_t*)h->s_pos.p, (const pg_pt_meta*)h->pt_meta.p, st, o));
+  PG_LAUNCH(h, s, "radius_rows_kernel", pg_launch_pdl(4, radius_rows_kernel, tiles, TPB_ROWS, s, nq, (const int32_t*)h->s_pos.p, (const pg_pt_meta*)h->pt_meta.p, st, o));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -685,7 +691,7 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   fill_out o{col, dist32, dist64, (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges};
   int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
   const int blocks = pg_div_up(gr.n_query, TPB_GATHER);
-  PG_LAUNCH(h, s, "radius_gather_kernel", radius_gather_kernel<<<blocks, TPB_GATHER, 0, s>>>(
+  PG_LAUNCH(h, s, "radius_gather_kernel", pg_launch_pdl(5, radius_gather_kernel, blocks, TPB_GATHER, s,
       gr.n_query, row_ptr, (const int32_t*)h->row_off.p, (const pg_tmp_ent*)h->tmp_ent.p,
       gr.has_gid ? (const int32_t*)h->s_gid.p : nullptr, o, (long long)capacity, ovf));
   PG_LAUNCH_CHECK(h);

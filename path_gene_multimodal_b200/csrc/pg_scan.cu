@@ -15,9 +15,11 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 // this one on the stream and resets the accumulators.
 template <bool CLEAR>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(int32_t* in, int32_t* __restrict__ out, int32_t n, pg_scan_state st, int32_t* total_copy, pg_scan_publish pub) {
+scan_kernel(int32_t* in, int32_t* out, int32_t n, pg_scan_state st, int32_t* total_copy, pg_scan_publish pub) {
   using TS = pg_tile_scan<SCAN_THREADS>;
   __shared__ typename TS::smem_t sm;
+  pg_pdl_launch();
+  pg_pdl_wait();
   if (pub.acc && blockIdx.x == 0) pg_publish_stats(pub, SCAN_THREADS);
   const int tile = TS::take_tile(sm, st);
   const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -108,9 +110,9 @@ int pg_scan_i32(pg_handle* h, const int32_t* in, int32_t* out, int32_t n, cudaSt
   int rc = pg_scan_prepare(h, num_tiles, SCAN_THREADS, s, &st);
   if (rc) return rc;
   if (clear_in)
-    PG_LAUNCH(h, s, "scan_kernel", scan_kernel<true><<<num_tiles, SCAN_THREADS, 0, s>>>(const_cast<int32_t*>(in), out, n, st, total_copy, pub));
+    PG_LAUNCH(h, s, "scan_kernel", pg_launch_pdl(1, scan_kernel<true>, num_tiles, SCAN_THREADS, s, const_cast<int32_t*>(in), out, n, st, total_copy, pub));
   else
-    PG_LAUNCH(h, s, "scan_kernel", scan_kernel<false><<<num_tiles, SCAN_THREADS, 0, s>>>(const_cast<int32_t*>(in), out, n, st, total_copy, pub));
+    PG_LAUNCH(h, s, "scan_kernel", pg_launch_pdl(1, scan_kernel<false>, num_tiles, SCAN_THREADS, s, const_cast<int32_t*>(in), out, n, st, total_copy, pub));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
