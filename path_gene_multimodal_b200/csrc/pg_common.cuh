@@ -53,6 +53,7 @@ struct pg_handle {
     double r = 0; int32_t flags = 0; int32_t* row_ptr = nullptr; int32_t* degree = nullptr; int32_t* nbr_count = nullptr;
     int32_t n_types = 0; pg_degree_stats* stats = nullptr; int32_t* hist = nullptr; int32_t hist_len = 0;
   } last_count;
+  pg_buf knn_retry;    // int32 [N]     cell-order positions of the points the kNN block pass could not finish
   pg_buf row_count;    // int32 [N+1]   per-row counts before the scan (K7)
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
@@ -98,6 +99,7 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
+#define PG_MISC_KNN_RETRY 76  // int32: points the kNN block pass handed to the ring pass
 #define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
 #define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])

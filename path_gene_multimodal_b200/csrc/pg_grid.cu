@@ -57,7 +57,7 @@ __global__ void init_bounds_kernel(unsigned long long* keys) {
 
 // K2: PTS points per thread (independent 256-bit loads in flight, one wave of CTAs for 1M points), reduction
 // atomics (no return value, nothing else written)
-constexpr int PTS = 4;
+constexpr int PTS = 2;
 __device__ __forceinline__ void ld_xy2(const double2* p, double2& a, double2& b) {
   unsigned long long x0, y0, x1, y1;
   // volatile + not .nc: stays behind pg_pdl_wait (the coordinates may come from the kernel before this one)
@@ -114,7 +114,7 @@ scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     // sentinel behind the last record: infinitely far from everything (the queries pad their loads with it)
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    pg_st_rec(rec + n, inf, inf, 0x7fffffff, -1, 0, PG_TYPE_OTHER_SHIFT);
+    pg_st_rec(rec + n, inf, inf, 0x7fffffff, 0x7fffffff, 0, PG_TYPE_OTHER_SHIFT);
   }
   double2 p[PTS];
   int t[PTS], id[PTS], dst[PTS];

@@ -1,118 +1,270 @@
 // K5: k-nearest-neighbour query on the uniform grid.
 // Reference: /root/reference/hovernet_tile_inference.ipynb:1815-1850 - KNN.from_array(coords, k)
 // (libpysal -> scipy cKDTree.query(k+1) minus self) and the per-neighbour sqrt(dx*dx+dy*dy).
-// Order is the canonical (d^2, id) of north_star; self is removed by index, so duplicates at
+// Order is the canonical (d^2, id) of north_star; self is removed by id, so duplicates at
 // distance 0 are ordinary neighbours.
+//
+// Two passes, both one thread per point in cell order with the k best kept sorted in registers:
+//   block pass (k <= 16): searches only the 3x3 block of cells around the point - three contiguous runs of the
+//       strip-ordered record array, walked as one merged loop with four 256-bit loads in flight, exactly like the
+//       radius walk. Sorted insertion is what costs (about 6 k instructions) and inside a warp it would run
+//       whenever ANY lane has a hit, i.e. at nearly every candidate; so hits are only appended to a small
+//       shared-memory buffer, and the whole warp merges its buffers together when one of them is about to fill
+//       (and once at the end). The loop bounds are made warp-uniform for that (lanes past their own end read the
+//       sentinel record at infinity). A point is final when its k-th distance does not reach past the block;
+//       the rare others are appended to a retry list.
+//   ring pass: the general search (ring expansion until the k-th distance is inside the searched block) over the
+//       retry list - or over every point when k > 16.
+#include <algorithm>
 #include <cmath>
 #include "pg_query.cuh"
 
 namespace {
 
 constexpr int TPB = 128;
+constexpr int BUF = 16;  // buffered hits per thread (12 B x BUF x TPB = 24 KB of shared memory)
 
+// The k best so far, ascending by (d2, id), RIGHT-aligned in KMAX register slots: the k-th best always sits in the
+// last slot (so the bar is a fixed register, whatever k is) and the KMAX - k slots in front hold -infinity, which
+// nothing ever sorts before. Every index below is a compile-time constant, so the list stays in registers.
 template <int KMAX>
 struct topk {
   double d2[KMAX];
   int id[KMAX];
-  __device__ __forceinline__ void init() {
+  __device__ __forceinline__ void init(int k) {
 #pragma unroll
-    for (int s = 0; s < KMAX; ++s) { d2[s] = __longlong_as_double(0x7ff0000000000000ll); id[s] = 0x7fffffff; }
+    for (int s = 0; s < KMAX; ++s) {
+      const bool used = s >= KMAX - k;
+      d2[s] = __longlong_as_double(used ? 0x7ff0000000000000ll : 0xfff0000000000000ll);
+      id[s] = used ? 0x7fffffff : -1;
+    }
   }
-  // insert (cd2, cid), known to sort before slot k-1; fully unrolled so the lists stay in registers
-  __device__ __forceinline__ void insert(double cd2, int cid, int k) {
-    bool placed = false;
+  // insert (cd2, cid), known to sort before the last slot: the last slot drops out. The place r of the newcomer
+  // is counted with KMAX - 1 independent comparisons (no serial "already placed" chain), then every slot picks
+  // its new content with two integer tests.
+  __device__ __forceinline__ void insert(double cd2, int cid) {
+    int r = 0;
+#pragma unroll
+    for (int s = 0; s < KMAX - 1; ++s) r += (d2[s] < cd2 || (d2[s] == cd2 && id[s] < cid)) ? 1 : 0;
 #pragma unroll
     for (int s = KMAX - 1; s > 0; --s) {
-      if (s < k && !placed) {
-        const bool before_prev = cd2 < d2[s - 1] || (cd2 == d2[s - 1] && cid < id[s - 1]);
-        if (before_prev) { d2[s] = d2[s - 1]; id[s] = id[s - 1]; }
-        else { d2[s] = cd2; id[s] = cid; placed = true; }
-      }
+      const bool shift = s > r, here = s == r;
+      d2[s] = shift ? d2[s - 1] : (here ? cd2 : d2[s]);
+      id[s] = shift ? id[s - 1] : (here ? cid : id[s]);
     }
-    if (!placed) { d2[0] = cd2; id[0] = cid; }
+    if (r == 0) { d2[0] = cd2; id[0] = cid; }
   }
-  __device__ __forceinline__ double worst_d2(int k) const {
-    double w = d2[0];
-#pragma unroll
-    for (int s = 1; s < KMAX; ++s) if (s == k - 1) w = d2[s];
-    return w;
-  }
-  __device__ __forceinline__ int worst_id(int k) const {
-    int w = id[0];
-#pragma unroll
-    for (int s = 1; s < KMAX; ++s) if (s == k - 1) w = id[s];
-    return w;
-  }
+  __device__ __forceinline__ double worst_d2() const { return d2[KMAX - 1]; }
+  __device__ __forceinline__ int worst_id() const { return id[KMAX - 1]; }
 };
 
-// One thread per point in cell order. Ring expansion: after the (2R+1)^2 block has been searched
-// the result is final once the k-th best distance is no larger than the distance from the query
-// to the nearest face of the block that still has cells behind it.
+// the same list for large k, in local memory (dynamic indexing, loops kept rolled): 64 slots do not fit registers
 template <int KMAX>
-__global__ void __launch_bounds__(TPB)
-knn_kernel(pg_grid_view g, int k, int32_t* __restrict__ knn_idx, double* __restrict__ dist64,
-           float* __restrict__ dist32, double x_lo, double x_hi, int32_t* halo_ok) {
-  const int p = blockIdx.x * TPB + threadIdx.x;
-  if (p >= g.n) return;
-  const pg_rec me = pg_ld_rec(g.rec + p);
-  if (me.row >= g.n_query) return;
-  const double2 q = make_double2(me.x, me.y);
-  const int cx = pg_cell_coord(q.x, g.x0, g.inv_cell, g.nx);
-  const int cy = pg_cell_coord(q.y, g.y0, g.inv_cell, g.ny);
-  topk<KMAX> top;
-  top.init();
-  double wd2 = top.d2[0];
-  int wid = top.id[0];
-  auto scan = [&](int b, int e) {
-    for (int j = b; j < e; ++j) {
-      const pg_rec c = pg_ld_rec(g.rec + j);
-      const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
-      if (d2 <= wd2 && j != p) {
-        const int cid = c.id;
-        if (d2 < wd2 || cid < wid) {
-          top.insert(d2, cid, k);
-          wd2 = top.worst_d2(k);
-          wid = top.worst_id(k);
-        }
-      }
+struct topk_local {
+  double d2[KMAX];
+  int id[KMAX];
+  __device__ __forceinline__ void init(int k) {
+#pragma unroll 1
+    for (int s = 0; s < KMAX; ++s) {
+      const bool used = s >= KMAX - k;
+      d2[s] = __longlong_as_double(used ? 0x7ff0000000000000ll : 0xfff0000000000000ll);
+      id[s] = used ? 0x7fffffff : -1;
     }
-  };
-  const double margin = 1e-6 * g.cell;
-  int R = 1;
-  pg_visit_block(g, cx, cy, 1, scan);
-  while (true) {
-    const bool covers = cx - R <= 0 && cx + R >= g.nx - 1 && cy - R <= 0 && cy + R >= g.ny - 1;
-    if (covers) break;
-    // distance to the faces of the searched block that have unsearched cells behind them
-    double bound = __longlong_as_double(0x7ff0000000000000ll);
-    if (cx - R > 0) bound = fmin(bound, q.x - (g.x0 + (double)(cx - R) * g.cell));
-    if (cx + R < g.nx - 1) bound = fmin(bound, (g.x0 + (double)(cx + R + 1) * g.cell) - q.x);
-    if (cy - R > 0) bound = fmin(bound, q.y - (g.y0 + (double)(cy - R) * g.cell));
-    if (cy + R < g.ny - 1) bound = fmin(bound, (g.y0 + (double)(cy + R + 1) * g.cell) - q.y);
-    bound -= margin;
-    if (bound > 0.0 && wd2 <= bound * bound) break;
-    ++R;
-    pg_visit_ring(g, cx, cy, R, scan);
   }
-  const int64_t o = (int64_t)me.row * k;
-#pragma unroll
+  __device__ __forceinline__ void insert(double cd2, int cid) {
+    int s = KMAX - 1;
+#pragma unroll 1
+    while (s > 0 && (cd2 < d2[s - 1] || (cd2 == d2[s - 1] && cid < id[s - 1]))) { d2[s] = d2[s - 1]; id[s] = id[s - 1]; --s; }
+    d2[s] = cd2; id[s] = cid;
+  }
+  __device__ __forceinline__ double worst_d2() const { return d2[KMAX - 1]; }
+  __device__ __forceinline__ int worst_id() const { return id[KMAX - 1]; }
+};
+
+struct knn_out {
+  int32_t* knn_idx;
+  double* dist64;
+  float* dist32;
+  double x_lo, x_hi;
+  int32_t* halo_ok;
+};
+
+template <int KMAX, class TOP>
+__device__ __forceinline__ void write_row(const knn_out& o, const TOP& top, int k, int row, double qx) {
+  const int64_t base = (int64_t)row * k - (KMAX - k);
+#pragma unroll (KMAX <= 32 ? KMAX : 1)
   for (int s = 0; s < KMAX; ++s) {
-    if (s < k) {
-      knn_idx[o + s] = top.id[s];
+    if (s >= KMAX - k) {
+      o.knn_idx[base + s] = top.id[s];
       const double d = sqrt(top.d2[s]);
-      if (dist64) dist64[o + s] = d;
-      if (dist32) dist32[o + s] = (float)d;
+      if (o.dist64) o.dist64[base + s] = d;
+      if (o.dist32) o.dist32[base + s] = (float)d;
     }
   }
-  if (halo_ok) {
+  if (o.halo_ok) {
     // every point with x in [x_lo, x_hi) is present; the answer is complete iff the k-th
     // neighbour is strictly closer than both faces (slack keeps the test conservative)
-    const double dk = sqrt(wd2) * (1.0 + 1e-9);
-    if (!(dk < q.x - x_lo && dk < x_hi - q.x)) atomicExch(halo_ok, 0);
+    const double dk = sqrt(top.worst_d2()) * (1.0 + 1e-9);
+    if (!(dk < qx - o.x_lo && dk < o.x_hi - qx)) atomicExch(o.halo_ok, 0);
   }
 }
 
-__global__ void set_flag_kernel(int32_t* f, int v) { *f = v; }
+// distance from (qx, qy) in cell (cx, cy) to the nearest face of the (2R+1)^2 block that still has cells behind it
+// (infinity when the block covers the grid), minus a safety margin
+__device__ __forceinline__ double block_bound(const pg_grid_view& g, double qx, double qy, int cx, int cy, int R) {
+  double bound = __longlong_as_double(0x7ff0000000000000ll);
+  if (cx - R > 0) bound = fmin(bound, qx - (g.x0 + (double)(cx - R) * g.cell));
+  if (cx + R < g.nx - 1) bound = fmin(bound, (g.x0 + (double)(cx + R + 1) * g.cell) - qx);
+  if (cy - R > 0) bound = fmin(bound, qy - (g.y0 + (double)(cy - R) * g.cell));
+  if (cy + R < g.ny - 1) bound = fmin(bound, (g.y0 + (double)(cy + R + 1) * g.cell) - qy);
+  return bound - 1e-6 * g.cell;
+}
+
+// ---- block pass
+template <int KMAX>
+__global__ void __launch_bounds__(TPB)
+knn_block_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* retry_count) {
+  __shared__ double s_d2[BUF][TPB];
+  __shared__ int s_id[BUF][TPB];
+  const unsigned FULL = 0xffffffffu;
+  const int tid = threadIdx.x;
+  pg_pdl_launch();
+  pg_pdl_wait();
+  const int p = blockIdx.x * TPB + tid;
+  const int pad = g.n;  // the sentinel record
+  const pg_rec me = pg_ld_rec_ordered(g.rec + min(p, g.n - 1));
+  const bool active = p < g.n && me.row < g.n_query;
+  const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
+  const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
+  topk<KMAX> top;
+  top.init(k);
+  double wd2 = top.worst_d2();
+  int wid = top.worst_id();
+  int nb = 0;
+
+  auto merge = [&]() __attribute__((always_inline)) {  // warp-uniform: every lane folds its buffered hits into its sorted list
+    const int mx = __reduce_max_sync(FULL, nb);
+    for (int b = 0; b < mx; ++b) {
+      if (b < nb) {
+        const double cd2 = s_d2[b][tid];
+        const int cid = s_id[b][tid];
+        if (cd2 < wd2 || (cd2 == wd2 && cid < wid)) {  // the bar may have moved since the hit was buffered
+          top.insert(cd2, cid);
+          wd2 = top.worst_d2();
+          wid = top.worst_id();
+        }
+      }
+    }
+    nb = 0;
+  };
+  auto consider = [&](const pg_rec& c) __attribute__((always_inline)) {
+    const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+    if ((d2 < wd2 || (d2 == wd2 && c.id < wid)) && c.id != me.id) {
+      s_d2[nb][tid] = d2; s_id[nb][tid] = c.id;
+      ++nb;
+    }
+  };
+
+  const int sy = cy >> PG_STRIP_LOG, ly = cy & (PG_STRIP - 1);
+  const bool has_l = cx > 0, has_r = cx + 1 < g.nx;
+  int edge = -1;  // strip-edge points: the row across the edge lives in the adjacent strip (see the radius walk)
+  if (active) {
+    if (ly == 0 && sy > 0) edge = (((sy - 1) * g.nx + cx) << PG_STRIP_LOG) + PG_STRIP - 1;
+    else if (ly == PG_STRIP - 1 && sy + 1 < g.nys) edge = ((sy + 1) * g.nx + cx) << PG_STRIP_LOG;
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && !__any_sync(FULL, edge >= 0)) break;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0, b2 = 0, e2 = 0;
+    if (active && (pass == 0 || edge >= 0)) {
+      const int32_t* c;
+      int lo, hi;
+      if (pass == 0) {
+        c = g.cell_start + ((sy * g.nx + cx) << PG_STRIP_LOG);
+        lo = max(ly - 1, 0); hi = min(ly + 1, PG_STRIP - 1) + 1;
+      } else {
+        c = g.cell_start + edge;
+        lo = 0; hi = 1;
+      }
+      b1 = c[lo]; e1 = c[hi];
+      if (has_l) { b0 = c[lo - PG_STRIP]; e0 = c[hi - PG_STRIP]; }
+      if (has_r) { b2 = c[lo + PG_STRIP]; e2 = c[hi + PG_STRIP]; }
+    }
+    // the point's own column first: its near candidates lower the bar before the side columns are looked at
+    const int n0 = e1 - b1, n01 = n0 + (e0 - b0), tot = n01 + (e2 - b2);
+    const int off1 = b0 - n0, off2 = b2 - n01;
+    auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b1 : (t < n01 ? off1 : off2)) : pad; };
+    const int tmax = __reduce_max_sync(FULL, tot);
+    for (int t = 0; t < tmax; t += 4) {
+      const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+      const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
+      const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
+      consider(r0); consider(r1); consider(r2); consider(r3);
+      if (__any_sync(FULL, nb > BUF - 4)) merge();
+    }
+  }
+  merge();
+  if (!active) return;
+  // final iff the k-th distance does not reach past the faces of the block that have cells behind them
+  const double bound = block_bound(g, me.x, me.y, cx, cy, 1);
+  const bool covers = cx - 1 <= 0 && cx + 1 >= g.nx - 1 && cy - 1 <= 0 && cy + 1 >= g.ny - 1;
+  if (covers || (bound > 0.0 && wd2 <= bound * bound)) {
+    write_row<KMAX>(o, top, k, me.row, me.x);
+  } else {
+    retry[atomicAdd(retry_count, 1)] = p;
+  }
+}
+
+// ---- ring pass: over `list[0 .. *list_count)` (positions in the cell-ordered array), or over every point
+template <int KMAX, class TOP>
+__global__ void __launch_bounds__(TPB)
+knn_ring_kernel(pg_grid_view g, int k, knn_out o, const int32_t* list, const int32_t* list_count) {
+  pg_pdl_launch();
+  pg_pdl_wait();
+  const int limit = list ? *list_count : g.n;
+  for (int t = blockIdx.x * TPB + threadIdx.x; t < limit; t += gridDim.x * TPB) {
+    const int p = list ? list[t] : t;
+    const pg_rec me = pg_ld_rec_ordered(g.rec + p);
+    if (me.row >= g.n_query) continue;
+    const double2 q = make_double2(me.x, me.y);
+    const int cx = pg_cell_coord(q.x, g.x0, g.inv_cell, g.nx);
+    const int cy = pg_cell_coord(q.y, g.y0, g.inv_cell, g.ny);
+    TOP top;
+    top.init(k);
+    double wd2 = top.worst_d2();
+    int wid = top.worst_id();
+    auto scan = [&](int b, int e) __attribute__((always_inline)) {
+      for (int j = b; j < e; ++j) {
+        const pg_rec c = pg_ld_rec(g.rec + j);
+        const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
+        if (d2 <= wd2 && c.id != me.id) {
+          const int cid = c.id;
+          if (d2 < wd2 || cid < wid) {
+            top.insert(d2, cid);
+            wd2 = top.worst_d2();
+            wid = top.worst_id();
+          }
+        }
+      }
+    };
+    int R = 1;
+    pg_visit_block(g, cx, cy, 1, scan);
+    while (true) {
+      const bool covers = cx - R <= 0 && cx + R >= g.nx - 1 && cy - R <= 0 && cy + R >= g.ny - 1;
+      if (covers) break;
+      const double bound = block_bound(g, q.x, q.y, cx, cy, R);
+      if (bound > 0.0 && wd2 <= bound * bound) break;
+      ++R;
+      pg_visit_ring(g, cx, cy, R, scan);
+    }
+    write_row<KMAX>(o, top, k, me.row, q.x);
+  }
+}
+
+__global__ void knn_prepare_kernel(int32_t* halo_ok, int32_t* retry_count) {
+  if (halo_ok) *halo_ok = 1;
+  *retry_count = 0;
+}
 
 }  // namespace
 
@@ -127,15 +279,30 @@ extern "C" int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64,
   PG_REQUIRE(h, k >= 1 && k <= PG_MAX_K, "pg_knn: k must be in 1..%d (got %d)", PG_MAX_K, k);
   PG_REQUIRE(h, k < gr.n, "pg_knn: k (%d) must be smaller than the number of points (%d)", k, gr.n);
   PG_REQUIRE(h, knn_idx != nullptr, "pg_knn: knn_idx is NULL");
-  if (halo_ok) { PG_LAUNCH(h, s, "set_flag_kernel", set_flag_kernel<<<1, 1, 0, s>>>(halo_ok, 1)); }
+  int32_t* retry_count = (int32_t*)((char*)h->misc.p + PG_MISC_KNN_RETRY);
+  PG_LAUNCH(h, s, "knn_prepare_kernel", knn_prepare_kernel<<<1, 1, 0, s>>>(halo_ok, retry_count));
+  PG_LAUNCH_CHECK(h);
   if (gr.n_query == 0) return PG_OK;
   pg_grid_view v = pg_make_view(h);
+  knn_out o{knn_idx, dist64, dist32, x_lo, x_hi, halo_ok};
   const int blocks = pg_div_up(gr.n, TPB);
-  if (k <= 4) PG_LAUNCH(h, s, "knn_kernel<4>", knn_kernel<4><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
-  else if (k <= 8) PG_LAUNCH(h, s, "knn_kernel<8>", knn_kernel<8><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
-  else if (k <= 16) PG_LAUNCH(h, s, "knn_kernel<16>", knn_kernel<16><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
-  else if (k <= 32) PG_LAUNCH(h, s, "knn_kernel<32>", knn_kernel<32><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
-  else PG_LAUNCH(h, s, "knn_kernel<64>", knn_kernel<64><<<blocks, TPB, 0, s>>>(v, k, knn_idx, dist64, dist32, x_lo, x_hi, halo_ok));
+  if (k <= 16) {
+    int rc = pg_reserve(h, h->knn_retry, ((size_t)gr.n + 8) * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t* retry = (int32_t*)h->knn_retry.p;
+    const int ring_blocks = std::min(blocks, h->sm_count * 8);
+    if (k <= 8) {
+      PG_LAUNCH(h, s, "knn_block_kernel<8>", pg_launch_pdl(6, knn_block_kernel<8>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_ring_kernel<8>", pg_launch_pdl(7, knn_ring_kernel<8, topk<8>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
+    } else {
+      PG_LAUNCH(h, s, "knn_block_kernel<16>", pg_launch_pdl(6, knn_block_kernel<16>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_ring_kernel<16>", pg_launch_pdl(7, knn_ring_kernel<16, topk<16>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
+    }
+  } else if (k <= 32) {
+    PG_LAUNCH(h, s, "knn_ring_kernel<32>", pg_launch_pdl(7, knn_ring_kernel<32, topk<32>>, blocks, TPB, s, v, (int)k, o, (const int32_t*)nullptr, (const int32_t*)nullptr));
+  } else {
+    PG_LAUNCH(h, s, "knn_ring_kernel<64>", pg_launch_pdl(7, knn_ring_kernel<64, topk_local<64>>, blocks, TPB, s, v, (int)k, o, (const int32_t*)nullptr, (const int32_t*)nullptr));
+  }
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
