@@ -2,99 +2,263 @@
 // stand-alone K8 (neighbour-type composition + degree statistics over any CSR).
 // Reference: /root/reference/hovernet_tile_inference.ipynb:1865-1894 (nx.Graph union, weight = min),
 // :2969-2975 (i<j edge list); composition / degree per SURVEY A.5 (README.md:127,136).
+#include <cstring>
 #include "pg_query.cuh"
 
 namespace {
 
 constexpr int TPB = 256;
-constexpr int SORT_CAP = 48;
 constexpr uint8_t RECIP_INVALID = 255, RECIP_NONE = 254;
 
-// pass A: one thread per directed edge i->j. Records the slot of i inside j's list (or NONE) and
-// counts, per node, the reverse-only edges it will receive.
+// The union is built count -> scan -> push -> rank, one thread per ROW in the first and third step (a row of
+// k ids is one or two sectors: vector loads, k independent reads of the neighbours' rows in flight), one lane per
+// OUTPUT ENTRY in the last:
+//   mark  row i reads the row of each neighbour j and records where i sits in it (the slot, or NONE); every
+//         reverse-only edge i->j bumps row_count[j], the row's own valid entries bump row_count[i].
+//   scan  row_count -> und_row_ptr (the scan clears row_count behind itself: it is the push cursor next).
+//   push  row i writes its own entries (weight = min over both directions) at the front of its range and pushes
+//         each reverse-only edge to the BACK of row j's range (cursor[j] counts arrivals).
+//   rank  a warp owns 32 consecutive rows = one contiguous range of the staged entries; lane p of that range
+//         finds its row by shuffle search, counts the row's smaller ids and writes the entry to its place:
+//         rows leave ascending by column whatever order the pushes arrived in, all output traffic coalesced.
 // Lists hold ids in "column space" (global ids when the rows are a strip + halo of a larger slide):
 // row_id[i] is the id of row i, id_map[id] the row of an id (-1 / >= n: no row here). NULL = identity.
-__global__ void __launch_bounds__(TPB)
-sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k, const int32_t* __restrict__ row_id,
-                const int32_t* __restrict__ id_map, int n_ids, uint8_t* __restrict__ recip,
-                int32_t* __restrict__ extra) {
-  const int64_t e = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (e >= (int64_t)n * k) return;
-  const int i = (int)(e / k);
-  const int my_id = row_id ? row_id[i] : i;
-  const int jid = knn_idx[e];
-  if (jid < 0 || jid == my_id || (id_map && jid >= n_ids) || (!id_map && jid >= n)) { recip[e] = RECIP_INVALID; return; }
-  const int j = id_map ? id_map[jid] : jid;
-  if (j < 0 || j >= n) { recip[e] = RECIP_NONE; return; }  // neighbour has no row here: own entry only
-  const int32_t* row = knn_idx + (int64_t)j * k;
-  int found = RECIP_NONE;
-  for (int s = 0; s < k; ++s)
-    if (row[s] == my_id) { found = s; break; }
-  recip[e] = (uint8_t)found;
-  if (found == RECIP_NONE) atomicAdd(&extra[j], 1);
-}
-
-// per node: own valid entries (start value of its append cursor) and the undirected degree
-__global__ void __launch_bounds__(TPB)
-sym_degree_kernel(const uint8_t* __restrict__ recip, const int32_t* __restrict__ extra, int n, int k,
-                  int32_t* __restrict__ cursor, int32_t* __restrict__ row_count) {
-  const int i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  int own = 0;
-  for (int s = 0; s < k; ++s) own += recip[(int64_t)i * k + s] != RECIP_INVALID;
-  cursor[i] = own;
-  row_count[i] = own + extra[i];
-}
-
-template <class DT>
-__global__ void __launch_bounds__(TPB)
-sym_scatter_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k,
-                   const int32_t* __restrict__ row_id, const int32_t* __restrict__ id_map,
-                   const uint8_t* __restrict__ recip, const int32_t* __restrict__ row_ptr,
-                   int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_col, double* __restrict__ tmp_w) {
-  const int64_t e = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (e >= (int64_t)n * k) return;
-  const uint8_t rc = recip[e];
-  if (rc == RECIP_INVALID) return;
-  const int i = (int)(e / k), slot = (int)(e - (int64_t)i * k);
-  const int jid = knn_idx[e];
-  const int j = id_map ? id_map[jid] : jid;
-  double w = (double)dist[e];
-  if (rc != RECIP_NONE) w = fmin(w, (double)dist[(int64_t)j * k + rc]);  // weight = min over directions
-  int own_rank = 0;
-  for (int s = 0; s < slot; ++s) own_rank += recip[(int64_t)i * k + s] != RECIP_INVALID;
-  const int64_t o = (int64_t)row_ptr[i] + own_rank;
-  tmp_col[o] = jid;
-  tmp_w[o] = w;
-  if (rc == RECIP_NONE && j >= 0 && j < n) {
-    const int64_t r = (int64_t)row_ptr[j] + atomicAdd(&cursor[j], 1);
-    tmp_col[r] = row_id ? row_id[i] : i;
-    tmp_w[r] = w;
+template <int K>
+__device__ __forceinline__ void load_row_i32(const int32_t* __restrict__ p, int k, int (&v)[K ? K : 1]) {
+  if (K == 0) return;
+  if ((K & 3) == 0) {
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+      const int4 t = reinterpret_cast<const int4*>(p)[q];
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < K; ++q) v[q] = p[q];
   }
 }
 
-// rows come out of the scatter in arrival order; emit them ascending by column
+// slot of `id` in the k-list at `row` (NONE if absent)
+template <int K>
+__device__ __forceinline__ int find_slot(const int32_t* __restrict__ row, int k, int id) {
+  int found = RECIP_NONE;
+  if (K != 0) {
+    int v[K ? K : 1];
+    load_row_i32<K>(row, k, v);
+#pragma unroll
+    for (int s = K - 1; s >= 0; --s) found = v[s] == id ? s : found;
+  } else {
+    for (int s = 0; s < k; ++s)
+      if (row[s] == id) { found = s; break; }
+  }
+  return found;
+}
+
+// K = compile-time k (rows 16-byte aligned when k % 4 == 0) or 0 = any k
+template <int K>
 __global__ void __launch_bounds__(TPB)
-sym_sort_rows_kernel(const int32_t* __restrict__ row_ptr, int n, const int32_t* __restrict__ tmp_col,
-                     const double* __restrict__ tmp_w, int32_t* __restrict__ col, double* __restrict__ w64,
-                     float* __restrict__ w32) {
+sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k_rt, const int32_t* __restrict__ row_id,
+                const int32_t* __restrict__ id_map, int n_ids, uint8_t* __restrict__ recip,
+                int32_t* __restrict__ row_count) {
   const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  const int64_t base = row_ptr[i];
-  const int cnt = row_ptr[i + 1] - row_ptr[i];
-  pg_sorted_chunk<SORT_CAP> buf;
-  int emitted = 0, last = -1;
-  while (emitted < cnt) {
-    buf.reset(last);
-    for (int t = 0; t < cnt; ++t) buf.push(tmp_col[base + t], tmp_w[base + t]);
-    if (buf.m == 0) break;
-    for (int t = 0; t < buf.m; ++t) {
-      col[base + emitted + t] = buf.key[t];
-      if (w64) w64[base + emitted + t] = buf.val[t];
-      if (w32) w32[base + emitted + t] = (float)buf.val[t];
+  const int k = K ? K : k_rt;
+  const int my_id = row_id ? row_id[i] : i;
+  const int32_t* mine = knn_idx + (int64_t)i * k;
+  uint8_t* rc_out = recip + (int64_t)i * k;
+  int own = 0;
+  if (K != 0) {
+    int ids[K ? K : 1];
+    load_row_i32<K>(mine, k, ids);
+    int rc[K ? K : 1];
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const int jid = ids[s];
+      int r = RECIP_INVALID;
+      if (!(jid < 0 || jid == my_id || (id_map && jid >= n_ids) || (!id_map && jid >= n))) {
+        const int j = id_map ? id_map[jid] : jid;
+        r = RECIP_NONE;
+        if (j >= 0 && j < n) {  // else: the neighbour has no row here, own entry only
+          r = find_slot<K>(knn_idx + (int64_t)j * k, k, my_id);
+          if (r == RECIP_NONE) atomicAdd(&row_count[j], 1);
+        }
+        ++own;
+      }
+      rc[s] = r;
     }
-    emitted += buf.m;
-    last = buf.key[buf.m - 1];
+    if ((K & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < K / 4; ++q)
+        reinterpret_cast<uint32_t*>(rc_out)[q] = (uint32_t)rc[4 * q] | ((uint32_t)rc[4 * q + 1] << 8) |
+                                                 ((uint32_t)rc[4 * q + 2] << 16) | ((uint32_t)rc[4 * q + 3] << 24);
+    } else {
+#pragma unroll
+      for (int s = 0; s < K; ++s) rc_out[s] = (uint8_t)rc[s];
+    }
+  } else {
+    for (int s = 0; s < k; ++s) {
+      const int jid = mine[s];
+      int r = RECIP_INVALID;
+      if (!(jid < 0 || jid == my_id || (id_map && jid >= n_ids) || (!id_map && jid >= n))) {
+        const int j = id_map ? id_map[jid] : jid;
+        r = RECIP_NONE;
+        if (j >= 0 && j < n) {
+          r = find_slot<0>(knn_idx + (int64_t)j * k, k, my_id);
+          if (r == RECIP_NONE) atomicAdd(&row_count[j], 1);
+        }
+        ++own;
+      }
+      rc_out[s] = (uint8_t)r;
+    }
+  }
+  if (own) atomicAdd(&row_count[i], own);
+}
+
+// a row of K items of T as 16-byte vector loads when the row is a whole number of them (the caller checks the
+// base alignment), scalar loads otherwise
+template <class T, int K>
+__device__ __forceinline__ void load_row(const T* __restrict__ p, T (&v)[K]) {
+  if ((K * sizeof(T)) % 16 == 0) {
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int q = 0; q < (int)(K * sizeof(T) / 16); ++q) {
+      const uint4 t = reinterpret_cast<const uint4*>(p)[q];
+      T tmp[PER];
+      memcpy(tmp, &t, 16);
+#pragma unroll
+      for (int e = 0; e < PER; ++e) v[q * PER + e] = tmp[e];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < K; ++q) v[q] = p[q];
+  }
+}
+
+// push: only the reverse-only edges travel (to the BACK of the target row's range in the staging arrays); a
+// row's own entries are read where they are by the rank pass
+template <class DT>
+__device__ __forceinline__ void push_entry(int s_rc, int jid, DT w, int my_id, int n,
+                                           const int32_t* __restrict__ id_map, const int32_t* __restrict__ row_ptr,
+                                           int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_col,
+                                           DT* __restrict__ tmp_w) {
+  if (s_rc != RECIP_NONE) return;
+  const int j = id_map ? id_map[jid] : jid;
+  if (j < 0 || j >= n) return;
+  const int64_t r = (int64_t)row_ptr[j + 1] - 1 - atomicAdd(&cursor[j], 1);
+  tmp_col[r] = my_id;
+  tmp_w[r] = w;
+}
+
+// K = compile-time k with 16-byte aligned rows, or 0 = any k
+template <class DT, int K>
+__global__ void __launch_bounds__(TPB)
+sym_push_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k_rt,
+                const int32_t* __restrict__ row_id, const int32_t* __restrict__ id_map,
+                const uint8_t* __restrict__ recip, const int32_t* __restrict__ row_ptr,
+                int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_col, DT* __restrict__ tmp_w) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int k = K ? K : k_rt;
+  const int my_id = row_id ? row_id[i] : i;
+  if (K != 0) {
+    constexpr int KK = K ? K : 4;
+    uint32_t rcw[KK / 4];
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < KK / 4; ++q) {
+      rcw[q] = reinterpret_cast<const uint32_t*>(recip + (int64_t)i * KK)[q];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) any |= ((rcw[q] >> (8 * e)) & 0xffu) == RECIP_NONE;
+    }
+    if (!any) return;
+    int ids[KK];
+    DT ds[KK];
+    load_row<int, KK>(knn_idx + (int64_t)i * KK, ids);
+    load_row<DT, KK>(dist + (int64_t)i * KK, ds);
+#pragma unroll
+    for (int s = 0; s < KK; ++s)
+      push_entry<DT>((int)((rcw[s >> 2] >> ((s & 3) * 8)) & 0xffu), ids[s], ds[s], my_id, n, id_map, row_ptr, cursor,
+                     tmp_col, tmp_w);
+  } else {
+    for (int s = 0; s < k; ++s)
+      push_entry<DT>(recip[(int64_t)i * k + s], knn_idx[(int64_t)i * k + s], dist[(int64_t)i * k + s], my_id, n, id_map,
+                     row_ptr, cursor, tmp_col, tmp_w);
+  }
+}
+
+// rank: a warp owns 32 consecutive rows = one contiguous range of the output. Row r's range is its own valid
+// entries (read from its k-list, weight = min over both directions, ipynb:1888-1892) followed by the arrivals
+// staged at the back; every lane takes one entry of the range, counts the entries of the row that sort before
+// it and writes it to its place.
+template <class DT>
+__global__ void __launch_bounds__(TPB)
+sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k,
+                const int32_t* __restrict__ id_map, const uint8_t* __restrict__ recip,
+                const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ tmp_col,
+                const DT* __restrict__ tmp_w, int32_t* __restrict__ col, double* __restrict__ w64,
+                float* __restrict__ w32) {
+  const int lane = threadIdx.x & 31;
+  const int r0 = ((blockIdx.x * TPB + threadIdx.x) >> 5) << 5;
+  if (r0 >= n) return;  // warp-uniform
+  const int rp = row_ptr[min(r0 + lane, n)];
+  const int begin = __shfl_sync(0xffffffffu, rp, 0);
+  const int end = row_ptr[min(r0 + 32, n)];
+  const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+  const int my_cnt = (lane == 31 ? end : rp_next) - rp;
+  int my_own = 0;  // valid entries of the lane's row
+  if (r0 + lane < n)
+    for (int s = 0; s < k; ++s) my_own += recip[(int64_t)(r0 + lane) * k + s] != RECIP_INVALID;
+  for (int p0 = begin; p0 < end; p0 += 32) {
+    const int p = p0 + lane;
+    int kk = 0;  // the last row of the 32 that starts at or before p (empty rows share their start with the next row)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, rp, kk + step);
+      if (v <= p) kk += step;
+    }
+    const int rcnt = __shfl_sync(0xffffffffu, my_cnt, kk);
+    const int rbase = __shfl_sync(0xffffffffu, rp, kk);
+    const int own = __shfl_sync(0xffffffffu, my_own, kk);
+    if (p >= end) continue;
+    const int64_t rowk = (int64_t)(r0 + kk) * k;
+    const int me = p - rbase;  // position in the row's unsorted range: own entries by slot, then the arrivals
+    int c;
+    DT w;
+    int my_slot = -1;
+    if (me < own) {
+      int s = me;
+      if (own != k) {  // skip the invalid slots
+        int seen = 0;
+        for (s = 0; s < k; ++s)
+          if (recip[rowk + s] != RECIP_INVALID && seen++ == me) break;
+      }
+      my_slot = s;
+      c = knn_idx[rowk + s];
+      w = dist[rowk + s];
+      const int rc = recip[rowk + s];
+      if (rc != RECIP_NONE) {
+        const int j = id_map ? id_map[c] : c;
+        w = min(w, dist[(int64_t)j * k + rc]);
+      }
+    } else {
+      c = tmp_col[p];
+      w = tmp_w[p];
+    }
+    // place = number of entries that sort before (id, position): any input yields a permutation
+    int rank = 0;
+    for (int s = 0; s < k; ++s) {
+      const int cu = knn_idx[rowk + s];
+      const bool valid = own == k || recip[rowk + s] != RECIP_INVALID;
+      rank += (valid && (cu < c || (cu == c && (my_slot < 0 || s < my_slot)))) ? 1 : 0;
+    }
+    for (int u = own; u < rcnt; ++u) {
+      const int cu = tmp_col[rbase + u];
+      rank += (cu < c || (cu == c && my_slot < 0 && u < me)) ? 1 : 0;
+    }
+    const int64_t dst = (int64_t)rbase + rank;
+    col[dst] = c;
+    if (w64) w64[dst] = (double)w;
+    if (w32) w32[dst] = (float)w;
   }
 }
 
@@ -114,20 +278,44 @@ upper_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restric
   up_count[i] = end - lo;
 }
 
+// one warp per 32 consecutive rows = one contiguous range of the edge list, one lane per edge (coalesced
+// 16-byte stores); the upper entries of a row are the last up_cnt entries of its (ascending) range
 __global__ void __launch_bounds__(TPB)
 upper_fill_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                   const double* __restrict__ w64, const float* __restrict__ w32,
                   const int32_t* __restrict__ row_id, const int32_t* __restrict__ up_ptr, int n,
                   long long* __restrict__ edges, double* __restrict__ ew64, float* __restrict__ ew32) {
-  const int i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  const int id = row_id ? row_id[i] : i;
-  const int cnt = up_ptr[i + 1] - up_ptr[i];
-  const int64_t src = (int64_t)row_ptr[i + 1] - cnt, dst = up_ptr[i];
-  for (int t = 0; t < cnt; ++t) {
-    if (edges) { edges[2 * (dst + t)] = id; edges[2 * (dst + t) + 1] = col[src + t]; }
-    if (ew64) ew64[dst + t] = w64 ? w64[src + t] : (double)w32[src + t];
-    if (ew32) ew32[dst + t] = w32 ? w32[src + t] : (float)w64[src + t];
+  const int lane = threadIdx.x & 31;
+  const int r0 = ((blockIdx.x * TPB + threadIdx.x) >> 5) << 5;
+  if (r0 >= n) return;  // warp-uniform
+  const int row = min(r0 + lane, n - 1);
+  const int up = up_ptr[min(r0 + lane, n)];
+  const int row_end = row_ptr[row + 1];
+  const int id = row_id ? row_id[row] : row;
+  const int begin = __shfl_sync(0xffffffffu, up, 0);
+  const int end = up_ptr[min(r0 + 32, n)];
+  const bool edges16 = ((uintptr_t)edges & 15) == 0;
+  for (int p0 = begin; p0 < end; p0 += 32) {
+    const int p = p0 + lane;
+    int kk = 0;  // the last row of the 32 whose range starts at or before p
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, up, kk + step);
+      if (v <= p && r0 + kk + step < n) kk += step;
+    }
+    const int ubase = __shfl_sync(0xffffffffu, up, kk);
+    const int nxt = __shfl_sync(0xffffffffu, up, min(kk + 1, 31));
+    const int unext = (kk == 31 || r0 + kk + 1 >= n) ? end : nxt;
+    const int rend = __shfl_sync(0xffffffffu, row_end, kk);
+    const int rid = __shfl_sync(0xffffffffu, id, kk);
+    if (p >= end) continue;
+    const int64_t src = (int64_t)rend - (unext - ubase) + (p - ubase);
+    if (edges) {
+      if (edges16) *reinterpret_cast<longlong2*>(edges + 2 * (int64_t)p) = make_longlong2(rid, col[src]);
+      else { edges[2 * (int64_t)p] = rid; edges[2 * (int64_t)p + 1] = col[src]; }
+    }
+    if (ew64) ew64[p] = w64 ? w64[src] : (double)w32[src];
+    if (ew32) ew32[p] = w32 ? w32[src] : (float)w64[src];
   }
 }
 
@@ -291,18 +479,23 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
              "pg_knn_symmetrize_count: row_id and id_map go together (both NULL = identity)");
   int rc;
   if ((rc = pg_reserve(h, h->sym_extra, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
-  if ((rc = pg_reserve(h, h->sym_cursor, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if ((rc = pg_reserve(h, h->sym_recip, (size_t)n * k + 16))) return rc;
-  if ((rc = pg_reserve(h, h->row_count, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
+  int32_t* row_count = (int32_t*)h->sym_extra.p;
   if (n > 0) {
-    PG_CUDA(h, cudaMemsetAsync(h->sym_extra.p, 0, (size_t)n * sizeof(int32_t), s));
-    PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<<<pg_div_up((int64_t)n * k, TPB), TPB, 0, s>>>(knn_idx, n, k, row_id, id_map, n_ids, (uint8_t*)h->sym_recip.p,
-                                                                  (int32_t*)h->sym_extra.p));
-    PG_LAUNCH(h, s, "sym_degree_kernel", sym_degree_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const uint8_t*)h->sym_recip.p, (const int32_t*)h->sym_extra.p,
-                                                       n, k, (int32_t*)h->sym_cursor.p, (int32_t*)h->row_count.p));
+    PG_CUDA(h, cudaMemsetAsync(row_count, 0, (size_t)n * sizeof(int32_t), s));
+    const int blocks = pg_div_up(n, TPB);
+    const bool vec = ((uintptr_t)knn_idx & 15) == 0;
+#define PG_MARK(K) PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<K><<<blocks, TPB, 0, s>>>(knn_idx, n, k, row_id, id_map, n_ids, (uint8_t*)h->sym_recip.p, row_count))
+    if (vec && k == 8) PG_MARK(8);
+    else if (vec && k == 16) PG_MARK(16);
+    else if (vec && k == 4) PG_MARK(4);
+    else if (k == 5) PG_MARK(5);
+    else PG_MARK(0);
+#undef PG_MARK
     PG_LAUNCH_CHECK(h);
   }
-  return pg_scan_i32(h, (const int32_t*)h->row_count.p, und_row_ptr, n, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1);
+  // the scan leaves row_count all zero again: pg_knn_symmetrize_fill uses it as the push cursor
+  return pg_scan_i32(h, row_count, und_row_ptr, n, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1, true);
 }
 
 int pg_knn_symmetrize_total(pg_handle* h, int64_t* total) {
@@ -336,16 +529,21 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
   pg_buf& tw = h->rank;
   if ((rc = pg_reserve(h, tcol, ((size_t)total + 4) * sizeof(int32_t)))) return rc;
   if ((rc = pg_reserve(h, tw, ((size_t)total + 4) * sizeof(double)))) return rc;
-  const int blocks_e = pg_div_up((int64_t)n * k, TPB);
-  if (dist64)
-    PG_LAUNCH(h, s, "sym_scatter_kernel<double>", sym_scatter_kernel<double><<<blocks_e, TPB, 0, s>>>(knn_idx, dist64, n, k, row_id, id_map, (const uint8_t*)h->sym_recip.p, und_row_ptr,
-                                                       (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
-  else
-    PG_LAUNCH(h, s, "sym_scatter_kernel<float>", sym_scatter_kernel<float><<<blocks_e, TPB, 0, s>>>(knn_idx, dist32, n, k, row_id, id_map, (const uint8_t*)h->sym_recip.p, und_row_ptr,
-                                                      (int32_t*)h->sym_cursor.p, (int32_t*)tcol.p, (double*)tw.p));
-  PG_LAUNCH(h, s, "sym_sort_rows_kernel", sym_sort_rows_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(und_row_ptr, n, (const int32_t*)tcol.p, (const double*)tw.p,
-                                                        und_col, und_w64, und_w32));
+  int32_t* cursor = (int32_t*)h->sym_extra.p;  // all zero since the count pass's scan
+  const uint8_t* recip = (const uint8_t*)h->sym_recip.p;
+  const int blocks = pg_div_up(n, TPB);
+#define PG_PUSH(DT, D, K) PG_LAUNCH(h, s, "sym_push_kernel", sym_push_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, row_id, id_map, recip, und_row_ptr, cursor, (int32_t*)tcol.p, (DT*)tw.p))
+  const bool vec = (((uintptr_t)knn_idx | (uintptr_t)dist64 | (uintptr_t)dist32) & 15) == 0;
+  if (dist64) {
+    if (vec && k == 8) PG_PUSH(double, dist64, 8); else if (vec && k == 16) PG_PUSH(double, dist64, 16); else PG_PUSH(double, dist64, 0);
+    PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<double><<<blocks, TPB, 0, s>>>(knn_idx, dist64, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const double*)tw.p, und_col, und_w64, und_w32));
+  } else {
+    if (vec && k == 8) PG_PUSH(float, dist32, 8); else if (vec && k == 16) PG_PUSH(float, dist32, 16); else PG_PUSH(float, dist32, 0);
+    PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<float><<<blocks, TPB, 0, s>>>(knn_idx, dist32, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const float*)tw.p, und_col, und_w64, und_w32));
+  }
+#undef PG_PUSH
   PG_LAUNCH_CHECK(h);
+  // the cursor holds the arrival counts now; the next count pass clears it again
   return PG_OK;
 }
 

@@ -107,6 +107,59 @@ def test_map_morph_ragged_and_degenerate(engine):
     assert feat["area"][4] == 12.0
 
 
+@pytest.mark.parametrize("vt", [np.float32, np.float64])
+def test_map_morph_staging_boundaries(engine, vt):
+    # the warp's vertex range goes through a shared-memory slab by bulk copy (16-byte granularity) when it fits and
+    # is walked straight from global memory (8-lane groups) when it does not: exercise odd range starts, vertex
+    # arrays that are only 8-byte aligned, input / output with different alignment phases, rings closed explicitly
+    # (33 vertices), and warps whose range is too long for the slab, all in one table
+    n = 5000
+    rng = np.random.default_rng(99)
+    nv = rng.integers(3, 34, size=n)
+    nv[32 * 7: 32 * 9] = rng.integers(40, 90, size=64)       # two warps past the slab capacity
+    nv[32 * 20 + 5] = 1500                                    # one huge ring inside an otherwise ordinary warp
+    nv[rng.integers(0, n, size=50)] = 0
+    off = np.zeros(n + 1, dtype=np.int32)
+    off[1:] = np.cumsum(nv)
+    m = int(off[-1])
+    owner = np.repeat(np.arange(n), nv)
+    kth = np.arange(m) - off[owner]
+    t = 2 * np.pi * kth / np.maximum(nv[owner], 1)
+    a, b = rng.uniform(4, 12, n), rng.uniform(2, 4, n)
+    cen = rng.uniform(0, 508, (n, 2))
+    xy = np.stack([cen[owner, 0] + a[owner] * np.cos(t), cen[owner, 1] + b[owner] * np.sin(t)], axis=1)
+    xy = (np.round(xy * 2) / 2).astype(vt)
+    closed = np.flatnonzero(nv == 33)                         # make the 33-vertex rings explicitly closed
+    xy[off[closed] + 32] = xy[off[closed]]
+    tile_x = (np.arange(16) * 508).astype(np.int32)
+    tile_y = (np.arange(16)[::-1] * 508).astype(np.int32)
+    nuc_tile = rng.integers(0, 16, size=n).astype(np.int32)
+    feat = omorph.polygon_features_csr(off, xy.astype(np.float64))
+    want = xy.astype(np.float64) + np.stack([tile_x[nuc_tile][owner], tile_y[nuc_tile][owner]], axis=1)
+    for in_shift, out_shift in ((0, 0), (1, 1), (1, 0)):
+        buf = torch.zeros((m + 2, 2), dtype=dev(xy).dtype, device="cuda")
+        src = buf[in_shift: in_shift + m]
+        src.copy_(dev(xy))
+        if vt is np.float64 and in_shift:                     # double2 rows stay 16-byte aligned under a row shift
+            assert src.data_ptr() % 16 == 0
+        dst_buf = torch.full((m + 2, 2), -7.0, dtype=src.dtype, device="cuda")
+        dst = dst_buf[out_shift: out_shift + m]
+        res = engine.map_morph(dev(off), src, dev(nuc_tile), dev(tile_x), dev(tile_y), write_polygons=True, extra=True,
+                               out={"wsi_poly_xy": dst})
+        assert res["wsi_poly_xy"].data_ptr() == dst.data_ptr()
+        assert np.array_equal(dst.cpu().numpy().astype(np.float64), want), (in_shift, out_shift)
+        guard = dst_buf.cpu().numpy()
+        assert (guard[:out_shift] == -7.0).all() and (guard[out_shift + m:] == -7.0).all()   # nothing written outside
+        for name in ("area", "perimeter", "circularity"):
+            np.testing.assert_allclose(res[name].cpu().numpy(), feat[name], rtol=RTOL, equal_nan=True, err_msg=name)
+        np.testing.assert_allclose(res["eccentricity"].cpu().numpy(), feat["eccentricity"], rtol=RTOL, atol=ECC_ATOL,
+                                   equal_nan=True)
+        bb = res["poly_bbox"].cpu().numpy()
+        ok = nv >= 3
+        assert np.array_equal(bb[ok, 0], feat["bbox_xmin"][ok] + tile_x[nuc_tile][ok])
+        assert np.array_equal(bb[ok, 3], feat["bbox_ymax"][ok] + tile_y[nuc_tile][ok])
+
+
 def test_map_morph_full_size_properties(engine):
     # C3 shape (reduced count so the oracle finishes in seconds is covered above); here: 2M x 32, invariants only
     n = 2_000_000
