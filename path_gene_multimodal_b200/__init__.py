@@ -8,6 +8,8 @@ Public surface (reference-style module-level functions; see DESIGN.md / INTEGRAT
     build_knn_graph, build_radius_graph,
     neighbour_type_composition, degree_stats,
     filter_graph_by_type                                  (cell_graph)
+    read_nuclei_table, write_nuclei_table, table_to_soa,
+    add_wsi_coords_to_table, process_nuclei_file          (nuclei_io: Parquet / CSV <-> SoA / CSR)
 Everything computes in libpathgraph.so (csrc/, C ABI in include/pathgraph.h); no CPU fallback.
 """
 __version__ = "0.1.0"
@@ -20,6 +22,8 @@ _EXPORTS = {
     "build_knn_graph": "cell_graph", "build_radius_graph": "cell_graph",
     "neighbour_type_composition": "cell_graph", "degree_stats": "cell_graph",
     "filter_graph_by_type": "cell_graph",
+    "read_nuclei_table": "nuclei_io", "write_nuclei_table": "nuclei_io", "table_to_soa": "nuclei_io",
+    "add_wsi_coords_to_table": "nuclei_io", "process_nuclei_file": "nuclei_io",
     "Engine": "engine", "get_engine": "engine",
 }
 

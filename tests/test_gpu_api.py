@@ -67,6 +67,33 @@ def test_add_wsi_coords_empty_frame():
     assert len(got) == 0 and "wsi_polygon" in got.columns and "wsi_centroid_x" in got.columns
 
 
+def test_process_nuclei_file_matches_reference_golden(tmp_path, golden_add_wsi):
+    # file -> file: the reference's Parquet layout in, the reference's two files out, CUDA in between
+    from path_gene_multimodal_b200 import nuclei_io
+
+    nuc, tiles, expected = frames_from_golden(golden_add_wsi)
+    src, out_pq, out_csv = tmp_path / "local.parquet", tmp_path / "wsi.parquet", tmp_path / "wsi.csv"
+    nuc.to_parquet(src, index=False)
+    table = nuclei_io.process_nuclei_file(src, tiles, out_pq, out_csv, morphology=True)
+    assert table.column_names[:len(golden_add_wsi["out_columns"])] == golden_add_wsi["out_columns"]
+    ref_csv = tmp_path / "ref.csv"
+    got = pd.read_parquet(out_pq)
+    for c in golden_add_wsi["out_columns"]:
+        if c in nuclei_io.LIST_COLUMNS:
+            for a, b in zip(got[c], expected[c]):
+                assert (a is None and b is None) or np.array_equal(np.array(a.tolist(), dtype=np.float64), np.array(b, dtype=np.float64)), c
+        elif expected[c].dtype.kind in "fi":
+            assert np.array_equal(got[c].to_numpy(), expected[c].to_numpy()), c
+        else:
+            assert got[c].tolist() == expected[c].tolist(), c
+    expected.to_csv(ref_csv, index=False)
+    ours = pd.read_csv(out_csv)
+    assert ours[golden_add_wsi["out_columns"]].to_csv(index=False) == ref_csv.read_text()
+    soa = nuclei_io.table_to_soa(table)
+    feat = omorph.polygon_features_csr(soa.poly_off, soa.poly_xy)
+    np.testing.assert_allclose(got["area"].to_numpy(), feat["area"], rtol=1e-5, equal_nan=True)
+
+
 def test_polygon_morphology_tables(known_answers):
     from path_gene_multimodal_b200 import nuclei_morphology_table, polygon_morphology_table
 
