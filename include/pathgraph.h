@@ -198,6 +198,16 @@ int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_
                    int32_t* gid, int32_t n_base, int32_t capacity, int32_t* count_out,
                    pg_stream stream);
 
+/* ---- K10: node features for the GNN input.  hovernet_tile_inference.ipynb:2903 (cell 21:
+ * z = (v - mean) / std(ddof=0), NaN-skipping statistics, a column with sigma 0 / NaN becomes all 0.0) and
+ * ipynb:2950 (cell 23: pd.get_dummies(type, prefix="type"), features = one-hot columns then the *_z columns).
+ * feat float64 [n_feat][n] (one contiguous column per feature), type int32 [n], onehot_values int32 [n_onehot]
+ * (the distinct type values, ascending) -> x float32 [n][n_onehot + n_feat] row-major, stats float64
+ * [n_feat][2] = {mean, sigma} (device).  Deterministic (fixed-order pairwise merge of moments). */
+int pg_node_features(pg_handle* h, int32_t n, int32_t n_feat, const double* feat, const int32_t* type,
+                     const int32_t* onehot_values, int32_t n_onehot, float* x, double* stats,
+                     pg_stream stream);
+
 /* ---- launch accounting and per-kernel timing (CUDA events recorded on the launching stream) ----
  * pg_launch_count: kernels launched through this handle so far.
  * pg_profile_enable(1) starts recording one (name, start, stop) event pair per kernel launch and

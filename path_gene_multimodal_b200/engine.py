@@ -349,6 +349,21 @@ class Engine:
             self._p(hist, torch.int32, "hist"), int(hist_len) if hist is not None else 0, self._stream()))
         return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
 
+    # ---- K10 -----------------------------------------------------------------------------------
+    def node_features(self, feat, types=None, onehot_values=None):
+        """z-scored feature columns + type one-hot -> x float32 [N, n_onehot + n_feat] (pg_node_features).
+
+        feat float64 [n_feat, N] (one row per feature column), types int32 [N], onehot_values int32 [n_onehot]."""
+        n_feat, n = (int(feat.shape[0]), int(feat.shape[1])) if feat is not None else (0, int(types.numel()))
+        n_oh = int(onehot_values.numel()) if onehot_values is not None else 0
+        x = self._empty((n, n_oh + n_feat), torch.float32)
+        stats = self._empty((n_feat, 2), torch.float64)
+        self._check(self.lib.pg_node_features(
+            self._h, n, n_feat, self._p(feat, torch.float64, "feat"), self._p(types, torch.int32, "types"),
+            self._p(onehot_values, torch.int32, "onehot_values"), n_oh, self._p(x, torch.float32, "x"),
+            self._p(stats, torch.float64, "stats"), self._stream()))
+        return {"x": x, "stats": stats}
+
     # ---- K9 ------------------------------------------------------------------------------------
     def halo_pack(self, xy, types, gid, lo_edge, hi_edge, capacity):
         """Records (24 B: x, y, gid, type) of the points with x < lo_edge or x >= hi_edge."""

@@ -87,8 +87,10 @@ def test_process_nuclei_file_matches_reference_golden(tmp_path, golden_add_wsi):
         else:
             assert got[c].tolist() == expected[c].tolist(), c
     expected.to_csv(ref_csv, index=False)
-    ours = pd.read_csv(out_csv)
-    assert ours[golden_add_wsi["out_columns"]].to_csv(index=False) == ref_csv.read_text()
+    twin = tmp_path / "twin.csv"
+    nuclei_io.write_nuclei_table(table.select(golden_add_wsi["out_columns"]), csv_path=twin)
+    assert twin.read_text() == ref_csv.read_text()           # the CSV twin, byte for byte
+    assert out_csv.read_text().splitlines()[0].startswith(ref_csv.read_text().splitlines()[0])
     soa = nuclei_io.table_to_soa(table)
     feat = omorph.polygon_features_csr(soa.poly_off, soa.poly_xy)
     np.testing.assert_allclose(got["area"].to_numpy(), feat["area"], rtol=1e-5, equal_nan=True)
@@ -174,3 +176,63 @@ def test_non_finite_coordinates_raise(golden_graph):
     # and the handle is usable again afterwards
     g = build_radius_graph(coords, r=40.0)
     assert np.array_equal(g["edges"], ograph.radius_graph(coords, 40.0)["edges"])
+
+
+def _feature_frame(n, seed):
+    rng = np.random.default_rng(seed)
+    df = pd.DataFrame({
+        "type": rng.choice([1, 2, 3, 5], size=n, p=[0.5, 0.25, 0.2, 0.05]),     # type 4 absent: no type_4 column
+        "area": rng.gamma(5.0, 40.0, size=n),
+        "perimeter": rng.gamma(9.0, 6.0, size=n),
+        "eccentricity": rng.random(n),
+        "solidity": np.full(n, 0.75),                                            # constant column -> all 0.0
+        "major_axis_length": rng.gamma(6.0, 3.0, size=n) + 1e6,                  # large offset: cancellation test
+        "compactness": np.full(n, np.nan),                                       # empty column -> all 0.0
+        "elongation": rng.random(n) + 1.0,
+        "x_um": rng.random(n) * 0.25 * 508 * np.sqrt(n / 101.0),
+        "y_um": rng.random(n) * 0.25 * 508 * np.sqrt(n / 101.0),
+    })
+    df.loc[rng.integers(0, n, size=max(1, n // 50)), "area"] = np.nan            # NaN rows are skipped by mean / std
+    return df
+
+
+@pytest.mark.parametrize("n", [1, 101, 50_000])
+def test_node_feature_matrix_against_the_notebook_cells(n):
+    from oracle import features as ofeat
+    from path_gene_multimodal_b200 import node_feature_matrix
+
+    df = _feature_frame(n, seed=40 + n)
+    want, want_cols = ofeat.node_features(df)
+    got = node_feature_matrix(df)
+    assert got["columns"] == want_cols
+    n_oh = sum(c.startswith("type_") for c in want_cols)
+    assert got["x"].dtype == np.float32 and got["x"].shape == want.shape
+    assert np.array_equal(got["x"][:, :n_oh], want[:, :n_oh])                    # one-hot: exact
+    np.testing.assert_allclose(got["x"][:, n_oh:], want[:, n_oh:], rtol=1e-5, atol=1e-6, equal_nan=True)
+    again = node_feature_matrix(df)
+    assert np.array_equal(again["x"], got["x"], equal_nan=True)                  # deterministic reduction order
+    for c in ("solidity_z", "compactness_z"):
+        assert (got["x"][:, want_cols.index(c)] == 0.0).all()
+    cols = [c[:-2] for c in want_cols[n_oh:]]
+    np.testing.assert_allclose(got["mean"], [df[c].mean() for c in cols], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(got["std"], [df[c].std(ddof=0) for c in cols], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_assemble_graph_data_cells_23_to_27():
+    from oracle import features as ofeat
+    from path_gene_multimodal_b200 import assemble_graph_data
+
+    df = _feature_frame(3000, seed=7)
+    data = assemble_graph_data(df, r=40.0)
+    coords = df[["x_um", "y_um"]].to_numpy()
+    ref = ograph.radius_graph(coords, 40.0)
+    edges = ref["edges"]
+    assert np.array_equal(data["edges"], edges)
+    assert np.array_equal(data["edge_index"], np.hstack([edges.T, edges[:, ::-1].T]))          # SURVEY B-3 layout
+    dists = np.linalg.norm(coords[edges[:, 0]] - coords[edges[:, 1]], axis=1)                   # cell 26
+    want_attr = np.concatenate([dists[:, None], dists[:, None]], axis=0).astype(np.float32)
+    assert np.array_equal(data["edge_attr"], want_attr)
+    want_x, want_cols = ofeat.node_features(df)
+    assert data["feat_cols"] == want_cols and data["x"].shape == want_x.shape
+    np.testing.assert_allclose(data["x"], want_x, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(data["pos"], coords)

@@ -177,3 +177,19 @@ def test_zscore_rule():
     assert omorph.zscore([2.0, 2.0, 2.0]).tolist() == [0.0, 0.0, 0.0]          # sigma == 0 -> 0.0 (ipynb:2905-2906)
     z = omorph.zscore([1.0, 2.0, 3.0])
     assert abs(z.std()) - 1 < 1e-12 and abs(z.mean()) < 1e-12
+
+
+def test_feature_oracle_is_the_notebook_rule():
+    # cell 21 / 23 semantics on a hand-checkable frame: NaN-skipping mean / std(ddof=0), constant -> 0.0,
+    # one-hot columns only for the types present, ascending, before the z columns
+    import pandas as pd
+    from oracle import features as ofeat
+
+    df = pd.DataFrame({"type": [3, 1, 3, 5], "area": [1.0, 2.0, 3.0, np.nan], "solidity": [0.5] * 4,
+                       "elongation": [1.0, 1.0, 3.0, 3.0]})
+    x, cols = ofeat.node_features(df)
+    assert cols == ["type_1", "type_3", "type_5", "area_z", "solidity_z", "elongation_z"]
+    assert x.dtype == np.float32 and x[:, :3].tolist() == [[0, 1, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    s = np.sqrt(2.0 / 3.0)
+    np.testing.assert_allclose(x[:3, 3], np.array([-1 / s, 0.0, 1 / s], dtype=np.float32), rtol=1e-6)
+    assert np.isnan(x[3, 3]) and (x[:, 4] == 0).all() and x[:, 5].tolist() == [-1.0, -1.0, 1.0, 1.0]
