@@ -198,6 +198,15 @@ int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_
                    int32_t* gid, int32_t n_base, int32_t capacity, int32_t* count_out,
                    pg_stream stream);
 
+/* ---- K11: graph statistics the reference names (README.md:133-136 "cell-cell interaction patterns",
+ * "degree, clustering, centrality") over a symmetric CSR with ascending rows (K6 / K7 output).
+ * triangles int32 [n] (through node i), coeff float64 [n] = 2 T / (d (d - 1)), 0 for d < 2 (networkx.clustering);
+ * either may be NULL.  inter int64 [n_types][n_types]: inter[a][b] = directed edges from type a+1 to type b+1. */
+int pg_clustering(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,
+                  int32_t* triangles, double* coeff, pg_stream stream);
+int pg_type_interactions(pg_handle* h, int32_t n, const int32_t* type, const int32_t* nbr_count,
+                         int32_t n_types, int64_t* inter, pg_stream stream);
+
 /* ---- K10: node features for the GNN input.  hovernet_tile_inference.ipynb:2903 (cell 21:
  * z = (v - mean) / std(ddof=0), NaN-skipping statistics, a column with sigma 0 / NaN becomes all 0.0) and
  * ipynb:2950 (cell 23: pd.get_dummies(type, prefix="type"), features = one-hot columns then the *_z columns).

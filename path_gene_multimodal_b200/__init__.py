@@ -7,7 +7,8 @@ Public surface (reference-style module-level functions; see DESIGN.md / INTEGRAT
     polygon_morphology_table, nuclei_morphology_table     (polygon_morphology)
     build_knn_graph, build_radius_graph,
     neighbour_type_composition, degree_stats,
-    filter_graph_by_type                                  (cell_graph)
+    filter_graph_by_type, clustering_coefficients,
+    type_interaction_matrix                               (cell_graph)
     read_nuclei_table, write_nuclei_table, table_to_soa,
     add_wsi_coords_to_table, process_nuclei_file          (nuclei_io: Parquet / CSV <-> SoA / CSR)
     node_feature_matrix, assemble_graph_data, to_pyg      (graph_features: z-scores + one-hot -> x, PyG Data)
@@ -22,7 +23,8 @@ _EXPORTS = {
     "tag_polygons": "polygon_morphology", "zscore_columns": "polygon_morphology",
     "build_knn_graph": "cell_graph", "build_radius_graph": "cell_graph",
     "neighbour_type_composition": "cell_graph", "degree_stats": "cell_graph",
-    "filter_graph_by_type": "cell_graph",
+    "filter_graph_by_type": "cell_graph", "clustering_coefficients": "cell_graph",
+    "type_interaction_matrix": "cell_graph",
     "read_nuclei_table": "nuclei_io", "write_nuclei_table": "nuclei_io", "table_to_soa": "nuclei_io",
     "add_wsi_coords_to_table": "nuclei_io", "process_nuclei_file": "nuclei_io",
     "node_feature_matrix": "graph_features", "assemble_graph_data": "graph_features", "to_pyg": "graph_features",

@@ -72,6 +72,8 @@ SIGNATURES = {
     "pg_compose_degree": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]),
     "pg_halo_pack": (C.c_int, [vp, i32, vp, vp, vp, f64, f64, vp, i32, vp, vp]),
     "pg_halo_unpack": (C.c_int, [vp, vp, i32, i32, i32, f64, f64, vp, vp, vp, i32, i32, vp, vp]),
+    "pg_clustering": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+    "pg_type_interactions": (C.c_int, [vp, i32, vp, vp, i32, vp, vp]),
     "pg_node_features": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "pg_exclusive_scan_i32": (C.c_int, [vp, vp, vp, i32, vp]),
 }

@@ -162,3 +162,28 @@ def filter_graph_by_type(edges, types, keep_types=(1, 2)):
     keep = np.isin(t, list(keep_types))
     e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
     return np.nonzero(keep)[0], e[keep[e[:, 0]] & keep[e[:, 1]]]
+
+
+def clustering_coefficients(row_ptr, col, device=None) -> dict:
+    """``triangles`` int32 [N] and ``clustering`` float64 [N] (= networkx.clustering) of a symmetric CSR with
+    ascending rows (README.md:136 "clustering"); ``degree_centrality`` = degree / (N - 1) (networkx's definition)."""
+    eng = get_engine(device)
+    with torch.cuda.device(eng.device):
+        d_rp = _host.to_device(_host.as_int32(row_ptr, "row_ptr"), np.int32, eng.device)
+        d_col = _host.to_device(_host.as_int32(col, "col"), np.int32, eng.device)
+        res = eng.clustering(d_rp, d_col)
+        out = _host.to_host_many(res)
+    n = len(out["clustering"])
+    deg = np.diff(np.asarray(row_ptr, dtype=np.int64))
+    out["degree_centrality"] = deg / (n - 1.0) if n > 1 else np.ones(n)
+    return out
+
+
+def type_interaction_matrix(types, nbr_count, n_types: int = 5, device=None) -> np.ndarray:
+    """int64 [T,T]: number of directed edges from a node of type a+1 to a neighbour of type b+1 (README.md:133
+    "cell-cell interaction patterns"); symmetric for an undirected graph, diagonal counts each edge twice."""
+    eng = get_engine(device)
+    with torch.cuda.device(eng.device):
+        d_t = _host.to_device(_host.as_int32(types, "types"), np.int32, eng.device)
+        d_c = _host.to_device(_host.as_int32(nbr_count, "nbr_count"), np.int32, eng.device)
+        return _host.to_host(eng.type_interactions(d_t, d_c, n_types))

@@ -2,6 +2,7 @@
 // stand-alone K8 (neighbour-type composition + degree statistics over any CSR).
 // Reference: /root/reference/hovernet_tile_inference.ipynb:1865-1894 (nx.Graph union, weight = min),
 // :2969-2975 (i<j edge list); composition / degree per SURVEY A.5 (README.md:127,136).
+#include <algorithm>
 #include <cstring>
 #include "pg_query.cuh"
 
@@ -404,6 +405,77 @@ __global__ void finish_stats_kernel(pg_degree_stats* stats) {
   if (stats->n_nodes == 0) { stats->min_degree = 0; stats->max_degree = 0; }
 }
 
+// ---- K11 graph statistics named by the reference (README.md:136 "degree, clustering, centrality")
+// Local clustering coefficient over a symmetric CSR with ascending rows (what K6 / K7 emit): one lane per
+// directed edge (i, j) of a warp's 32 consecutive rows counts |N(i) & N(j)| by merging the two sorted rows; the
+// per-edge counts are added to tri2[i] (integer atomics: order-independent), which ends as twice the number of
+// triangles through i; coeff = tri2 / (d (d - 1)), 0 for d < 2 - networkx.clustering's definition.
+__global__ void __launch_bounds__(TPB)
+clustering_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int n,
+                        int32_t* __restrict__ tri2) {
+  const int lane = threadIdx.x & 31;
+  const int r0 = ((blockIdx.x * TPB + threadIdx.x) >> 5) << 5;
+  if (r0 >= n) return;  // warp-uniform
+  const int rp = row_ptr[min(r0 + lane, n)];
+  const int begin = __shfl_sync(0xffffffffu, rp, 0);
+  const int end = row_ptr[min(r0 + 32, n)];
+  const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+  const int my_cnt = (lane == 31 ? end : rp_next) - rp;
+  for (int p0 = begin; p0 < end; p0 += 32) {
+    const int p = p0 + lane;
+    int kk = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, rp, kk + step);
+      if (v <= p) kk += step;
+    }
+    const int rcnt = __shfl_sync(0xffffffffu, my_cnt, kk);
+    const int rbase = __shfl_sync(0xffffffffu, rp, kk);
+    if (p >= end) continue;
+    const int i = r0 + kk, j = col[p];
+    if (j == i || j < 0 || j >= n) continue;  // self loops / foreign ids close no triangle here
+    int a = rbase, a_end = rbase + rcnt, b = row_ptr[j], b_end = row_ptr[j + 1], common = 0;
+    while (a < a_end && b < b_end) {
+      const int ca = col[a], cb = col[b];
+      common += (ca == cb && ca != i && ca != j) ? 1 : 0;
+      a += ca <= cb;
+      b += cb <= ca;
+    }
+    if (common) atomicAdd(&tri2[i], common);
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+clustering_finish_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ tri2, int n,
+                         int32_t* __restrict__ triangles, double* __restrict__ coeff) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int d = row_ptr[i + 1] - row_ptr[i], t2 = tri2[i];
+  if (triangles) triangles[i] = t2 >> 1;
+  if (coeff) coeff[i] = d < 2 ? 0.0 : (double)t2 / ((double)d * (double)(d - 1));
+}
+
+// type-type interaction counts: inter[a][b] = number of (directed) edges from a node of type a+1 to a node of
+// type b+1 = sum of nbr_count rows grouped by the row's own type ("cell-cell interaction patterns", README.md:133)
+__global__ void __launch_bounds__(TPB)
+interactions_kernel(const int32_t* __restrict__ type, const int32_t* __restrict__ nbr_count, int n, int n_types,
+                    unsigned long long* __restrict__ inter) {
+  __shared__ unsigned long long s_acc[PG_MAX_TYPES * PG_MAX_TYPES];
+  for (int q = threadIdx.x; q < n_types * n_types; q += TPB) s_acc[q] = 0ull;
+  __syncthreads();
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    const int t = type[i];
+    if (t < 1 || t > n_types) continue;
+    for (int b = 0; b < n_types; ++b) {
+      const int c = nbr_count[(int64_t)i * n_types + b];
+      if (c) atomicAdd(&s_acc[(t - 1) * n_types + b], (unsigned long long)c);
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_types * n_types; q += TPB)
+    if (s_acc[q]) atomicAdd(&inter[q], s_acc[q]);
+}
+
 // ---- K9 halo pack / unpack ---------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB)
 halo_pack_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid,
@@ -611,6 +683,41 @@ int pg_compose_degree(pg_handle* h, int32_t n, const int32_t* row_ptr, const int
     PG_LAUNCH_CHECK(h);
   }
   if (stats) PG_LAUNCH(h, s, "finish_stats_kernel", finish_stats_kernel<<<1, 1, 0, s>>>(stats));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+int pg_clustering(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col, int32_t* triangles,
+                  double* coeff, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n >= 0 && row_ptr, "pg_clustering: bad argument");
+  if (n == 0) return PG_OK;
+  PG_REQUIRE(h, col != nullptr, "pg_clustering: col is NULL");
+  int rc;
+  if ((rc = pg_reserve(h, h->row_count, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
+  int32_t* tri2 = (int32_t*)h->row_count.p;
+  PG_CUDA(h, cudaMemsetAsync(tri2, 0, (size_t)n * sizeof(int32_t), s));
+  PG_LAUNCH(h, s, "clustering_count_kernel", clustering_count_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, col, n, tri2));
+  PG_LAUNCH(h, s, "clustering_finish_kernel", clustering_finish_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(row_ptr, tri2, n, triangles, coeff));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+int pg_type_interactions(pg_handle* h, int32_t n, const int32_t* type, const int32_t* nbr_count, int32_t n_types,
+                         int64_t* inter, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n >= 0 && n_types >= 1 && n_types <= PG_MAX_TYPES && inter, "pg_type_interactions: bad argument");
+  PG_REQUIRE(h, n == 0 || (type && nbr_count), "pg_type_interactions: type / nbr_count is NULL");
+  PG_CUDA(h, cudaMemsetAsync(inter, 0, (size_t)n_types * n_types * sizeof(int64_t), s));
+  if (n == 0) return PG_OK;
+  const int blocks = std::min(pg_div_up(n, TPB), h->sm_count * 4);
+  PG_LAUNCH(h, s, "interactions_kernel", interactions_kernel<<<blocks, TPB, 0, s>>>(type, nbr_count, n, n_types, (unsigned long long*)inter));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

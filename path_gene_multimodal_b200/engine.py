@@ -349,6 +349,28 @@ class Engine:
             self._p(hist, torch.int32, "hist"), int(hist_len) if hist is not None else 0, self._stream()))
         return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
 
+    # ---- K11 -----------------------------------------------------------------------------------
+    def clustering(self, row_ptr, col):
+        """Triangles through each node and the local clustering coefficient over a symmetric CSR (pg_clustering)."""
+        n = int(row_ptr.numel()) - 1
+        tri = self._empty((n,), torch.int32)
+        coeff = self._empty((n,), torch.float64)
+        if col is None or col.numel() == 0:  # no edges: no triangles (the C entry needs a col array to read)
+            return {"triangles": tri.zero_(), "clustering": coeff.zero_()}
+        self._check(self.lib.pg_clustering(self._h, n, self._p(row_ptr, torch.int32, "row_ptr"),
+                                           self._p(col, torch.int32, "col"), self._p(tri, torch.int32, "triangles"),
+                                           self._p(coeff, torch.float64, "coeff"), self._stream()))
+        return {"triangles": tri, "clustering": coeff}
+
+    def type_interactions(self, types, nbr_count, n_types=5):
+        """inter int64 [T,T]: directed edges from type a+1 to type b+1 (pg_type_interactions)."""
+        n = int(types.numel())
+        inter = self._empty((n_types, n_types), torch.int64)
+        self._check(self.lib.pg_type_interactions(self._h, n, self._p(types, torch.int32, "types"),
+                                                  self._p(nbr_count, torch.int32, "nbr_count"), int(n_types),
+                                                  self._p(inter, torch.int64, "inter"), self._stream()))
+        return inter
+
     # ---- K10 -----------------------------------------------------------------------------------
     def node_features(self, feat, types=None, onehot_values=None):
         """z-scored feature columns + type one-hot -> x float32 [N, n_onehot + n_feat] (pg_node_features).

@@ -236,3 +236,35 @@ def test_assemble_graph_data_cells_23_to_27():
     assert data["feat_cols"] == want_cols and data["x"].shape == want_x.shape
     np.testing.assert_allclose(data["x"], want_x, rtol=1e-5, atol=1e-6)
     assert np.array_equal(data["pos"], coords)
+
+
+def test_graph_statistics_against_networkx():
+    # README.md:133-136 "cell-cell interaction patterns", "degree, clustering, centrality" 
+    import networkx as nx
+    from path_gene_multimodal_b200 import (build_knn_graph, build_radius_graph, clustering_coefficients,
+                                           filter_graph_by_type, type_interaction_matrix)
+
+    xy, types, _ = synth.make_points(4000, 21)
+    for g in (build_radius_graph(xy, r=60.0, types=types, symmetric_csr=True), build_knn_graph(xy, k=6, types=types)):
+        G = nx.Graph()
+        G.add_nodes_from(range(len(xy)))
+        G.add_edges_from(map(tuple, g["edges"]))
+        st = clustering_coefficients(g["row_ptr"], g["col"])
+        want = nx.clustering(G)
+        np.testing.assert_allclose(st["clustering"], [want[i] for i in range(len(xy))], rtol=1e-12, atol=0)
+        tri = nx.triangles(G)
+        assert np.array_equal(st["triangles"], [tri[i] for i in range(len(xy))])
+        dc = nx.degree_centrality(G)
+        np.testing.assert_allclose(st["degree_centrality"], [dc[i] for i in range(len(xy))], rtol=1e-12)
+        inter = type_interaction_matrix(types, g["nbr_count"])
+        e = g["edges"]
+        want_i = np.zeros((5, 5), dtype=np.int64)
+        np.add.at(want_i, (types[e[:, 0]] - 1, types[e[:, 1]] - 1), 1)
+        np.add.at(want_i, (types[e[:, 1]] - 1, types[e[:, 0]] - 1), 1)
+        assert np.array_equal(inter, want_i)
+        # cell 12: the type-filtered sub-graph
+        nodes, sub = filter_graph_by_type(e, types, keep_types=(1, 2))
+        H = G.subgraph([i for i in range(len(xy)) if types[i] in (1, 2)])
+        assert len(nodes) == H.number_of_nodes() and len(sub) == H.number_of_edges()
+    empty = clustering_coefficients(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int64))
+    assert (empty["clustering"] == 0).all() and (empty["triangles"] == 0).all()
