@@ -325,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                                 "traffic": traffic, "traffic_source": traffic_src,
                                 "algorithmic_bytes_per_launch": int(kb), "avg_launch_ms": avg[dom],
                                 "share_of_step": share[dom] / step_sum, "peak_source": peak_src,
-                                "note": "the kernel is L1 / issue bound, not DRAM bound (ncu: L1TEX 77 %, issue 62 %, DRAM 8 % of peak); "
+                                "note": "the kernel is L1 / issue bound, not DRAM bound (ncu r1h: L1TEX 77 %, issue 62 %, DRAM 10 % of peak); "
                                         "its cold-cache DRAM traffic is below the algorithmic bytes because the parked entries and most "
                                         "of the meta records stay in L2"}
         alg = algorithmic_bytes(n, 2 * e_und)
@@ -355,7 +355,7 @@ def other_stages(eng, dev, flush, peak):
     import torch
 
     from path_gene_multimodal_b200 import synth
-    from path_gene_multimodal_b200.engine import default_knn_cell
+    from path_gene_multimodal_b200.engine import default_knn_cell, radius_cell
 
     def timed(fn, reps=5):
         ms = []
@@ -413,6 +413,44 @@ def other_stages(eng, dev, flush, peak):
 
     ms = timed(knn_union, reps=3)
     out["knn_k8_1M_full(grid+query+union+composition)"] = {"ms": ms, "nuclei_per_s": N_NUCLEI / ms * 1e3}
+    del dx, dt_, kres
+
+    # C1 (100k nuclei, V ~ U{8..32}) and one C4 slide (500k): the whole nuclei-table pass, device-resident -
+    # tile->WSI map + morphology (ragged float32 rings), kNN k=8 + undirected union + i<j edges + composition and,
+    # for C4, the r=50 px radius graph on the WSI centroids the map kernel just produced
+    for name, n_s, seed, with_radius in (("C1_100k", 100_000, synth.SEEDS["C1"], False),
+                                          ("C4_slide_500k", 500_000, synth.SEEDS["C4"], True)):
+        tab = synth.make_table(n_s, seed)
+        side_px = float(tab.n_tiles_side * 508)
+        t_off, t_xy = torch.from_numpy(tab.poly_off).to(dev), torch.from_numpy(tab.poly_xy).to(dev)
+        t_tile = torch.from_numpy(tab.nuc_tile).to(dev)
+        t_tx, t_ty = torch.from_numpy(tab.tile_x).to(dev), torch.from_numpy(tab.tile_y).to(dev)
+        t_cen, t_bb = torch.from_numpy(tab.centroid).to(dev), torch.from_numpy(tab.bbox).to(dev)
+        t_types = torch.from_numpy(tab.types).to(dev)
+        cell_k = default_knn_cell(n_s, side_px ** 2, 8)
+        bnd = (0.0, 0.0, side_px, side_px)
+        keep = {}
+
+        def slide():
+            mm = eng.map_morph(t_off, t_xy, t_tile, t_tx, t_ty, t_cen, t_bb, write_polygons=True, out=keep.get("mm"))
+            keep["mm"] = mm
+            wsi = mm["wsi_centroid"]
+            eng.grid_build(wsi, t_types, None, cell_k, bnd)
+            kn = eng.knn(8, dist_dtype=torch.float32, out=keep.get("kn"))
+            keep["kn"] = kn
+            sym = eng.symmetrize(kn["knn_idx"], kn["dist32"])
+            eng.csr_upper(sym["row_ptr"], sym["col"], sym["w32"])
+            eng.compose_degree(sym["row_ptr"], sym["col"], t_types, N_TYPES)
+            if with_radius:
+                eng.grid_build(wsi, t_types, None, radius_cell(RADIUS), bnd)
+                keep["rg"] = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True,
+                                              out=keep.get("rg"))
+
+        ms = timed(slide, reps=3)
+        m_s = int(tab.poly_xy.shape[0])
+        out[name + "_table_pass(map+morph+kNN8 union" + ("+radius50)" if with_radius else ")")] = {
+            "ms": ms, "nuclei_per_s": n_s / ms * 1e3, "vertices": m_s}
+        del t_off, t_xy, keep
     return out
 
 

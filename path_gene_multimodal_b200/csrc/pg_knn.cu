@@ -4,25 +4,21 @@
 // Order is the canonical (d^2, id) of north_star; self is removed by id, so duplicates at
 // distance 0 are ordinary neighbours.
 //
-// Two passes, both one thread per point in cell order with the k best kept sorted in registers:
-//   block pass (k <= 16): searches only the 3x3 block of cells around the point - three contiguous runs of the
+// Two passes, both one thread per point in cell order:
+//   select pass (k <= 16): searches only the 3x3 block of cells around the point - three contiguous runs of the
 //       strip-ordered record array, walked as one merged loop with four 256-bit loads in flight, exactly like the
-//       radius walk. Sorted insertion is what costs (about 6 k instructions) and inside a warp it would run
-//       whenever ANY lane has a hit, i.e. at nearly every candidate; so hits are only appended to a small
-//       shared-memory buffer, and the whole warp merges its buffers together when one of them is about to fill
-//       (and once at the end). The loop bounds are made warp-uniform for that (lanes past their own end read the
-//       sentinel record at infinity). A point is final when its k-th distance does not reach past the block;
-//       the rare others are appended to a retry list.
-//   ring pass: the general search (ring expansion until the k-th distance is inside the searched block) over the
-//       retry list - or over every point when k > 16.
+//       radius walk - and picks the k nearest by histogram + rank (see knn_select_kernel); a point is final when
+//       its k-th distance does not reach past the block; the others are appended to a retry list.
+//   ring pass: the general search (ring expansion until the k-th distance is inside the searched block, k best
+//       kept sorted in registers) over the retry list - or over every point when k > 16.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "pg_query.cuh"
 
 namespace {
 
 constexpr int TPB = 128;
-constexpr int BUF = 16;  // buffered hits per thread (12 B x BUF x TPB = 24 KB of shared memory)
 
 // The k best so far, ascending by (d2, id), RIGHT-aligned in KMAX register slots: the k-th best always sits in the
 // last slot (so the bar is a fixed register, whatever k is) and the KMAX - k slots in front hold -infinity, which
@@ -120,98 +116,141 @@ __device__ __forceinline__ double block_bound(const pg_grid_view& g, double qx, 
   return bound - 1e-6 * g.cell;
 }
 
-// ---- block pass
+// ---- select pass (k <= 16): the same 3x3 block, but no list is kept sorted while candidates stream by.
+//   pass 1  histogram of the candidates' squared distances below bound^2 (bound = distance to the nearest block
+//           face with cells behind it: nothing beyond it can be trusted) in 16 equal bins of d^2 - uniform points
+//           fill them evenly - packed as 16-bit counters in four registers;
+//   pick    the first bin b* where the running count reaches k: every point of bins 0..b* is a survivor, the k
+//           nearest are among them and (bins being monotone in d^2) nothing outside them can be nearer;
+//   pass 2  walk the runs again (L1 hits) and park the <= KMAX + KMAX/2 survivors in shared memory;
+//   rank    each survivor counts the survivors that sort before it by (d^2, id) and, if fewer than k do, writes
+//           itself straight to that slot of the output row.
+// Every lane does the same amount of work (no insertion that runs whenever ANY lane has a hit). A point whose
+// block cannot answer (fewer than k candidates inside bound, too many survivors, counters would overflow, the
+// block covers the whole grid) goes to the retry list of the ring pass.
+template <class F>
+__device__ __forceinline__ void walk3x3(const pg_grid_view& g, int cx, int cy, F&& f) {
+  const int pad = g.n;  // the sentinel record
+  const int sy = cy >> PG_STRIP_LOG, ly = cy & (PG_STRIP - 1);
+  const bool has_l = cx > 0, has_r = cx + 1 < g.nx;
+  int edge = -1;  // strip-edge points: the row across the edge lives in the adjacent strip
+  if (ly == 0 && sy > 0) edge = (((sy - 1) * g.nx + cx) << PG_STRIP_LOG) + PG_STRIP - 1;
+  else if (ly == PG_STRIP - 1 && sy + 1 < g.nys) edge = ((sy + 1) * g.nx + cx) << PG_STRIP_LOG;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int32_t* c;
+    int lo, hi;
+    if (pass == 0) {
+      c = g.cell_start + ((sy * g.nx + cx) << PG_STRIP_LOG);
+      lo = max(ly - 1, 0); hi = min(ly + 1, PG_STRIP - 1) + 1;
+    } else {
+      if (edge < 0) break;
+      c = g.cell_start + edge;
+      lo = 0; hi = 1;
+    }
+    const int b1 = c[lo], e1 = c[hi];
+    int b0 = 0, e0 = 0, b2 = 0, e2 = 0;
+    if (has_l) { b0 = c[lo - PG_STRIP]; e0 = c[hi - PG_STRIP]; }
+    if (has_r) { b2 = c[lo + PG_STRIP]; e2 = c[hi + PG_STRIP]; }
+    const int n0 = e0 - b0, n01 = n0 + (e1 - b1), tot = n01 + (e2 - b2);
+    const int off1 = b1 - n0, off2 = b2 - n01;
+    auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b0 : (t < n01 ? off1 : off2)) : pad; };
+    for (int t = 0; t < tot; t += 4) {
+      const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+      const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
+      const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
+      f(r0); f(r1); f(r2); f(r3);
+    }
+  }
+}
+
+constexpr int SEL_BINS = 16;
+
 template <int KMAX>
 __global__ void __launch_bounds__(TPB)
-knn_block_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* retry_count) {
-  __shared__ double s_d2[BUF][TPB];
-  __shared__ int s_id[BUF][TPB];
-  const unsigned FULL = 0xffffffffu;
+knn_select_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* retry_count) {
+  constexpr int S = KMAX + KMAX / 2;  // survivors a thread can park
+  __shared__ double s_d2[S][TPB];
+  __shared__ int s_id[S][TPB];
   const int tid = threadIdx.x;
   pg_pdl_launch();
   pg_pdl_wait();
   const int p = blockIdx.x * TPB + tid;
-  const int pad = g.n;  // the sentinel record
-  const pg_rec me = pg_ld_rec_ordered(g.rec + min(p, g.n - 1));
-  const bool active = p < g.n && me.row < g.n_query;
+  if (p >= g.n) return;
+  const pg_rec me = pg_ld_rec_ordered(g.rec + p);
+  if (me.row >= g.n_query) return;  // halo points own no row
   const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
   const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
-  topk<KMAX> top;
-  top.init(k);
-  double wd2 = top.worst_d2();
-  int wid = top.worst_id();
-  int nb = 0;
-
-  auto merge = [&]() __attribute__((always_inline)) {  // warp-uniform: every lane folds its buffered hits into its sorted list
-    const int mx = __reduce_max_sync(FULL, nb);
-    for (int b = 0; b < mx; ++b) {
-      if (b < nb) {
-        const double cd2 = s_d2[b][tid];
-        const int cid = s_id[b][tid];
-        if (cd2 < wd2 || (cd2 == wd2 && cid < wid)) {  // the bar may have moved since the hit was buffered
-          top.insert(cd2, cid);
-          wd2 = top.worst_d2();
-          wid = top.worst_id();
-        }
-      }
-    }
-    nb = 0;
-  };
-  auto consider = [&](const pg_rec& c) __attribute__((always_inline)) {
-    const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
-    if ((d2 < wd2 || (d2 == wd2 && c.id < wid)) && c.id != me.id) {
-      s_d2[nb][tid] = d2; s_id[nb][tid] = c.id;
-      ++nb;
-    }
-  };
-
-  const int sy = cy >> PG_STRIP_LOG, ly = cy & (PG_STRIP - 1);
-  const bool has_l = cx > 0, has_r = cx + 1 < g.nx;
-  int edge = -1;  // strip-edge points: the row across the edge lives in the adjacent strip (see the radius walk)
-  if (active) {
-    if (ly == 0 && sy > 0) edge = (((sy - 1) * g.nx + cx) << PG_STRIP_LOG) + PG_STRIP - 1;
-    else if (ly == PG_STRIP - 1 && sy + 1 < g.nys) edge = ((sy + 1) * g.nx + cx) << PG_STRIP_LOG;
-  }
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1 && !__any_sync(FULL, edge >= 0)) break;
-    int b0 = 0, e0 = 0, b1 = 0, e1 = 0, b2 = 0, e2 = 0;
-    if (active && (pass == 0 || edge >= 0)) {
-      const int32_t* c;
-      int lo, hi;
-      if (pass == 0) {
-        c = g.cell_start + ((sy * g.nx + cx) << PG_STRIP_LOG);
-        lo = max(ly - 1, 0); hi = min(ly + 1, PG_STRIP - 1) + 1;
-      } else {
-        c = g.cell_start + edge;
-        lo = 0; hi = 1;
-      }
-      b1 = c[lo]; e1 = c[hi];
-      if (has_l) { b0 = c[lo - PG_STRIP]; e0 = c[hi - PG_STRIP]; }
-      if (has_r) { b2 = c[lo + PG_STRIP]; e2 = c[hi + PG_STRIP]; }
-    }
-    // the point's own column first: its near candidates lower the bar before the side columns are looked at
-    const int n0 = e1 - b1, n01 = n0 + (e0 - b0), tot = n01 + (e2 - b2);
-    const int off1 = b0 - n0, off2 = b2 - n01;
-    auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b1 : (t < n01 ? off1 : off2)) : pad; };
-    const int tmax = __reduce_max_sync(FULL, tot);
-    for (int t = 0; t < tmax; t += 4) {
-      const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
-      const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
-      const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
-      consider(r0); consider(r1); consider(r2); consider(r3);
-      if (__any_sync(FULL, nb > BUF - 4)) merge();
-    }
-  }
-  merge();
-  if (!active) return;
-  // final iff the k-th distance does not reach past the faces of the block that have cells behind them
   const double bound = block_bound(g, me.x, me.y, cx, cy, 1);
-  const bool covers = cx - 1 <= 0 && cx + 1 >= g.nx - 1 && cy - 1 <= 0 && cy + 1 >= g.ny - 1;
-  if (covers || (bound > 0.0 && wd2 <= bound * bound)) {
-    write_row<KMAX>(o, top, k, me.row, me.x);
-  } else {
+  bool ok = bound > 0.0 && bound < 1e300;  // infinite: the block covers the grid (tiny inputs) - ring pass
+  const double bound2 = ok ? bound * bound : 0.0;
+  const double inv_binw = ok ? (double)SEL_BINS / bound2 : 0.0;
+  ok = ok && inv_binw < 1e300;
+
+  // ---- pass 1: histogram of d^2 below bound^2
+  unsigned long long pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;
+  int seen = 0;
+  auto bin_of = [&](double d2) { return min(SEL_BINS - 1, __double2int_rd(__dmul_rn(d2, inv_binw))); };
+  if (ok) {
+    walk3x3(g, cx, cy, [&](const pg_rec& c) {
+      const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+      ++seen;
+      if (d2 < bound2 && c.id != me.id) {
+        const int b = bin_of(d2);
+        const unsigned long long inc = 1ull << ((b & 3) * 16);
+        const int w = b >> 2;
+        pk0 += w == 0 ? inc : 0ull; pk1 += w == 1 ? inc : 0ull;
+        pk2 += w == 2 ? inc : 0ull; pk3 += w == 3 ? inc : 0ull;
+      }
+    });
+    ok = seen < 65536;  // 16-bit counters
+  }
+  // ---- pick the bin that holds the k-th nearest
+  int bstar = -1, m = 0;
+  if (ok) {
+    int cum = 0;
+#pragma unroll
+    for (int b = 0; b < SEL_BINS; ++b) {
+      const unsigned long long w = b < 4 ? pk0 : (b < 8 ? pk1 : (b < 12 ? pk2 : pk3));
+      cum += (int)((w >> ((b & 3) * 16)) & 0xffffu);
+      if (bstar < 0 && cum >= k) { bstar = b; m = cum; }
+    }
+    ok = bstar >= 0 && m <= S;
+  }
+  if (!ok) {
     retry[atomicAdd(retry_count, 1)] = p;
+    return;
+  }
+  // ---- pass 2: park the survivors
+  int cnt = 0;
+  walk3x3(g, cx, cy, [&](const pg_rec& c) {
+    const double d2 = pg_dist2(me.x, me.y, c.x, c.y);
+    if (d2 < bound2 && c.id != me.id && bin_of(d2) <= bstar && cnt < S) {
+      s_d2[cnt][tid] = d2; s_id[cnt][tid] = c.id;
+      ++cnt;
+    }
+  });
+  // ---- rank: place = number of survivors that sort before (ids are distinct)
+  const int64_t base = (int64_t)me.row * k;
+  for (int a = 0; a < cnt; ++a) {
+    const double da = s_d2[a][tid];
+    const int ia = s_id[a][tid];
+    int rank = 0;
+    for (int b = 0; b < cnt; ++b) {
+      const double db = s_d2[b][tid];
+      const int ib = s_id[b][tid];
+      rank += (db < da || (db == da && ib < ia)) ? 1 : 0;
+    }
+    if (rank < k) {
+      o.knn_idx[base + rank] = ia;
+      const double d = sqrt(da);
+      if (o.dist64) o.dist64[base + rank] = d;
+      if (o.dist32) o.dist32[base + rank] = (float)d;
+      if (rank == k - 1 && o.halo_ok) {  // see write_row
+        const double dk = d * (1.0 + 1e-9);
+        if (!(dk < me.x - o.x_lo && dk < o.x_hi - me.x)) atomicExch(o.halo_ok, 0);
+      }
+    }
   }
 }
 
@@ -292,10 +331,10 @@ extern "C" int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64,
     int32_t* retry = (int32_t*)h->knn_retry.p;
     const int ring_blocks = std::min(blocks, h->sm_count * 8);
     if (k <= 8) {
-      PG_LAUNCH(h, s, "knn_block_kernel<8>", pg_launch_pdl(6, knn_block_kernel<8>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_select_kernel<8>", pg_launch_pdl(6, knn_select_kernel<8>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
       PG_LAUNCH(h, s, "knn_ring_kernel<8>", pg_launch_pdl(7, knn_ring_kernel<8, topk<8>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
     } else {
-      PG_LAUNCH(h, s, "knn_block_kernel<16>", pg_launch_pdl(6, knn_block_kernel<16>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_select_kernel<16>", pg_launch_pdl(6, knn_select_kernel<16>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
       PG_LAUNCH(h, s, "knn_ring_kernel<16>", pg_launch_pdl(7, knn_ring_kernel<16, topk<16>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
     }
   } else if (k <= 32) {

@@ -29,7 +29,9 @@ for _ in range(reps):
     eng.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, 8), bounds)
     kres = eng.knn(8, dist_dtype=torch.float32, out=kres)
 sym = eng.symmetrize(kres["knn_idx"], kres["dist32"])
+eng.csr_upper(sym["row_ptr"], sym["col"], sym["w32"])
 eng.compose_degree(sym["row_ptr"], sym["col"], d_ty, 5)
+eng.clustering(sym["row_ptr"], sym["col"])
 n3 = 2_000_000
 off, pxy = synth.make_polygons(n3, synth.SEEDS["C3"], v_fixed=32)
 rng = np.random.default_rng(3)
