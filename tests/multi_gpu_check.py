@@ -30,8 +30,26 @@ def main():
     edges = sharding.run(sharding.equal_count_edges(l_xy[:, 0].contiguous(), world, 0.0, float(side)), comm)
     s_xy, s_ty, s_gid = sharding.run(sharding.partition_by_strips(l_xy, l_ty, l_gid, edges, rank, world), comm)
     strip = sharding.strips_from_edges(edges)[rank]
-    rg = sharding.run(sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world), comm)
-    kg = sharding.run(sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n), comm)
+    import time
+
+    def timed(make, reps=int(os.environ.get("PG_REPS", 2))):
+        """max-over-ranks wall time (barrier + synchronize on both sides) of the sharded build, best of `reps`."""
+        best, out = None, None
+        for _ in range(reps):
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = sharding.run(make(), comm)
+            torch.cuda.synchronize(); dist.barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            best = float(dt.item()) if best is None else min(best, float(dt.item()))
+        return out, best
+
+    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world))
+    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n))
+    if rank == 0:
+        print(f"sharded build, world={world} n={n}: radius r=50 {t_rad * 1e3:.2f} ms ({n / t_rad / 1e6:.0f} M nuclei/s), "
+              f"kNN k={k} + union + edges {t_knn * 1e3:.2f} ms ({n / t_knn / 1e6:.0f} M nuclei/s)  [halo exchange included]")
     # gather to rank 0 for the comparison
     def gather(t):
         sizes = [None] * world
