@@ -300,18 +300,28 @@ knn_ring_kernel(pg_grid_view g, int k, knn_out o, const int32_t* list, const int
     top.init(k);
     double wd2 = top.worst_d2();
     int wid = top.worst_id();
-    auto scan = [&](int b, int e) __attribute__((always_inline)) {
-      for (int j = b; j < e; ++j) {
-        const pg_rec c = pg_ld_rec(g.rec + j);
-        const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
-        if (d2 <= wd2 && c.id != me.id) {
-          const int cid = c.id;
-          if (d2 < wd2 || cid < wid) {
-            top.insert(d2, cid);
-            wd2 = top.worst_d2();
-            wid = top.worst_id();
-          }
+    auto consider = [&](const pg_rec& c) __attribute__((always_inline)) {
+      const double d2 = pg_dist2(q.x, q.y, c.x, c.y);
+      if (d2 <= wd2 && c.id != me.id) {
+        const int cid = c.id;
+        if (d2 < wd2 || cid < wid) {
+          top.insert(d2, cid);
+          wd2 = top.worst_d2();
+          wid = top.worst_id();
         }
+      }
+    };
+    const int pad = g.n;  // the sentinel record (infinitely far: never inserted)
+    auto scan = [&](int b, int e) __attribute__((always_inline)) {
+      if (KMAX > 16) {  // every point takes this path: one candidate at a time keeps the long list in registers
+        for (int j = b; j < e; ++j) consider(pg_ld_rec(g.rec + j));
+        return;
+      }
+      for (int j = b; j < e; j += 4) {  // four loads in flight: the retried points are few, their latency is what costs
+        const int p1 = j + 1 < e ? j + 1 : pad, p2 = j + 2 < e ? j + 2 : pad, p3 = j + 3 < e ? j + 3 : pad;
+        const pg_rec r0 = pg_ld_rec(g.rec + j), r1 = pg_ld_rec(g.rec + p1);
+        const pg_rec r2 = pg_ld_rec(g.rec + p2), r3 = pg_ld_rec(g.rec + p3);
+        consider(r0); consider(r1); consider(r2); consider(r3);
       }
     };
     int R = 1;
