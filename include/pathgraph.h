@@ -207,6 +207,24 @@ int pg_clustering(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t
 int pg_type_interactions(pg_handle* h, int32_t n, const int32_t* type, const int32_t* nbr_count,
                          int32_t n_types, int64_t* inter, pg_stream stream);
 
+/* ---- K12: raster region properties of an instance map: what skimage regionprops gives
+ * aggregated_hovernet_run.py:172-181 (bbox per instance) and hovernet_tile_inference.ipynb:2415-2429 (cell 18:
+ * area, perimeter, eccentricity, major / minor axis length, orientation).  inst_map int32 [height][width], labels
+ * 1..n_labels (0 = background; labels outside are ignored); every output is indexed by label - 1 and may be NULL.
+ * bbox = {min_row, min_col, max_row + 1, max_col + 1}; centroid = {row, col}; absent labels: area 0, NaN features. */
+typedef struct {
+  int32_t* area;        /* [n_labels] */
+  int32_t* bbox;        /* [n_labels][4] */
+  double* centroid;     /* [n_labels][2] */
+  double* perimeter;    /* [n_labels] */
+  double* eccentricity;
+  double* major_axis;
+  double* minor_axis;
+  double* orientation;
+} pg_raster_out;
+int pg_raster_props(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map,
+                    int32_t n_labels, const pg_raster_out* out, pg_stream stream);
+
 /* ---- K10: node features for the GNN input.  hovernet_tile_inference.ipynb:2903 (cell 21:
  * z = (v - mean) / std(ddof=0), NaN-skipping statistics, a column with sigma 0 / NaN becomes all 0.0) and
  * ipynb:2950 (cell 23: pd.get_dummies(type, prefix="type"), features = one-hot columns then the *_z columns).

@@ -35,6 +35,11 @@ class PgMorphOut(C.Structure):
                                         "minor_axis", "centroid_x", "centroid_y", "poly_bbox")]
 
 
+class PgRasterOut(C.Structure):
+    _fields_ = [(name, vp) for name in ("area", "bbox", "centroid", "perimeter", "eccentricity", "major_axis",
+                                        "minor_axis", "orientation")]
+
+
 class PathGraphError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libpathgraph error {code}: {msg}")
@@ -74,6 +79,7 @@ SIGNATURES = {
     "pg_halo_unpack": (C.c_int, [vp, vp, i32, i32, i32, f64, f64, vp, vp, vp, i32, i32, vp, vp]),
     "pg_clustering": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
     "pg_type_interactions": (C.c_int, [vp, i32, vp, vp, i32, vp, vp]),
+    "pg_raster_props": (C.c_int, [vp, i32, i32, vp, i32, C.POINTER(PgRasterOut), vp]),
     "pg_node_features": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "pg_exclusive_scan_i32": (C.c_int, [vp, vp, vp, i32, vp]),
 }

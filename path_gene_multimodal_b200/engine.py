@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PathGraphError, PgMorphOut
+from ._lib import PathGraphError, PgMorphOut, PgRasterOut
 
 _INF = float("inf")
 
@@ -348,6 +348,23 @@ class Engine:
             self._p(degree, torch.int32, "degree"), self._p(st, torch.int64, "stats"),
             self._p(hist, torch.int32, "hist"), int(hist_len) if hist is not None else 0, self._stream()))
         return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
+
+    # ---- K12 -----------------------------------------------------------------------------------
+    def raster_props(self, inst_map, n_labels):
+        """skimage-regionprops quantities of an int32 instance map [H,W] for labels 1..n_labels (pg_raster_props)."""
+        hgt, wid = int(inst_map.shape[0]), int(inst_map.shape[1])
+        n = int(n_labels)
+        res = {"area": self._empty((n,), torch.int32), "bbox": self._empty((n, 4), torch.int32),
+               "centroid": self._empty((n, 2), torch.float64)}
+        for name in ("perimeter", "eccentricity", "major_axis", "minor_axis", "orientation"):
+            res[name] = self._empty((n,), torch.float64)
+        ro = PgRasterOut()
+        ro.area, ro.bbox = self._p(res["area"], torch.int32, "area"), self._p(res["bbox"], torch.int32, "bbox")
+        for name in ("centroid", "perimeter", "eccentricity", "major_axis", "minor_axis", "orientation"):
+            setattr(ro, name, self._p(res[name], torch.float64, name))
+        self._check(self.lib.pg_raster_props(self._h, hgt, wid, self._p(inst_map, torch.int32, "inst_map"), n,
+                                             C.byref(ro), self._stream()))
+        return res
 
     # ---- K11 -----------------------------------------------------------------------------------
     def clustering(self, row_ptr, col):

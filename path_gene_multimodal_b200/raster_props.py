@@ -1,0 +1,70 @@
+"""Raster region properties of a HoverNeXt instance map (first half).
+
+Reference call sites: ``regionprops(inst_map)`` at aggregated_hovernet_run.py:172-181 (per-instance
+``bounding_box = [x_min, y_min, x_max, y_max]``) and ``regionprops_table(inst_map, properties=...)`` at
+hovernet_tile_inference.ipynb:2415-2429 (cell 18).  One CUDA pass pair over the map (pg_raster_props) replaces
+skimage's per-region Python loop; ``solidity`` (convex hull) and the contour polygons (find_contours +
+approximate_polygon, :183-198) are not built yet and are left out rather than approximated.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _host
+from .engine import get_engine
+from .polygon_morphology import derived_columns, zscore_columns
+
+
+def raster_regionprops(inst_map, device=None) -> pd.DataFrame:
+    """``regionprops_table`` columns for every label present (ascending, like skimage): ``label, area, perimeter,
+    eccentricity, major_axis_length, minor_axis_length, orientation, centroid-0, centroid-1, bbox-0 .. bbox-3``."""
+    m = np.asarray(inst_map)
+    if m.ndim == 3:  # aggregated_hovernet_run.py:165-166
+        m = m[0]
+    if m.ndim != 2:
+        raise ValueError("inst_map must be 2-D")
+    eng = get_engine(device)
+    n_labels = int(m.max()) if m.size else 0
+    cols = ["label", "area", "perimeter", "eccentricity", "major_axis_length", "minor_axis_length", "orientation",
+            "centroid-0", "centroid-1", "bbox-0", "bbox-1", "bbox-2", "bbox-3"]
+    if n_labels <= 0:
+        return pd.DataFrame({c: np.zeros(0, dtype=np.int64 if c in ("label", "area") or c.startswith("bbox") else np.float64)
+                             for c in cols})
+    with torch.cuda.device(eng.device):
+        d_m = _host.to_device(_host.as_int32(m, "inst_map"), np.int32, eng.device)
+        res = _host.to_host_many(eng.raster_props(d_m, n_labels))
+    keep = res["area"] > 0
+    lab = np.nonzero(keep)[0] + 1
+    df = pd.DataFrame({
+        "label": lab.astype(np.int64),
+        "area": res["area"][keep].astype(np.float64),   # skimage >= 0.20 reports area as float
+        "perimeter": res["perimeter"][keep],
+        "eccentricity": res["eccentricity"][keep],
+        "major_axis_length": res["major_axis"][keep],
+        "minor_axis_length": res["minor_axis"][keep],
+        "orientation": res["orientation"][keep],
+        "centroid-0": res["centroid"][keep, 0], "centroid-1": res["centroid"][keep, 1],
+    })
+    for c in range(4):
+        df[f"bbox-{c}"] = res["bbox"][keep, c].astype(np.int64)
+    return df
+
+
+def raster_morphology_table(inst_map, zscore: bool = False, device=None) -> pd.DataFrame:
+    """``morph_df`` of cell 18 (ipynb:2415-2456) from the raster, as the reference computes it: ``inst_id, area,
+    perimeter, eccentricity, major_axis_length, minor_axis_length, orientation`` + the derived ``perimeter_area,
+    compactness, roundness, elongation`` (+ ``*_z`` of cell 21).  ``solidity`` is absent (see module docstring)."""
+    df = raster_regionprops(inst_map, device=device)
+    out = df[["label", "area", "perimeter", "eccentricity", "major_axis_length", "minor_axis_length", "orientation"]].rename(
+        columns={"label": "inst_id"})
+    out = derived_columns(out)
+    return zscore_columns(out) if zscore else out
+
+
+def instance_bounding_boxes(inst_map, device=None) -> dict:
+    """``bbox_dict`` of aggregated_hovernet_run.py:172-181: inst_id -> [x_min, y_min, x_max, y_max] (max exclusive)."""
+    df = raster_regionprops(inst_map, device=device)
+    return {int(l): [int(c0), int(r0), int(c1), int(r1)]
+            for l, r0, c0, r1, c1 in zip(df["label"], df["bbox-0"], df["bbox-1"], df["bbox-2"], df["bbox-3"])}

@@ -268,3 +268,53 @@ def test_graph_statistics_against_networkx():
         assert len(nodes) == H.number_of_nodes() and len(sub) == H.number_of_edges()
     empty = clustering_coefficients(np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int64))
     assert (empty["clustering"] == 0).all() and (empty["triangles"] == 0).all()
+
+
+def _blob_map(h, w, n, seed):
+    rng = np.random.default_rng(seed)
+    m = np.zeros((h, w), dtype=np.int32)
+    rr, cc = np.mgrid[0:h, 0:w]
+    for lab in range(1, n + 1):
+        if lab % 17 == 0:
+            continue                                            # absent labels
+        cy, cx = rng.uniform(0, h), rng.uniform(0, w)           # some blobs are cut by the image border
+        a, b, th = rng.uniform(3, 14), rng.uniform(2, 8), rng.uniform(0, np.pi)
+        y, x = rr - cy, cc - cx
+        u, v = x * np.cos(th) + y * np.sin(th), -x * np.sin(th) + y * np.cos(th)
+        m[(u / a) ** 2 + (v / b) ** 2 <= 1] = lab               # later blobs overwrite earlier ones: ragged, touching regions
+    m[5, 5] = n + 1                                             # a single-pixel region
+    m[h - 1, 0:3] = n + 2                                       # a 1 x 3 line on the border
+    return m
+
+
+@pytest.mark.parametrize("shape", [(521, 521), (64, 37)])
+def test_raster_regionprops_against_restated_skimage(shape):
+    # regionprops(inst_map) of aggregated_hovernet_run.py:172 / cell 18, one CUDA pass pair
+    from oracle import raster as oraster
+    from path_gene_multimodal_b200 import instance_bounding_boxes, raster_morphology_table, raster_regionprops
+
+    m = _blob_map(*shape, n=120 if shape[0] > 100 else 9, seed=shape[1])
+    want = oraster.regionprops(m)
+    got = raster_regionprops(m)
+    assert got["label"].tolist() == want["label"].tolist()
+    assert np.array_equal(got["area"].to_numpy(), want["area"])
+    assert np.array_equal(got[[f"bbox-{c}" for c in range(4)]].to_numpy(), want["bbox"])
+    np.testing.assert_allclose(got[["centroid-0", "centroid-1"]].to_numpy(), want["centroid"], rtol=1e-13)
+    np.testing.assert_allclose(got["perimeter"].to_numpy(), want["perimeter"], rtol=1e-13)
+    for name in ("eccentricity", "major_axis_length", "minor_axis_length"):
+        np.testing.assert_allclose(got[name].to_numpy(), want[name], rtol=1e-9, atol=1e-7, err_msg=name)
+    # orientation is ill-defined for (near-)isotropic regions; compare where the tensor is anisotropic
+    aniso = want["eccentricity"] > 1e-3
+    np.testing.assert_allclose(got["orientation"].to_numpy()[aniso], want["orientation"][aniso], rtol=1e-7, atol=1e-9)
+    one = got[got["label"] == got["label"].max() - 1].iloc[0]   # the single pixel
+    assert one["area"] == 1 and one["perimeter"] == 0.0 and one["eccentricity"] == 0.0 and one["major_axis_length"] == 0.0
+    boxes = instance_bounding_boxes(m)
+    l0 = int(want["label"][0])
+    r0, c0, r1, c1 = want["bbox"][0]
+    assert boxes[l0] == [c0, r0, c1, r1]                        # [x_min, y_min, x_max, y_max], aggregated_hovernet_run.py:179-180
+    morph = raster_morphology_table(m, zscore=True)
+    assert {"inst_id", "perimeter_area", "compactness", "roundness", "elongation", "area_z"} <= set(morph.columns)
+    a, p_ = want["area"], want["perimeter"]
+    np.testing.assert_allclose(morph["compactness"].to_numpy(), 4 * np.pi * a / np.clip(p_, 1, None) ** 2, rtol=1e-12)
+    stacked = raster_regionprops(m[None])                        # (1, H, W) maps are squeezed like the reference does
+    assert stacked["label"].tolist() == got["label"].tolist()

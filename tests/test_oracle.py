@@ -193,3 +193,26 @@ def test_feature_oracle_is_the_notebook_rule():
     s = np.sqrt(2.0 / 3.0)
     np.testing.assert_allclose(x[:3, 3], np.array([-1 / s, 0.0, 1 / s], dtype=np.float32), rtol=1e-6)
     assert np.isnan(x[3, 3]) and (x[:, 4] == 0).all() and x[:, 5].tolist() == [-1.0, -1.0, 1.0, 1.0]
+
+
+def test_raster_oracle_on_analytic_shapes():
+    # the restated skimage regionprops (skimage absent: parity unpinned, see oracle/raster.py) on shapes with known answers
+    from oracle import raster as oraster
+
+    m = np.zeros((40, 60), dtype=np.int32)
+    m[3:8, 10:15] = 1                      # 5 x 5 square
+    m[20:24, 5:17] = 2                     # 4 x 12 rectangle (rows x cols)
+    rr, cc = np.mgrid[0:40, 0:60]
+    m[(rr - 20) ** 2 + (cc - 40) ** 2 <= 12 ** 2] = 4   # disc r = 12 (label 3 absent)
+    p = oraster.regionprops(m)
+    assert p["label"].tolist() == [1, 2, 4] and p["area"][:2].tolist() == [25.0, 48.0]
+    assert p["bbox"][0].tolist() == [3, 10, 8, 15] and p["bbox"][1].tolist() == [20, 5, 24, 17]
+    assert p["centroid"][0].tolist() == [5.0, 12.0] and p["centroid"][1].tolist() == [21.5, 10.5]
+    assert p["perimeter"][0] == 16.0 and p["perimeter"][1] == 28.0
+    assert abs(p["eccentricity"][0]) < 1e-7
+    assert np.isclose(p["major_axis_length"][1], 4 * np.sqrt((12 ** 2 - 1) / 12.0))     # variance of n pixels = (n^2-1)/12
+    assert np.isclose(p["minor_axis_length"][1], 4 * np.sqrt((4 ** 2 - 1) / 12.0))
+    assert np.isclose(p["eccentricity"][1], np.sqrt(1 - (4 ** 2 - 1) / (12 ** 2 - 1)))
+    assert abs(p["orientation"][1]) == np.pi / 2                                        # long axis along the columns
+    assert abs(p["perimeter"][2] / (2 * np.pi * 12) - 1) < 0.05 and p["eccentricity"][2] < 0.05
+    assert abs(p["area"][2] / (np.pi * 144) - 1) < 0.03
