@@ -191,13 +191,15 @@ sym_push_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
 // entries (read from its k-list, weight = min over both directions, ipynb:1888-1892) followed by the arrivals
 // staged at the back; every lane takes one entry of the range, counts the entries of the row that sort before
 // it and writes it to its place.
-template <class DT>
+template <class DT, int K>  // K = compile-time k with 16-byte aligned rows (vector loads), or 0 = any k
 __global__ void __launch_bounds__(TPB)
-sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k,
+sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k_rt,
                 const int32_t* __restrict__ id_map, const uint8_t* __restrict__ recip,
                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ tmp_col,
                 const DT* __restrict__ tmp_w, int32_t* __restrict__ col, double* __restrict__ w64,
                 float* __restrict__ w32) {
+  constexpr int KK = K ? K : 4;
+  const int k = K ? K : k_rt;
   const int lane = threadIdx.x & 31;
   const int r0 = ((blockIdx.x * TPB + threadIdx.x) >> 5) << 5;
   if (r0 >= n) return;  // warp-uniform
@@ -207,8 +209,18 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
   const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
   const int my_cnt = (lane == 31 ? end : rp_next) - rp;
   int my_own = 0;  // valid entries of the lane's row
-  if (r0 + lane < n)
-    for (int s = 0; s < k; ++s) my_own += recip[(int64_t)(r0 + lane) * k + s] != RECIP_INVALID;
+  if (r0 + lane < n) {
+    if (K != 0) {
+#pragma unroll
+      for (int q = 0; q < KK / 4; ++q) {
+        const uint32_t wrd = reinterpret_cast<const uint32_t*>(recip + (int64_t)(r0 + lane) * KK)[q];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) my_own += ((wrd >> (8 * e)) & 0xffu) != RECIP_INVALID;
+      }
+    } else {
+      for (int s = 0; s < k; ++s) my_own += recip[(int64_t)(r0 + lane) * k + s] != RECIP_INVALID;
+    }
+  }
   for (int p0 = begin; p0 < end; p0 += 32) {
     const int p = p0 + lane;
     int kk = 0;  // the last row of the 32 that starts at or before p (empty rows share their start with the next row)
@@ -226,31 +238,53 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
     int c;
     DT w;
     int my_slot = -1;
-    if (me < own) {
-      int s = me;
-      if (own != k) {  // skip the invalid slots
-        int seen = 0;
-        for (s = 0; s < k; ++s)
-          if (recip[rowk + s] != RECIP_INVALID && seen++ == me) break;
+    int rank = 0;  // place = number of entries that sort before (id, position): any input yields a permutation
+    if (K != 0 && own == k) {
+      // the common case - every slot of the row is valid: the row's ids in registers (two / four 16-byte loads)
+      int ids[KK];
+      load_row<int, KK>(knn_idx + rowk, ids);
+      if (me < own) {
+        my_slot = me;
+        c = 0;
+#pragma unroll
+        for (int s = 0; s < KK; ++s) c = s == me ? ids[s] : c;
+        w = dist[rowk + me];
+        const int rc = recip[rowk + me];
+        if (rc != RECIP_NONE) {
+          const int j = id_map ? id_map[c] : c;
+          w = min(w, dist[(int64_t)j * k + rc]);  // weight = min over directions (ipynb:1888-1892)
+        }
+      } else {
+        c = tmp_col[p];
+        w = tmp_w[p];
       }
-      my_slot = s;
-      c = knn_idx[rowk + s];
-      w = dist[rowk + s];
-      const int rc = recip[rowk + s];
-      if (rc != RECIP_NONE) {
-        const int j = id_map ? id_map[c] : c;
-        w = min(w, dist[(int64_t)j * k + rc]);
-      }
+#pragma unroll
+      for (int s = 0; s < KK; ++s) rank += (ids[s] < c || (ids[s] == c && (my_slot < 0 || s < my_slot))) ? 1 : 0;
     } else {
-      c = tmp_col[p];
-      w = tmp_w[p];
-    }
-    // place = number of entries that sort before (id, position): any input yields a permutation
-    int rank = 0;
-    for (int s = 0; s < k; ++s) {
-      const int cu = knn_idx[rowk + s];
-      const bool valid = own == k || recip[rowk + s] != RECIP_INVALID;
-      rank += (valid && (cu < c || (cu == c && (my_slot < 0 || s < my_slot)))) ? 1 : 0;
+      if (me < own) {
+        int s = me;
+        if (own != k) {  // skip the invalid slots
+          int seen = 0;
+          for (s = 0; s < k; ++s)
+            if (recip[rowk + s] != RECIP_INVALID && seen++ == me) break;
+        }
+        my_slot = s;
+        c = knn_idx[rowk + s];
+        w = dist[rowk + s];
+        const int rc = recip[rowk + s];
+        if (rc != RECIP_NONE) {
+          const int j = id_map ? id_map[c] : c;
+          w = min(w, dist[(int64_t)j * k + rc]);
+        }
+      } else {
+        c = tmp_col[p];
+        w = tmp_w[p];
+      }
+      for (int s = 0; s < k; ++s) {
+        const int cu = knn_idx[rowk + s];
+        const bool valid = own == k || recip[rowk + s] != RECIP_INVALID;
+        rank += (valid && (cu < c || (cu == c && (my_slot < 0 || s < my_slot)))) ? 1 : 0;
+      }
     }
     for (int u = own; u < rcnt; ++u) {
       const int cu = tmp_col[rbase + u];
@@ -608,10 +642,12 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
   const bool vec = (((uintptr_t)knn_idx | (uintptr_t)dist64 | (uintptr_t)dist32) & 15) == 0;
   if (dist64) {
     if (vec && k == 8) PG_PUSH(double, dist64, 8); else if (vec && k == 16) PG_PUSH(double, dist64, 16); else PG_PUSH(double, dist64, 0);
-    PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<double><<<blocks, TPB, 0, s>>>(knn_idx, dist64, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const double*)tw.p, und_col, und_w64, und_w32));
+#define PG_RANK(DT, D, K) PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const DT*)tw.p, und_col, und_w64, und_w32))
+    if (vec && k == 8) PG_RANK(double, dist64, 8); else if (vec && k == 16) PG_RANK(double, dist64, 16); else PG_RANK(double, dist64, 0);
   } else {
     if (vec && k == 8) PG_PUSH(float, dist32, 8); else if (vec && k == 16) PG_PUSH(float, dist32, 16); else PG_PUSH(float, dist32, 0);
-    PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<float><<<blocks, TPB, 0, s>>>(knn_idx, dist32, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const float*)tw.p, und_col, und_w64, und_w32));
+    if (vec && k == 8) PG_RANK(float, dist32, 8); else if (vec && k == 16) PG_RANK(float, dist32, 16); else PG_RANK(float, dist32, 0);
+#undef PG_RANK
   }
 #undef PG_PUSH
   PG_LAUNCH_CHECK(h);
