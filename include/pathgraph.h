@@ -86,6 +86,10 @@ int64_t pg_workspace_bytes(pg_handle* h);
  *   bbox      int32 [N,4]   tile-local bbox     (NULL = skip)   -> wsi_bbox int32 [N,4]
  *   wsi_poly_xy T   [M,2]   shifted vertices (NULL = skip)
  * Rows with < 3 vertices give NaN features. */
+/* Optional: tell the library how long the rings of the coming pg_map_morph_* calls are (n rings, total_vertices
+ * vertices), so that a warp's 32 rings fit its shared-memory staging slab; without it slabs are sized for rings of
+ * up to 33 vertices and longer tables take the slower 8-lanes-per-ring path. Results do not depend on it. */
+int pg_map_morph_hint(pg_handle* h, int32_t n, int64_t total_vertices);
 int pg_map_morph_f32(pg_handle* h, int32_t n, const int32_t* poly_off, const float* poly_xy,
                      const int32_t* nuc_tile, const int32_t* tile_x, const int32_t* tile_y,
                      const double* centroid, const int32_t* bbox, float* wsi_poly_xy,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "pg_destroy": (C.c_int, [vp]),
     "pg_last_error": (C.c_char_p, [vp]),
     "pg_workspace_bytes": (C.c_int64, [vp]),
+    "pg_map_morph_hint": (C.c_int, [vp, i32, i64]),
     "pg_map_morph_f32": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PgMorphOut), vp]),
     "pg_map_morph_f64": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PgMorphOut), vp]),
     "pg_grid_build": (C.c_int, [vp, i32, i32, vp, vp, vp, f64, C.POINTER(f64), vp]),

@@ -68,6 +68,7 @@ struct pg_handle {
   int32_t radius_flags = 0;
   cudaStream_t last_stream = nullptr;
   int32_t sm_count = 148;
+  double morph_mean_verts = 0;  // pg_map_morph_hint: expected vertices per ring (sizes K1's shared-memory slabs)
   // launch accounting / optional per-kernel CUDA-event timing (pg_profile_*)
   int64_t launches = 0;
   bool profiling = false;

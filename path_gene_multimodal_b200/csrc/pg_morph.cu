@@ -16,13 +16,16 @@
 //     the polygon's lane.
 // Both leave the Green's-theorem sums of a polygon (frame at one of its own vertices, float64) in its lane; the
 // closed-form epilogue and all per-polygon loads / stores run one polygon per lane, fully coalesced.
+#include <algorithm>
+#include <cmath>
 #include "pg_common.cuh"
 
 namespace {
 
 constexpr int TPB = 128;
 constexpr int WARPS = TPB / 32;
-constexpr int SLAB_VERTS = 32 * 33 + 2;  // 32 rings of 32 vertices, explicitly closed (+1), + alignment slack
+constexpr int SLAB_VERTS_MIN = 32 * 33 + 2;  // 32 rings of 32 vertices, explicitly closed (+1), + alignment slack
+constexpr size_t SLAB_BYTES_MAX = 200 * 1024;  // per CTA
 
 template <typename T> struct vec2_of;
 template <> struct vec2_of<float> { using type = float2; };
@@ -107,7 +110,8 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
                  const int32_t* __restrict__ nuc_tile, const int32_t* __restrict__ tile_x,
                  const int32_t* __restrict__ tile_y, const double2* __restrict__ centroid,
                  const int4* __restrict__ bbox, typename vec2_of<T>::type* __restrict__ wsi_poly,
-                 double2* __restrict__ wsi_centroid, int4* __restrict__ wsi_bbox, pg_morph_out out) {
+                 double2* __restrict__ wsi_centroid, int4* __restrict__ wsi_bbox, pg_morph_out out,
+                 int slab_verts) {
   using V2 = typename vec2_of<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t s_bar[WARPS];
@@ -127,12 +131,12 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
   // slab: vertex i of the range lives at slab[i]; the bulk transfers need 16-byte alignment on both sides, so
   // the slab is placed with the same alignment phase as the global range (`head` vertices precede the first
   // 16-byte boundary: 0 or 1 for float2, always 0 for double2) and the odd head / tail vertices move by hand
-  V2* slab_base = reinterpret_cast<V2*>(smem_raw) + (size_t)wid * SLAB_VERTS;
+  V2* slab_base = reinterpret_cast<V2*>(smem_raw) + (size_t)wid * slab_verts;
   const V2* gsrc = poly + wbeg;
   V2* gdst = wsi_poly ? wsi_poly + wbeg : nullptr;
   const int head = (int)(((16u - (uint32_t)((uintptr_t)gsrc & 15u)) & 15u) / sizeof(V2));
   const bool same_phase = !gdst || (((uintptr_t)gsrc ^ (uintptr_t)gdst) & 15u) == 0;
-  const bool staged = total > 0 && total <= SLAB_VERTS - 2 && same_phase;  // warp-uniform
+  const bool staged = total > 0 && total <= slab_verts - 2 && same_phase;  // warp-uniform
   V2* slab = slab_base + (head ? (int)(16 / sizeof(V2)) - head : 0);       // &slab[head] is 16-byte aligned
   int nbulk = 0;
   if (staged) {
@@ -325,17 +329,23 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   if (out) o = *out;
   const bool extra = o.major_axis || o.minor_axis || o.centroid_x || o.centroid_y || o.poly_bbox;
   const int blocks = pg_div_up(n, TPB);  // 32 polygons per warp
-  const size_t smem = (size_t)WARPS * SLAB_VERTS * sizeof(V2);
+  // slab per warp: the default holds 32 rings of up to 33 vertices (6 CTAs per SM for float32); tables with longer
+  // rings (mean from pg_map_morph_hint - the Python layer knows M) get 32 rings of the mean length + 40 % spread
+  int slab_verts = SLAB_VERTS_MIN;
+  if (h->morph_mean_verts > 33.0) slab_verts = (int)std::ceil(46.0 * h->morph_mean_verts) + 2;
+  slab_verts = std::min(slab_verts, (int)(SLAB_BYTES_MAX / (WARPS * sizeof(V2))));
+  slab_verts &= ~1;  // whole 16-byte units per warp
+  const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
   auto kern = extra ? map_morph_kernel<T, true> : map_morph_kernel<T, false>;
-  static bool attr_set[2] = {false, false};  // per instantiation of this template (T), per EXTRA
-  if (!attr_set[extra]) {
+  static size_t attr_set[2] = {0, 0};  // per instantiation of this template (T), per EXTRA: largest size opted in
+  if (smem > attr_set[extra]) {
     PG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[extra] = true;
+    attr_set[extra] = smem;
   }
   PG_LAUNCH(h, s, extra ? "map_morph_kernel<T, true>" : "map_morph_kernel<T, false>",
             kern<<<blocks, TPB, smem, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,
                                            (const double2*)centroid, (const int4*)bbox, (V2*)wsi_poly_xy,
-                                           (double2*)wsi_centroid, (int4*)wsi_bbox, o));
+                                           (double2*)wsi_centroid, (int4*)wsi_bbox, o, slab_verts));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -343,6 +353,13 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
 }  // namespace
 
 extern "C" {
+
+int pg_map_morph_hint(pg_handle* h, int32_t n, int64_t total_vertices) {
+  if (!h) return PG_ERR_INVALID;
+  PG_REQUIRE(h, n >= 0 && total_vertices >= 0, "pg_map_morph_hint: negative size");
+  h->morph_mean_verts = n > 0 ? (double)total_vertices / (double)n : 0.0;
+  return PG_OK;
+}
 
 int pg_map_morph_f32(pg_handle* h, int32_t n, const int32_t* poly_off, const float* poly_xy, const int32_t* nuc_tile,
                      const int32_t* tile_x, const int32_t* tile_y, const double* centroid, const int32_t* bbox,

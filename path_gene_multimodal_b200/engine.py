@@ -167,6 +167,7 @@ class Engine:
             for name in ("centroid_x", "centroid_y"):
                 setattr(mo, name, self._p(get(name, (n,), torch.float64), torch.float64, name))
             mo.poly_bbox = self._p(get("poly_bbox", (n, 4), torch.float64), torch.float64, "poly_bbox")
+        self._check(self.lib.pg_map_morph_hint(self._h, n, m))
         fn = self.lib.pg_map_morph_f32 if vt == torch.float32 else self.lib.pg_map_morph_f64
         self._check(fn(self._h, n, self._p(poly_off, torch.int32, "poly_off"), self._p(poly_xy, vt, "poly_xy"),
                        self._p(nuc_tile, torch.int32, "nuc_tile"), self._p(tile_x, torch.int32, "tile_x"),

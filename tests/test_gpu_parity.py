@@ -160,6 +160,37 @@ def test_map_morph_staging_boundaries(engine, vt):
         assert np.array_equal(bb[ok, 3], feat["bbox_ymax"][ok] + tile_y[nuc_tile][ok])
 
 
+def test_map_morph_long_rings_use_bigger_slabs(engine):
+    # rings of 40..90 vertices: the engine passes the mean ring length (pg_map_morph_hint) and the slabs grow, so the
+    # staged path still applies; the same call after a hint for short rings takes the group path - same results
+    n = 3000
+    rng = np.random.default_rng(5)
+    nv = rng.integers(40, 91, size=n)
+    off = np.zeros(n + 1, dtype=np.int32)
+    off[1:] = np.cumsum(nv)
+    owner = np.repeat(np.arange(n), nv)
+    t = 2 * np.pi * (np.arange(off[-1]) - off[owner]) / nv[owner]
+    a, b = rng.uniform(10, 30, n), rng.uniform(5, 10, n)
+    xy = np.stack([300 + a[owner] * np.cos(t), 200 + b[owner] * np.sin(t)], axis=1)
+    xy = (np.round(xy * 2) / 2).astype(np.float32)
+    big = engine.map_morph(dev(off), dev(xy), write_polygons=True, extra=True)
+    _check_morph(big, off, xy)
+    engine._check(engine.lib.pg_map_morph_hint(engine._h, n, 20 * n))      # pretend the rings are short
+    fn = engine.lib.pg_map_morph_f32
+    small = {k: torch.empty_like(v) for k, v in big.items()}
+    from path_gene_multimodal_b200._lib import PgMorphOut
+    import ctypes as C
+    mo = PgMorphOut()
+    for name in ("area", "perimeter", "eccentricity", "circularity", "major_axis", "minor_axis", "centroid_x", "centroid_y", "poly_bbox"):
+        setattr(mo, name, small[name].data_ptr())
+    engine._check(fn(engine._h, n, dev(off).data_ptr(), dev(xy).data_ptr(), None, None, None, None, None,
+                     small["wsi_poly_xy"].data_ptr(), None, None, C.byref(mo), engine._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(small["wsi_poly_xy"], big["wsi_poly_xy"])
+    for name in ("area", "perimeter", "circularity", "eccentricity"):
+        np.testing.assert_allclose(small[name].cpu().numpy(), big[name].cpu().numpy(), rtol=RTOL, atol=ECC_ATOL, err_msg=name)
+
+
 def test_map_morph_full_size_properties(engine):
     # C3 shape (reduced count so the oracle finishes in seconds is covered above); here: 2M x 32, invariants only
     n = 2_000_000
