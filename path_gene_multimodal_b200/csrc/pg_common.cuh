@@ -35,7 +35,7 @@ struct pg_handle {
   pg_buf cell_of;      // scratch (K7 staging columns)
   pg_buf rank;         // scratch (K7 staging weights)
   pg_buf s_rec;        // pg_rec [N]    points in cell order, one 32-byte sector each (see pg_query.cuh)
-  pg_buf s_pos;        // int32 [N]     cell-order position of point i (inverse of the counting sort)
+  pg_buf s_pos;        // unused (the walk writes its per-point records in row order)
   pg_buf s_gid;        // int32 [N]     copy of the caller's gids (only when given), for the fill pass
   // radius graph (pg_radius.cu): the walk leaves one 32-byte pg_pt_meta per point IN CELL ORDER (coalesced) and
   // parks the accepted entries of each row in tmp_ent; the row pass un-permutes the meta records into row order

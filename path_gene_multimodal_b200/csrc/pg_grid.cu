@@ -107,7 +107,7 @@ histogram_kernel(const double2* xy, int n, bool aligned32, double x0, double y0,
 __global__ void __launch_bounds__(TPB)
 scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
                int n, bool aligned32, double x0, double y0, double inv_cell, int nx, int ny, int32_t* cursor,
-               pg_rec* rec, int32_t* pos, int32_t* gid_copy) {
+               pg_rec* rec, int32_t* gid_copy) {
   const int base = blockIdx.x * TPB * PTS + threadIdx.x * 2;
   pg_pdl_launch();
   pg_pdl_wait();
@@ -140,7 +140,6 @@ scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
     if (i < n) {
       const int tshift = (t[k] >= 1 && t[k] <= PG_PACKED_TYPES) ? (t[k] - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
       pg_st_rec(rec + dst[k], p[k].x, p[k].y, i, id[k], t[k], tshift);
-      pos[i] = dst[k];
       if (gid) gid_copy[i] = id[k];
     }
   }
@@ -214,7 +213,6 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
     PG_CUDA(h, cudaMemsetAsync(h->cell_start.p, 0, 16, s));  // B[0] = 0 (and the alignment pad) once per allocation
   }
   if ((rc = pg_reserve(h, h->s_rec, (size_t)(n + 2) * sizeof(pg_rec)))) return rc;
-  if ((rc = pg_reserve(h, h->s_pos, (size_t)(n + 8) * sizeof(int32_t)))) return rc;
   if (gid && (rc = pg_reserve(h, h->s_gid, (size_t)(n + 4) * sizeof(int32_t)))) return rc;
   h->last_count.valid = false;
   const bool aligned32 = ((uintptr_t)xy & 31) == 0;
@@ -238,7 +236,7 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
   if (n > 0) {
     PG_LAUNCH(h, s, "scatter_kernel", pg_launch_pdl(2, scatter_kernel, pg_div_up(n, TPB * PTS), TPB, s,
         (const double2*)xy, type, gid, n, aligned32, g.x0, g.y0, g.inv_cell, g.nx, g.ny, B + 1, (pg_rec*)h->s_rec.p,
-        (int32_t*)h->s_pos.p, gid ? (int32_t*)h->s_gid.p : nullptr));
+        gid ? (int32_t*)h->s_gid.p : nullptr));
     PG_LAUNCH_CHECK(h);
   }
   g.built = true;

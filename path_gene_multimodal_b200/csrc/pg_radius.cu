@@ -12,12 +12,12 @@
 //          in flight; the points on a strip edge add a short second loop over the three cells across the edge.
 //          Loads past the end of a run are pointed at a sentinel record at infinity, and a point meets itself
 //          like any other candidate (undone once after the loop), so the loop body has no special cases.
-//          Per point it leaves ONE 32-byte pg_pt_meta {degree, entries, offset, 5 type counts} at its cell-order
-//          position (a full-sector coalesced store) and parks the row's accepted (id, d2) entries - staged in a
+//          Per point it leaves ONE 32-byte pg_pt_meta {degree, entries, offset, 5 type counts} at its ROW's
+//          position (one scattered full-sector store: fire and forget) and parks the row's accepted (id, d2) entries - staged in a
 //          small shared-memory slab - in the CTA's own region of a temporary array (space claimed with a
 //          shared-memory atomic per warp; a shared overflow region takes what does not fit).
-//   rows   (pg_radius_count, kernel 2) one thread per ROW: follows pos[row] to the point's meta record (the one
-//          scattered access, a single 256-bit load) and writes row_ptr (decoupled look-back scan of the entry
+//   rows   (pg_radius_count, kernel 2) one thread per 4 ROWS: reads their meta records (contiguous 256-bit loads)
+//          and writes row_ptr (decoupled look-back scan of the entry
 //          counts), degree, nbr_count and row_off coalesced; the degree statistics / histogram are reduced
 //          here too (CTA -> accumulators; the last CTA publishes them and re-arms the accumulators).
 //   gather (pg_radius_fill) warp-flattened over 32 rows: lane p of the warp's contiguous output range finds its
@@ -252,7 +252,7 @@ radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
         [&]() {});
     }
   }
-  st_meta(o.meta + q, m);
+  st_meta(o.meta + me.row, m);  // in ROW order: a scattered full-sector store here buys the row pass coalesced loads
 }
 
 struct rows_out {
@@ -276,7 +276,7 @@ struct rows_out {
 // The statistics are reduced between publishing the tile's aggregate and reading the predecessors', i.e. inside
 // the look-back wait.
 __global__ void __launch_bounds__(TPB_ROWS)
-radius_rows_kernel(int n_query, const int32_t* pos, const pg_pt_meta* meta, pg_scan_state st, rows_out o) {
+radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_out o) {
   using TS = pg_tile_scan<TPB_ROWS>;
   __shared__ typename TS::smem_t sm;
   __shared__ int s_hist[PG_ACC_HIST_MAX];
@@ -291,20 +291,12 @@ radius_rows_kernel(int n_query, const int32_t* pos, const pg_pt_meta* meta, pg_s
   pg_pdl_wait();
 
   pg_pt_meta m[ROWS_ITEMS];
-  int p[ROWS_ITEMS];
-  if (full) {
-    const int4 pp = *reinterpret_cast<const int4*>(pos + row0);
-    p[0] = pp.x; p[1] = pp.y; p[2] = pp.z; p[3] = pp.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < ROWS_ITEMS; ++i) p[i] = row0 + i < n_query ? pos[row0 + i] : -1;
-  }
   if (o.hist_mode == 1)
     for (int i = tid; i < o.hist_len; i += TPB_ROWS) s_hist[i] = 0;
   if (tid == 0) { s_mn = 0x7fffffff; s_mx = -1; s_sum = 0; s_sq = 0; }
 #pragma unroll
   for (int i = 0; i < ROWS_ITEMS; ++i) {
-    if (p[i] >= 0) m[i] = ld_meta(meta + p[i]);
+    if (row0 + i < n_query) m[i] = ld_meta(meta + row0 + i);
     else { m[i].deg = 0; m[i].cnt = 0; m[i].off = -1; }
   }
   int v[ROWS_ITEMS], tsum = 0;
@@ -592,7 +584,7 @@ int launch_count_pass(pg_handle* h, cudaStream_t s) {
   pg_scan_state st;
   int rc = pg_scan_prepare(h, tiles, TPB_ROWS, s, &st);
   if (rc) return rc;
-  PG_LAUNCH(h, s, "radius_rows_kernel", pg_launch_pdl(4, radius_rows_kernel, tiles, TPB_ROWS, s, nq, (const int32_t*)h->s_pos.p, (const pg_pt_meta*)h->pt_meta.p, st, o));
+  PG_LAUNCH(h, s, "radius_rows_kernel", pg_launch_pdl(4, radius_rows_kernel, tiles, TPB_ROWS, s, nq, (const pg_pt_meta*)h->pt_meta.p, st, o));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
