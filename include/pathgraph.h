@@ -169,6 +169,33 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
                            const int32_t* id_map, const int32_t* und_row_ptr, int32_t* und_col,
                            double* und_w64, float* und_w32, pg_stream stream);
 
+/* The same union with the downstream passes fused into it (what build_knn_graph needs in one go): give
+ * pg_knn_union_count an up_row_ptr int32 [n+1] and it also scans, per row, the entries above the row's id; then
+ * pg_knn_union_fill writes - besides the symmetric CSR - the i<j edge list of ipynb:1894 / :2969-2975 (edges int64
+ * [E_und][2] sorted by (i, j), weights), the neighbour-type composition (type int32 indexed by COLUMN id, nbr_count
+ * int32 [n][n_types]), the degree and its statistics, from the same rank pass.  Every pointer of pg_union_out may be
+ * NULL.  pg_knn_union_total returns both totals (one host synchronisation). */
+typedef struct {
+  int64_t* edges;
+  double* edge_w64;
+  float* edge_w32;
+  const int32_t* type;
+  int32_t n_types;
+  int32_t* nbr_count;
+  int32_t* degree;
+  pg_degree_stats* stats;
+  int32_t* hist;
+  int32_t hist_len;
+} pg_union_out;
+int pg_knn_union_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
+                       const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, int32_t* up_row_ptr,
+                       pg_stream stream);
+int pg_knn_union_total(pg_handle* h, int64_t* total, int64_t* upper_total);
+int pg_knn_union_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const double* dist64,
+                      const float* dist32, const int32_t* row_id, const int32_t* id_map,
+                      const int32_t* und_row_ptr, const int32_t* up_row_ptr, int32_t* und_col,
+                      double* und_w64, float* und_w32, const pg_union_out* extra, pg_stream stream);
+
 /* ---- symmetric CSR (rows ascending by column) -> `edges` (i<j) list; ipynb:2969-2975 / G.edges of
  * ipynb:1894.  row_id int32 [n] = id of each row in column space (NULL = identity; set for strips). */
 int pg_csr_upper_count(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,

@@ -35,6 +35,11 @@ class PgMorphOut(C.Structure):
                                         "minor_axis", "centroid_x", "centroid_y", "poly_bbox")]
 
 
+class PgUnionOut(C.Structure):
+    _fields_ = [("edges", vp), ("edge_w64", vp), ("edge_w32", vp), ("type", vp), ("n_types", C.c_int32),
+                ("nbr_count", vp), ("degree", vp), ("stats", vp), ("hist", vp), ("hist_len", C.c_int32)]
+
+
 class PgRasterOut(C.Structure):
     _fields_ = [(name, vp) for name in ("area", "bbox", "centroid", "perimeter", "eccentricity", "major_axis",
                                         "minor_axis", "orientation")]
@@ -72,6 +77,9 @@ SIGNATURES = {
     "pg_knn_symmetrize_count": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp, vp]),
     "pg_knn_symmetrize_total": (C.c_int, [vp, C.POINTER(i64)]),
     "pg_knn_symmetrize_fill": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pg_knn_union_count": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
+    "pg_knn_union_total": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "pg_knn_union_fill": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PgUnionOut), vp]),
     "pg_csr_upper_count": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
     "pg_csr_upper_total": (C.c_int, [vp, C.POINTER(i64)]),
     "pg_csr_upper_fill": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

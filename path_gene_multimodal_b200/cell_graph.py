@@ -75,18 +75,19 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
                "knn_neighbor_distances": _host.to_host(kn["dist"])}
         eng.grid_check()
         if undirected:
-            sym = eng.symmetrize(kn["knn_idx"], kn["dist"])
-            up = eng.csr_upper(sym["row_ptr"], sym["col"], sym["w64"])
-            comp = eng.compose_degree(sym["row_ptr"], sym["col"], d_t, n_types, compose=d_t is not None)
+            # union + i<j edges + composition + degree statistics: one fused pass chain (pg_knn_union_*)
+            u = eng.knn_union(kn["knn_idx"], kn["dist"], types=d_t, n_types=n_types)
+            host = _host.to_host_many({"edges": u["edges"], "weight": u["edge_w"], "row_ptr": u["row_ptr"], "col": u["col"],
+                                       "csr_weight": u["w"], "degree": u["degree"], "stats": u["stats"], "hist": u["hist"],
+                                       "nbr_count": u["nbr_count"]})
             out.update({
-                "edges": _host.to_host(up["edges"]), "weight": _host.to_host(up["w64"]),
-                "row_ptr": _host.to_host(sym["row_ptr"]).astype(np.int64),
-                "col": _host.to_host(sym["col"]).astype(np.int64), "csr_weight": _host.to_host(sym["w64"]),
-                "degree": _host.to_host(comp["degree"]),
-                "degree_stats": eng.decode_stats(comp["stats"], comp["hist"]),
+                "edges": host["edges"], "weight": host["weight"],
+                "row_ptr": host["row_ptr"].astype(np.int64), "col": host["col"].astype(np.int64),
+                "csr_weight": host["csr_weight"], "degree": host["degree"],
+                "degree_stats": eng.decode_stats(host["stats"], host["hist"]),
             })
             if d_t is not None:
-                out["nbr_count"] = _host.to_host(comp["nbr_count"])
+                out["nbr_count"] = host["nbr_count"]
     return out
 
 

@@ -58,7 +58,7 @@ struct pg_handle {
   pg_buf scan_state;   // scan descriptors + ticket
   pg_buf misc;         // bounds / flags / cursors
   pg_buf sym_extra;    // int32 [N] K7: undirected row counts, then (cleared by the scan) the push cursor
-  pg_buf sym_cursor;   // unused
+  pg_buf sym_cursor;   // int32 [N] K7: per-row counts of entries above the row id (the i<j edge list), when asked for
   pg_buf sym_recip;    // uint8 [N*k]
   int32_t* pinned = nullptr;  // host-pinned: [0]=radius total [1]=sym total [2]=upper total [3]=overflow [4..]=scratch
   uint32_t scan_epoch = 0;

@@ -60,14 +60,15 @@ template <int K>
 __global__ void __launch_bounds__(TPB)
 sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k_rt, const int32_t* __restrict__ row_id,
                 const int32_t* __restrict__ id_map, int n_ids, uint8_t* __restrict__ recip,
-                int32_t* __restrict__ row_count) {
+                int32_t* __restrict__ row_count, int32_t* __restrict__ up_count) {
+  // up_count (optional): entries of the final row with column > the row's id, i.e. its share of the i<j edge list
   const int i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const int k = K ? K : k_rt;
   const int my_id = row_id ? row_id[i] : i;
   const int32_t* mine = knn_idx + (int64_t)i * k;
   uint8_t* rc_out = recip + (int64_t)i * k;
-  int own = 0;
+  int own = 0, own_up = 0;
   if (K != 0) {
     int ids[K ? K : 1];
     load_row_i32<K>(mine, k, ids);
@@ -81,9 +82,13 @@ sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k_rt, const int3
         r = RECIP_NONE;
         if (j >= 0 && j < n) {  // else: the neighbour has no row here, own entry only
           r = find_slot<K>(knn_idx + (int64_t)j * k, k, my_id);
-          if (r == RECIP_NONE) atomicAdd(&row_count[j], 1);
+          if (r == RECIP_NONE) {
+            atomicAdd(&row_count[j], 1);
+            if (up_count && my_id > jid) atomicAdd(&up_count[j], 1);
+          }
         }
         ++own;
+        own_up += jid > my_id;
       }
       rc[s] = r;
     }
@@ -105,14 +110,19 @@ sym_mark_kernel(const int32_t* __restrict__ knn_idx, int n, int k_rt, const int3
         r = RECIP_NONE;
         if (j >= 0 && j < n) {
           r = find_slot<0>(knn_idx + (int64_t)j * k, k, my_id);
-          if (r == RECIP_NONE) atomicAdd(&row_count[j], 1);
+          if (r == RECIP_NONE) {
+            atomicAdd(&row_count[j], 1);
+            if (up_count && my_id > jid) atomicAdd(&up_count[j], 1);
+          }
         }
         ++own;
+        own_up += jid > my_id;
       }
       rc_out[s] = (uint8_t)r;
     }
   }
   if (own) atomicAdd(&row_count[i], own);
+  if (up_count && own_up) atomicAdd(&up_count[i], own_up);
 }
 
 // a row of K items of T as 16-byte vector loads when the row is a whole number of them (the caller checks the
@@ -191,23 +201,55 @@ sym_push_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
 // entries (read from its k-list, weight = min over both directions, ipynb:1888-1892) followed by the arrivals
 // staged at the back; every lane takes one entry of the range, counts the entries of the row that sort before
 // it and writes it to its place.
+// optional fused outputs of the rank pass (all NULL: plain symmetrisation)
+struct rank_extra {
+  const int32_t* row_id;   // id of each row (NULL = identity), for the edge list
+  const int32_t* up_ptr;   // [n+1] exclusive scan of the rows' upper-entry counts (NULL: no edge list)
+  long long* edges; double* ew64; float* ew32;
+  const int32_t* type;     // type by column id
+  int n_types;
+  int32_t* nbr_count;      // [n][n_types]
+  int32_t* degree;
+  pg_degree_stats* stats; int32_t* hist; int hist_len;
+  pg_stats_acc* acc; int32_t* acc_hist;
+};
+
 template <class DT, int K>  // K = compile-time k with 16-byte aligned rows (vector loads), or 0 = any k
 __global__ void __launch_bounds__(TPB)
 sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist, int n, int k_rt,
                 const int32_t* __restrict__ id_map, const uint8_t* __restrict__ recip,
                 const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ tmp_col,
                 const DT* __restrict__ tmp_w, int32_t* __restrict__ col, double* __restrict__ w64,
-                float* __restrict__ w32) {
+                float* __restrict__ w32, rank_extra x) {
+  __shared__ int s_cnt[TPB / 32][32 * PG_MAX_TYPES];
+  __shared__ int s_hist[PG_ACC_HIST_MAX];
+  __shared__ int s_mn, s_mx, s_last;
+  __shared__ unsigned long long s_sum, s_sq;
+  const bool want_stats = x.stats != nullptr || x.hist != nullptr;
+  if (want_stats) {  // CTA-wide state: before any warp may leave
+    if (x.hist && x.hist_len <= PG_ACC_HIST_MAX)
+      for (int i = threadIdx.x; i < x.hist_len; i += TPB) s_hist[i] = 0;
+    if (threadIdx.x == 0) { s_mn = 0x7fffffff; s_mx = -1; s_sum = 0; s_sq = 0; }
+    __syncthreads();
+  }
   constexpr int KK = K ? K : 4;
   const int k = K ? K : k_rt;
   const int lane = threadIdx.x & 31;
   const int r0 = ((blockIdx.x * TPB + threadIdx.x) >> 5) << 5;
-  if (r0 >= n) return;  // warp-uniform
+  const bool warp_on = r0 < n;  // warp-uniform (no early exit: the statistics below need every warp at the barriers)
   const int rp = row_ptr[min(r0 + lane, n)];
   const int begin = __shfl_sync(0xffffffffu, rp, 0);
-  const int end = row_ptr[min(r0 + 32, n)];
+  const int end = warp_on ? row_ptr[min(r0 + 32, n)] : begin;
   const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
   const int my_cnt = (lane == 31 ? end : rp_next) - rp;
+  // fused extras: my row's id, its slice of the i<j edge list, its type counters
+  const int my_rid = (r0 + lane < n) ? (x.row_id ? x.row_id[r0 + lane] : r0 + lane) : 0;
+  int my_up = 0, my_upn = 0;
+  if (x.up_ptr) { my_up = x.up_ptr[min(r0 + lane, n)]; my_upn = x.up_ptr[min(r0 + lane + 1, n)] - my_up; }
+  int* wcnt = s_cnt[threadIdx.x >> 5];
+  if (x.nbr_count)
+    for (int t = 0; t < x.n_types; ++t) wcnt[lane * x.n_types + t] = 0;
+  __syncwarp();
   int my_own = 0;  // valid entries of the lane's row
   if (r0 + lane < n) {
     if (K != 0) {
@@ -232,6 +274,8 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
     const int rcnt = __shfl_sync(0xffffffffu, my_cnt, kk);
     const int rbase = __shfl_sync(0xffffffffu, rp, kk);
     const int own = __shfl_sync(0xffffffffu, my_own, kk);
+    const int rid = __shfl_sync(0xffffffffu, my_rid, kk);
+    const int upb = __shfl_sync(0xffffffffu, my_up, kk), upn = __shfl_sync(0xffffffffu, my_upn, kk);
     if (p >= end) continue;
     const int64_t rowk = (int64_t)(r0 + kk) * k;
     const int me = p - rbase;  // position in the row's unsorted range: own entries by slot, then the arrivals
@@ -294,6 +338,77 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
     col[dst] = c;
     if (w64) w64[dst] = (double)w;
     if (w32) w32[dst] = (float)w;
+    if (x.up_ptr) {  // the row's last up_n sorted entries are its i<j edges (ipynb:1894 G.edges / :2969-2975)
+      const int at = rank - (rcnt - upn);
+      if (at >= 0) {
+        const int64_t e = (int64_t)upb + at;
+        if (x.edges) *reinterpret_cast<longlong2*>(x.edges + 2 * e) = make_longlong2(rid, c);
+        if (x.ew64) x.ew64[e] = (double)w;
+        if (x.ew32) x.ew32[e] = (float)w;
+      }
+    }
+    if (x.nbr_count) {  // neighbour-type composition (README.md:127): one shared-memory counter per (row, type)
+      const int ty = x.type[c];
+      if (ty >= 1 && ty <= x.n_types) atomicAdd(&wcnt[kk * x.n_types + ty - 1], 1);
+    }
+  }
+  __syncwarp();
+  if (warp_on && x.nbr_count) {  // the warp's 32 rows x n_types counters are one contiguous range of nbr_count
+    const int rows_here = min(32, n - r0);
+    for (int i = lane; i < rows_here * x.n_types; i += 32) x.nbr_count[(int64_t)r0 * x.n_types + i] = wcnt[i];
+  }
+  if (x.degree && r0 + lane < n) x.degree[r0 + lane] = my_cnt;
+  if (!want_stats) return;
+  // ---- degree statistics: thread -> warp -> CTA -> accumulators; the last CTA publishes them and re-arms
+  {
+    const bool have = r0 + lane < n;
+    const int d = have ? my_cnt : 0;
+    int mn = have ? d : 0x7fffffff, mx = have ? d : -1;
+    long long sum = d, sq = (long long)d * d;
+    if (x.hist) {
+      const int bin = have ? min(d, x.hist_len - 1) : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin >= 0 && lane == __ffs(peers) - 1) {
+        if (x.hist_len <= PG_ACC_HIST_MAX) atomicAdd(&s_hist[bin], __popc(peers));
+        else atomicAdd(&x.hist[bin], __popc(peers));
+      }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, dd); sq += __shfl_xor_sync(0xffffffffu, sq, dd); }
+    if (lane == 0) {
+      atomicMin(&s_mn, mn); atomicMax(&s_mx, mx);
+      atomicAdd(&s_sum, (unsigned long long)sum); atomicAdd(&s_sq, (unsigned long long)sq);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicMin(&x.acc->min_degree, s_mn); atomicMax(&x.acc->max_degree, s_mx);
+    atomicAdd(&x.acc->sum_degree, s_sum); atomicAdd(&x.acc->sumsq_degree, s_sq);
+  }
+  if (x.hist && x.hist_len <= PG_ACC_HIST_MAX)
+    for (int i = threadIdx.x; i < x.hist_len; i += TPB)
+      if (s_hist[i]) atomicAdd(&x.acc_hist[i], s_hist[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&x.acc->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (x.hist && x.hist_len <= PG_ACC_HIST_MAX)
+    for (int i = threadIdx.x; i < x.hist_len; i += TPB) {
+      x.hist[i] = *(volatile int32_t*)&x.acc_hist[i];
+      x.acc_hist[i] = 0;
+    }
+  if (threadIdx.x == 0) {
+    volatile pg_stats_acc* a = x.acc;
+    if (x.stats) {
+      x.stats->min_degree = n > 0 ? a->min_degree : 0; x.stats->max_degree = n > 0 ? a->max_degree : 0;
+      x.stats->sum_degree = (long long)a->sum_degree; x.stats->sumsq_degree = (long long)a->sumsq_degree;
+      x.stats->n_nodes = n;
+    }
+    a->min_degree = 0x7fffffff; a->max_degree = -1; a->sum_degree = 0; a->sumsq_degree = 0; a->n_nodes = 0; a->done = 0;
   }
 }
 
@@ -572,26 +687,30 @@ halo_unpack_kernel(const pg_halo_rec* __restrict__ recs, int n_recs, int skip_be
 
 extern "C" {
 
-int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
-                            const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, pg_stream stream) {
+int pg_knn_union_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
+                       const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, int32_t* up_row_ptr,
+                       pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = s;
-  PG_REQUIRE(h, n >= 0 && k >= 1 && k <= PG_MAX_K, "pg_knn_symmetrize_count: need n >= 0 and 1 <= k <= %d", PG_MAX_K);
-  PG_REQUIRE(h, und_row_ptr != nullptr && (n == 0 || knn_idx != nullptr), "pg_knn_symmetrize_count: NULL argument");
-  PG_REQUIRE(h, (int64_t)n * k < (int64_t)1 << 31, "pg_knn_symmetrize_count: n*k must be < 2^31");
+  PG_REQUIRE(h, n >= 0 && k >= 1 && k <= PG_MAX_K, "pg_knn_union_count: need n >= 0 and 1 <= k <= %d", PG_MAX_K);
+  PG_REQUIRE(h, und_row_ptr != nullptr && (n == 0 || knn_idx != nullptr), "pg_knn_union_count: NULL argument");
+  PG_REQUIRE(h, (int64_t)n * k < (int64_t)1 << 31, "pg_knn_union_count: n*k must be < 2^31");
   PG_REQUIRE(h, (row_id == nullptr) == (id_map == nullptr) && (!id_map || n_ids > 0),
-             "pg_knn_symmetrize_count: row_id and id_map go together (both NULL = identity)");
+             "pg_knn_union_count: row_id and id_map go together (both NULL = identity)");
   int rc;
   if ((rc = pg_reserve(h, h->sym_extra, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   if ((rc = pg_reserve(h, h->sym_recip, (size_t)n * k + 16))) return rc;
+  if (up_row_ptr && (rc = pg_reserve(h, h->sym_cursor, ((size_t)n + 4) * sizeof(int32_t)))) return rc;
   int32_t* row_count = (int32_t*)h->sym_extra.p;
+  int32_t* up_count = up_row_ptr ? (int32_t*)h->sym_cursor.p : nullptr;
   if (n > 0) {
     PG_CUDA(h, cudaMemsetAsync(row_count, 0, (size_t)n * sizeof(int32_t), s));
+    if (up_count) PG_CUDA(h, cudaMemsetAsync(up_count, 0, (size_t)n * sizeof(int32_t), s));
     const int blocks = pg_div_up(n, TPB);
     const bool vec = ((uintptr_t)knn_idx & 15) == 0;
-#define PG_MARK(K) PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<K><<<blocks, TPB, 0, s>>>(knn_idx, n, k, row_id, id_map, n_ids, (uint8_t*)h->sym_recip.p, row_count))
+#define PG_MARK(K) PG_LAUNCH(h, s, "sym_mark_kernel", sym_mark_kernel<K><<<blocks, TPB, 0, s>>>(knn_idx, n, k, row_id, id_map, n_ids, (uint8_t*)h->sym_recip.p, row_count, up_count))
     if (vec && k == 8) PG_MARK(8);
     else if (vec && k == 16) PG_MARK(16);
     else if (vec && k == 4) PG_MARK(4);
@@ -600,35 +719,50 @@ int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* k
 #undef PG_MARK
     PG_LAUNCH_CHECK(h);
   }
-  // the scan leaves row_count all zero again: pg_knn_symmetrize_fill uses it as the push cursor
-  return pg_scan_i32(h, row_count, und_row_ptr, n, s, (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1, true);
-}
-
-int pg_knn_symmetrize_total(pg_handle* h, int64_t* total) {
-  if (!h || !total) return PG_ERR_INVALID;
-  PG_CUDA(h, cudaSetDevice(h->device));
-  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[1], (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1, sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, h->last_stream));
-  PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
-  *total = h->pinned[1];
+  int32_t* totals = (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS);
+  // the scan leaves row_count all zero again: pg_knn_union_fill uses it as the push cursor
+  if ((rc = pg_scan_i32(h, row_count, und_row_ptr, n, s, totals + 1, true))) return rc;
+  if (up_row_ptr && (rc = pg_scan_i32(h, up_count, up_row_ptr, n, s, totals + 2, false))) return rc;
   return PG_OK;
 }
 
-int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const double* dist64,
-                           const float* dist32, const int32_t* row_id, const int32_t* id_map,
-                           const int32_t* und_row_ptr, int32_t* und_col, double* und_w64, float* und_w32,
-                           pg_stream stream) {
+int pg_knn_union_total(pg_handle* h, int64_t* total, int64_t* upper_total) {
+  if (!h || !total) return PG_ERR_INVALID;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[1], (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS) + 1, 2 * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, h->last_stream));
+  PG_CUDA(h, cudaStreamSynchronize(h->last_stream));
+  *total = h->pinned[1];
+  if (upper_total) *upper_total = h->pinned[2];  // meaningful after a count pass that was given up_row_ptr
+  return PG_OK;
+}
+
+int pg_knn_union_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const double* dist64,
+                      const float* dist32, const int32_t* row_id, const int32_t* id_map,
+                      const int32_t* und_row_ptr, const int32_t* up_row_ptr, int32_t* und_col, double* und_w64,
+                      float* und_w32, const pg_union_out* extra, pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
   h->last_stream = s;
-  PG_REQUIRE(h, n >= 0 && k >= 1 && k <= PG_MAX_K, "pg_knn_symmetrize_fill: bad n / k");
-  PG_REQUIRE(h, dist64 || dist32, "pg_knn_symmetrize_fill: one of dist64 / dist32 is required");
-  PG_REQUIRE(h, und_row_ptr && (n == 0 || (knn_idx && und_col)), "pg_knn_symmetrize_fill: NULL argument");
-  if (n == 0) return PG_OK;
+  PG_REQUIRE(h, n >= 0 && k >= 1 && k <= PG_MAX_K, "pg_knn_union_fill: bad n / k");
+  PG_REQUIRE(h, n == 0 || dist64 || dist32, "pg_knn_union_fill: one of dist64 / dist32 is required");
+  PG_REQUIRE(h, und_row_ptr && (n == 0 || (knn_idx && und_col)), "pg_knn_union_fill: NULL argument");
+  pg_union_out x{};
+  if (extra) x = *extra;
+  PG_REQUIRE(h, !(x.edges || x.edge_w64 || x.edge_w32) || up_row_ptr, "pg_knn_union_fill: the edge list needs up_row_ptr from the count pass");
+  PG_REQUIRE(h, !x.nbr_count || (x.type && x.n_types >= 1 && x.n_types <= PG_MAX_TYPES),
+             "pg_knn_union_fill: nbr_count needs type and 1 <= n_types <= %d", PG_MAX_TYPES);
+  PG_REQUIRE(h, !x.hist || x.hist_len >= 1, "pg_knn_union_fill: hist_len must be >= 1");
+  PG_REQUIRE(h, ((uintptr_t)x.edges & 15) == 0, "pg_knn_union_fill: edges must be 16-byte aligned");
+  if (x.hist && (n == 0 || x.hist_len > PG_ACC_HIST_MAX)) PG_CUDA(h, cudaMemsetAsync(x.hist, 0, (size_t)x.hist_len * sizeof(int32_t), s));
+  if (n == 0) {
+    if (x.stats) PG_CUDA(h, cudaMemsetAsync(x.stats, 0, sizeof(pg_degree_stats), s));
+    return PG_OK;
+  }
   // the total of the matching count pass sizes the staging rows
   int64_t total = 0;
-  int rc = pg_knn_symmetrize_total(h, &total);
+  int rc = pg_knn_union_total(h, &total, nullptr);
   if (rc) return rc;
   // staging (arrival-order rows) lives in the grid's scratch that is free at this point
   pg_buf& tcol = h->cell_of;
@@ -637,22 +771,48 @@ int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* kn
   if ((rc = pg_reserve(h, tw, ((size_t)total + 4) * sizeof(double)))) return rc;
   int32_t* cursor = (int32_t*)h->sym_extra.p;  // all zero since the count pass's scan
   const uint8_t* recip = (const uint8_t*)h->sym_recip.p;
+  rank_extra rx{};
+  rx.row_id = row_id;
+  rx.up_ptr = (x.edges || x.edge_w64 || x.edge_w32) ? up_row_ptr : nullptr;
+  rx.edges = (long long*)x.edges; rx.ew64 = x.edge_w64; rx.ew32 = x.edge_w32;
+  rx.type = x.type; rx.n_types = x.nbr_count ? x.n_types : 1; rx.nbr_count = x.nbr_count;
+  rx.degree = x.degree; rx.stats = x.stats; rx.hist = x.hist; rx.hist_len = x.hist_len;
+  rx.acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
+  rx.acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
   const int blocks = pg_div_up(n, TPB);
-#define PG_PUSH(DT, D, K) PG_LAUNCH(h, s, "sym_push_kernel", sym_push_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, row_id, id_map, recip, und_row_ptr, cursor, (int32_t*)tcol.p, (DT*)tw.p))
   const bool vec = (((uintptr_t)knn_idx | (uintptr_t)dist64 | (uintptr_t)dist32) & 15) == 0;
+#define PG_PUSH(DT, D, K) PG_LAUNCH(h, s, "sym_push_kernel", sym_push_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, row_id, id_map, recip, und_row_ptr, cursor, (int32_t*)tcol.p, (DT*)tw.p))
+#define PG_RANK(DT, D, K) PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const DT*)tw.p, und_col, und_w64, und_w32, rx))
   if (dist64) {
-    if (vec && k == 8) PG_PUSH(double, dist64, 8); else if (vec && k == 16) PG_PUSH(double, dist64, 16); else PG_PUSH(double, dist64, 0);
-#define PG_RANK(DT, D, K) PG_LAUNCH(h, s, "sym_rank_kernel", sym_rank_kernel<DT, K><<<blocks, TPB, 0, s>>>(knn_idx, D, n, k, id_map, recip, und_row_ptr, (const int32_t*)tcol.p, (const DT*)tw.p, und_col, und_w64, und_w32))
-    if (vec && k == 8) PG_RANK(double, dist64, 8); else if (vec && k == 16) PG_RANK(double, dist64, 16); else PG_RANK(double, dist64, 0);
+    if (vec && k == 8) { PG_PUSH(double, dist64, 8); PG_RANK(double, dist64, 8); }
+    else if (vec && k == 16) { PG_PUSH(double, dist64, 16); PG_RANK(double, dist64, 16); }
+    else { PG_PUSH(double, dist64, 0); PG_RANK(double, dist64, 0); }
   } else {
-    if (vec && k == 8) PG_PUSH(float, dist32, 8); else if (vec && k == 16) PG_PUSH(float, dist32, 16); else PG_PUSH(float, dist32, 0);
-    if (vec && k == 8) PG_RANK(float, dist32, 8); else if (vec && k == 16) PG_RANK(float, dist32, 16); else PG_RANK(float, dist32, 0);
-#undef PG_RANK
+    if (vec && k == 8) { PG_PUSH(float, dist32, 8); PG_RANK(float, dist32, 8); }
+    else if (vec && k == 16) { PG_PUSH(float, dist32, 16); PG_RANK(float, dist32, 16); }
+    else { PG_PUSH(float, dist32, 0); PG_RANK(float, dist32, 0); }
   }
 #undef PG_PUSH
+#undef PG_RANK
   PG_LAUNCH_CHECK(h);
   // the cursor holds the arrival counts now; the next count pass clears it again
   return PG_OK;
+}
+
+// the plain symmetrisation = the union without the fused extras
+int pg_knn_symmetrize_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
+                            const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, pg_stream stream) {
+  return pg_knn_union_count(h, n, k, knn_idx, row_id, id_map, n_ids, und_row_ptr, nullptr, stream);
+}
+
+int pg_knn_symmetrize_total(pg_handle* h, int64_t* total) { return pg_knn_union_total(h, total, nullptr); }
+
+int pg_knn_symmetrize_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const double* dist64,
+                           const float* dist32, const int32_t* row_id, const int32_t* id_map,
+                           const int32_t* und_row_ptr, int32_t* und_col, double* und_w64, float* und_w32,
+                           pg_stream stream) {
+  return pg_knn_union_fill(h, n, k, knn_idx, dist64, dist32, row_id, id_map, und_row_ptr, nullptr, und_col, und_w64,
+                           und_w32, nullptr, stream);
 }
 
 int pg_csr_upper_count(pg_handle* h, int32_t n, const int32_t* row_ptr, const int32_t* col,

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PathGraphError, PgMorphOut, PgRasterOut
+from ._lib import PathGraphError, PgMorphOut, PgRasterOut, PgUnionOut
 
 _INF = float("inf")
 
@@ -308,6 +308,56 @@ class Engine:
             self._p(row_ptr, torch.int32, "row_ptr"), self._p(col, torch.int32, "col"),
             self._p(w64, torch.float64, "w64"), self._p(w32, torch.float32, "w32"), self._stream()))
         return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}
+
+    def knn_union(self, knn_idx, knn_dist, types=None, n_types=5, hist_len=64, row_id=None, id_map=None,
+                  want_edges=True, compose=True):
+        """Undirected union + i<j edge list + composition + degree statistics in one pass chain (pg_knn_union_*).
+
+        Returns row_ptr, col, w (dtype of ``knn_dist``), edges int64 [E,2], edge_w, degree, stats, hist and, with
+        ``types`` (indexed by column id), nbr_count.  One host synchronisation (the two totals)."""
+        n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
+        row_ptr = self._empty((n + 1,), torch.int32)
+        up_ptr = self._empty((n + 1,), torch.int32) if want_edges else None
+        n_ids = int(id_map.numel()) if id_map is not None else 0
+        self._check(self.lib.pg_knn_union_count(self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+                                                self._p(row_id, torch.int32, "row_id"),
+                                                self._p(id_map, torch.int32, "id_map"), n_ids,
+                                                self._p(row_ptr, torch.int32, "row_ptr"),
+                                                self._p(up_ptr, torch.int32, "up_ptr"), self._stream()))
+        total, upper = C.c_int64(), C.c_int64()
+        self._check(self.lib.pg_knn_union_total(self._h, C.byref(total), C.byref(upper)))
+        e, eu = int(total.value), int(upper.value) if want_edges else 0
+        is64 = knn_dist.dtype == torch.float64
+        wt = torch.float64 if is64 else torch.float32
+        col, w = self._empty((e,), torch.int32), self._empty((e,), wt)
+        edges = self._empty((eu, 2), torch.int64) if want_edges else None
+        edge_w = self._empty((eu,), wt) if want_edges else None
+        do_comp = compose and types is not None
+        nbr = self._empty((n, n_types), torch.int32) if do_comp else None
+        degree = self._empty((n,), torch.int32)
+        st = self._empty((4,), torch.int64)
+        hist = self._empty((hist_len,), torch.int32) if hist_len else None
+        x = PgUnionOut()
+        x.edges = self._p(edges, torch.int64, "edges")
+        x.edge_w64 = self._p(edge_w, torch.float64, "edge_w") if is64 else None
+        x.edge_w32 = None if is64 else self._p(edge_w, torch.float32, "edge_w")
+        x.type = self._p(types, torch.int32, "types") if do_comp else None
+        x.n_types = int(n_types)
+        x.nbr_count = self._p(nbr, torch.int32, "nbr_count")
+        x.degree = self._p(degree, torch.int32, "degree")
+        x.stats = self._p(st, torch.int64, "stats")
+        x.hist = self._p(hist, torch.int32, "hist")
+        x.hist_len = int(hist_len) if hist is not None else 0
+        self._check(self.lib.pg_knn_union_fill(
+            self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+            self._p(knn_dist, torch.float64, "dist64") if is64 else None,
+            None if is64 else self._p(knn_dist, torch.float32, "dist32"),
+            self._p(row_id, torch.int32, "row_id"), self._p(id_map, torch.int32, "id_map"),
+            self._p(row_ptr, torch.int32, "row_ptr"), self._p(up_ptr, torch.int32, "up_ptr"),
+            self._p(col, torch.int32, "col"), self._p(w, torch.float64, "w") if is64 else None,
+            None if is64 else self._p(w, torch.float32, "w"), C.byref(x), self._stream()))
+        return {"row_ptr": row_ptr, "col": col, "w": w, "edges": edges, "edge_w": edge_w, "up_ptr": up_ptr,
+                "nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
 
     def csr_upper(self, row_ptr, col, w=None, row_id=None, want_w32=False):
         """Symmetric CSR (rows ascending) -> edges int64 [E,2] with i<j, sorted by (i,j), + weights."""

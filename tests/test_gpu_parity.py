@@ -418,3 +418,63 @@ def test_full_size_c2_against_scipy(engine):
 def test_full_size_c1_knn_against_scipy(engine):
     xy, types, side = synth.make_points(100_000, seed=synth.SEEDS["C1"])
     _check_knn(engine, xy, types, 8, bounds=(0.0, 0.0, float(side), float(side)))
+
+
+# ---------------------------------------------------------------- fused union (K7 + edge list + K8 in one chain)
+@pytest.mark.parametrize("k,dt", [(5, torch.float64), (8, torch.float32), (8, torch.float64), (16, torch.float32)])
+def test_knn_union_fused_equals_separate_passes(engine, k, dt):
+    from path_gene_multimodal_b200.engine import default_knn_cell
+
+    xy, types, side = synth.make_points(30_000, 77 + k)
+    xy[100:140] = xy[100]                                  # duplicates: ties by id, heavy reverse rows
+    engine.grid_build(dev(xy), dev(types), None, default_knn_cell(len(xy), float(side) ** 2, k), None)
+    kn = engine.knn(k, dist_dtype=dt)
+    d = kn["dist"]
+    sym = engine.symmetrize(kn["knn_idx"], d)
+    up = engine.csr_upper(sym["row_ptr"], sym["col"], sym["w"])
+    comp = engine.compose_degree(sym["row_ptr"], sym["col"], dev(types), 5)
+    fu = engine.knn_union(kn["knn_idx"], d, types=dev(types), n_types=5)
+    assert torch.equal(fu["row_ptr"], sym["row_ptr"]) and torch.equal(fu["col"], sym["col"]) and torch.equal(fu["w"], sym["w"])
+    assert torch.equal(fu["edges"], up["edges"])
+    assert torch.equal(fu["edge_w"], up["w64"] if dt == torch.float64 else up["w32"])
+    assert torch.equal(fu["nbr_count"], comp["nbr_count"]) and torch.equal(fu["degree"], comp["degree"])
+    assert engine.decode_stats(fu["stats"], fu["hist"]).keys() == engine.decode_stats(comp["stats"], comp["hist"]).keys()
+    a, b = engine.decode_stats(fu["stats"], fu["hist"]), engine.decode_stats(comp["stats"], comp["hist"])
+    assert all(np.array_equal(a[q], b[q]) for q in a)
+    # oracle: the notebook's union
+    idx, dist = ograph.knn(xy, k)
+    e, w, rp, col, _ = ograph.undirected_union(idx, dist)
+    assert np.array_equal(fu["edges"].cpu().numpy(), e)
+    # ids in another space (strips: global ids): rows permuted, lists / types by id
+    n = len(xy)
+    perm = torch.randperm(n, device="cuda", dtype=torch.int64)          # row r has id perm[r]
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device="cuda")
+    idx_ids = perm[kn["knn_idx"].long()].int()                           # lists in id space, still in row order
+    types_by_id = torch.empty(n, dtype=torch.int32, device="cuda")
+    types_by_id[perm] = dev(types)
+    fp = engine.knn_union(idx_ids.contiguous(), d, types=types_by_id, n_types=5, row_id=perm.int().contiguous(),
+                          id_map=inv.int().contiguous())
+    assert torch.equal(fp["row_ptr"], sym["row_ptr"]) and torch.equal(fp["degree"], comp["degree"])
+    assert torch.equal(fp["nbr_count"], comp["nbr_count"])
+    ee = fp["edges"]
+    assert bool((ee[:, 0] < ee[:, 1]).all()) and ee.shape == up["edges"].shape
+    back = torch.stack([inv[ee[:, 0]], inv[ee[:, 1]]], dim=1)
+    back = torch.stack([back.min(dim=1).values, back.max(dim=1).values], dim=1)
+    key = back[:, 0] * n + back[:, 1]
+    assert torch.equal(back[torch.argsort(key)], up["edges"])
+
+
+def test_knn_union_small_and_empty(engine):
+    idx = dev(np.array([[1, 2], [0, 2], [0, 1], [0, 1]], dtype=np.int32))
+    dist = dev(np.array([[1.0, 2.0], [1.0, 1.5], [2.0, 1.5], [3.0, 3.5]], dtype=np.float64))
+    fu = engine.knn_union(idx, dist, types=dev(np.array([1, 2, 2, 5], dtype=np.int32)), n_types=5, hist_len=8)
+    assert fu["row_ptr"].tolist() == [0, 3, 6, 8, 10] and fu["col"].tolist() == [1, 2, 3, 0, 2, 3, 0, 1, 0, 1]
+    assert fu["edges"].tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3]]
+    assert fu["edge_w"].tolist() == [1.0, 2.0, 3.0, 1.5, 3.5]
+    assert fu["nbr_count"].tolist() == [[0, 2, 0, 0, 1], [1, 1, 0, 0, 1], [1, 1, 0, 0, 0], [1, 1, 0, 0, 0]]
+    st = engine.decode_stats(fu["stats"], fu["hist"])
+    assert (st["min"], st["max"], st["sum"], st["n"]) == (2, 3, 10, 4) and st["hist"][:4].tolist() == [0, 0, 2, 2]
+    e0 = engine.knn_union(torch.empty((0, 3), dtype=torch.int32, device="cuda"),
+                          torch.empty((0, 3), dtype=torch.float32, device="cuda"), hist_len=4)
+    assert e0["row_ptr"].tolist() == [0] and e0["edges"].shape == (0, 2) and e0["hist"].tolist() == [0, 0, 0, 0]
