@@ -408,7 +408,7 @@ def other_stages(eng, dev, flush, peak):
 
     def knn_union():
         knn()
-        eng.knn_union(kres["knn_idx"], kres["dist32"], types=dt_, n_types=N_TYPES, want_edges=False)
+        eng.knn_union(kres["knn_idx"], kres["dist32"], types=dt_, n_types=N_TYPES, want_edges=False, symmetric_dist=True)
 
     ms = timed(knn_union, reps=3)
     out["knn_k8_1M_full(grid+query+union+composition)"] = {"ms": ms, "nuclei_per_s": N_NUCLEI / ms * 1e3}
@@ -437,7 +437,7 @@ def other_stages(eng, dev, flush, peak):
             eng.grid_build(wsi, t_types, None, cell_k, bnd)
             kn = eng.knn(8, dist_dtype=torch.float32, out=keep.get("kn"))
             keep["kn"] = kn
-            eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=N_TYPES)
+            eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=N_TYPES, symmetric_dist=True)
             if with_radius:
                 eng.grid_build(wsi, t_types, None, radius_cell(RADIUS), bnd)
                 keep["rg"] = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True,

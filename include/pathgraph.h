@@ -186,6 +186,8 @@ typedef struct {
   pg_degree_stats* stats;
   int32_t* hist;
   int32_t hist_len;
+  int32_t symmetric_dist; /* non-zero: dist(i->j) == dist(j->i) bit for bit (true for lists made by pg_knn on one
+                           * coordinate set), so the weight = min over both directions needs no reverse lookup */
 } pg_union_out;
 int pg_knn_union_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
                        const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, int32_t* up_row_ptr,

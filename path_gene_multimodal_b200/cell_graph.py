@@ -76,7 +76,7 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
         eng.grid_check()
         if undirected:
             # union + i<j edges + composition + degree statistics: one fused pass chain (pg_knn_union_*)
-            u = eng.knn_union(kn["knn_idx"], kn["dist"], types=d_t, n_types=n_types)
+            u = eng.knn_union(kn["knn_idx"], kn["dist"], types=d_t, n_types=n_types, symmetric_dist=True)
             host = _host.to_host_many({"edges": u["edges"], "weight": u["edge_w"], "row_ptr": u["row_ptr"], "col": u["col"],
                                        "csr_weight": u["w"], "degree": u["degree"], "stats": u["stats"], "hist": u["hist"],
                                        "nbr_count": u["nbr_count"]})

@@ -212,6 +212,7 @@ struct rank_extra {
   int32_t* degree;
   pg_degree_stats* stats; int32_t* hist; int hist_len;
   pg_stats_acc* acc; int32_t* acc_hist;
+  bool sym_dist;           // the lists' distances are symmetric bit for bit: no reverse read for the min
 };
 
 template <class DT, int K>  // K = compile-time k with 16-byte aligned rows (vector loads), or 0 = any k
@@ -293,10 +294,12 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
 #pragma unroll
         for (int s = 0; s < KK; ++s) c = s == me ? ids[s] : c;
         w = dist[rowk + me];
-        const int rc = recip[rowk + me];
-        if (rc != RECIP_NONE) {
-          const int j = id_map ? id_map[c] : c;
-          w = min(w, dist[(int64_t)j * k + rc]);  // weight = min over directions (ipynb:1888-1892)
+        if (!x.sym_dist) {  // weight = min over directions (ipynb:1888-1892); equal by construction for pg_knn lists
+          const int rc = recip[rowk + me];
+          if (rc != RECIP_NONE) {
+            const int j = id_map ? id_map[c] : c;
+            w = min(w, dist[(int64_t)j * k + rc]);
+          }
         }
       } else {
         c = tmp_col[p];
@@ -316,7 +319,7 @@ sym_rank_kernel(const int32_t* __restrict__ knn_idx, const DT* __restrict__ dist
         c = knn_idx[rowk + s];
         w = dist[rowk + s];
         const int rc = recip[rowk + s];
-        if (rc != RECIP_NONE) {
+        if (rc != RECIP_NONE && !x.sym_dist) {
           const int j = id_map ? id_map[c] : c;
           w = min(w, dist[(int64_t)j * k + rc]);
         }
@@ -777,6 +780,7 @@ int pg_knn_union_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx
   rx.edges = (long long*)x.edges; rx.ew64 = x.edge_w64; rx.ew32 = x.edge_w32;
   rx.type = x.type; rx.n_types = x.nbr_count ? x.n_types : 1; rx.nbr_count = x.nbr_count;
   rx.degree = x.degree; rx.stats = x.stats; rx.hist = x.hist; rx.hist_len = x.hist_len;
+  rx.sym_dist = x.symmetric_dist != 0;
   rx.acc = (pg_stats_acc*)((char*)h->misc.p + PG_MISC_ACC);
   rx.acc_hist = (int32_t*)((char*)h->misc.p + PG_MISC_ACC_HIST);
   const int blocks = pg_div_up(n, TPB);

@@ -310,11 +310,13 @@ class Engine:
         return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}
 
     def knn_union(self, knn_idx, knn_dist, types=None, n_types=5, hist_len=64, row_id=None, id_map=None,
-                  want_edges=True, compose=True):
+                  want_edges=True, compose=True, symmetric_dist=False):
         """Undirected union + i<j edge list + composition + degree statistics in one pass chain (pg_knn_union_*).
 
         Returns row_ptr, col, w (dtype of ``knn_dist``), edges int64 [E,2], edge_w, degree, stats, hist and, with
-        ``types`` (indexed by column id), nbr_count.  One host synchronisation (the two totals)."""
+        ``types`` (indexed by column id), nbr_count.  One host synchronisation (the two totals).  ``symmetric_dist``:
+        the lists come from ``knn()`` on one coordinate set (d(i,j) == d(j,i) bit for bit), so weight = min needs no
+        reverse lookup."""
         n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
         row_ptr = self._empty((n + 1,), torch.int32)
         up_ptr = self._empty((n + 1,), torch.int32) if want_edges else None
@@ -348,6 +350,7 @@ class Engine:
         x.stats = self._p(st, torch.int64, "stats")
         x.hist = self._p(hist, torch.int32, "hist")
         x.hist_len = int(hist_len) if hist is not None else 0
+        x.symmetric_dist = 1 if symmetric_dist else 0
         self._check(self.lib.pg_knn_union_fill(
             self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
             self._p(knn_dist, torch.float64, "dist64") if is64 else None,

@@ -28,7 +28,7 @@ for _ in range(reps):
     flush.zero_()
     eng.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, 8), bounds)
     kres = eng.knn(8, dist_dtype=torch.float32, out=kres)
-sym = eng.knn_union(kres["knn_idx"], kres["dist32"], types=d_ty, n_types=5)
+sym = eng.knn_union(kres["knn_idx"], kres["dist32"], types=d_ty, n_types=5, symmetric_dist=True)
 eng.csr_upper(sym["row_ptr"], sym["col"], sym["w"])          # the stand-alone passes, for any CSR
 eng.compose_degree(sym["row_ptr"], sym["col"], d_ty, 5)
 eng.clustering(sym["row_ptr"], sym["col"])

@@ -23,7 +23,7 @@ for k in [int(a) for a in sys.argv[1:]] or [8, 16]:
     def run():
         eng.grid_build(d_xy, d_ty, None, cell, bounds)
         kres = eng.knn(k, dist_dtype=torch.float32)
-        u = eng.knn_union(kres["knn_idx"], kres["dist32"], types=d_ty, n_types=5)
+        u = eng.knn_union(kres["knn_idx"], kres["dist32"], types=d_ty, n_types=5, symmetric_dist=True)
         return u, u
 
     for _ in range(3):

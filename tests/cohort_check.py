@@ -63,7 +63,7 @@ def main():
         bnd = (0.0, 0.0, side_px, side_px)
         eng.grid_build(wsi, t_types, None, default_knn_cell(n, side_px ** 2, 8), bnd)
         kn = eng.knn(8, dist_dtype=torch.float32)
-        up = comp = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=5)
+        up = comp = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=5, symmetric_dist=True)
         eng.grid_build(wsi, t_types, None, radius_cell(50.0), bnd)
         rg = eng.radius_graph(50.0, upper=True, n_types=5, want_dist32=True, want_edges=True)
         st = eng.decode_stats(rg["stats"], rg["hist"])

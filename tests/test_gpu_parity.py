@@ -434,6 +434,8 @@ def test_knn_union_fused_equals_separate_passes(engine, k, dt):
     up = engine.csr_upper(sym["row_ptr"], sym["col"], sym["w"])
     comp = engine.compose_degree(sym["row_ptr"], sym["col"], dev(types), 5)
     fu = engine.knn_union(kn["knn_idx"], d, types=dev(types), n_types=5)
+    fs = engine.knn_union(kn["knn_idx"], d, types=dev(types), n_types=5, symmetric_dist=True)   # pg_knn lists: same weights
+    assert torch.equal(fs["w"], fu["w"]) and torch.equal(fs["edge_w"], fu["edge_w"]) and torch.equal(fs["col"], fu["col"])
     assert torch.equal(fu["row_ptr"], sym["row_ptr"]) and torch.equal(fu["col"], sym["col"]) and torch.equal(fu["w"], sym["w"])
     assert torch.equal(fu["edges"], up["edges"])
     assert torch.equal(fu["edge_w"], up["w64"] if dt == torch.float64 else up["w32"])
