@@ -123,6 +123,52 @@ def reference_pipeline(coords, types, r, n_types=N_TYPES):
     return len(edges), edge_index.shape, edge_attr.shape
 
 
+def cpu_stage_timings():
+    """SURVEY 8(d) timing protocol: the reference's CPU stages on the GPU box's host, on bounded samples of the
+    BASELINE workloads (a few seconds each), next to the GPU numbers of the same run. kind = "port": the oracle's
+    restatements (the reference function itself cannot travel to the GPU box; scipy / networkx are its own deps)."""
+    import pandas as pd  # noqa: F401
+    from scipy.spatial import cKDTree
+
+    from oracle import graph as ograph
+    from oracle import morphology as omorph
+    from oracle import tile_to_wsi as omap
+    from path_gene_multimodal_b200 import synth
+
+    out = {"cores_available": len(os.sched_getaffinity(0)), "os_cpu_count": os.cpu_count()}
+
+    def clock(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return time.perf_counter() - t0, r
+
+    # (i) a1-a3: add_wsi_coords_to_nuclei on a C1-style table (per-row Python loops, single-threaded by nature)
+    n1 = 20_000
+    tab = synth.make_table(n1, synth.SEEDS["C1"], dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    dt, _ = clock(lambda: omap.add_wsi_coords_to_nuclei_oracle(nuc, tiles))
+    out["add_wsi_coords_to_nuclei"] = {"nuclei_per_s": n1 / dt, "sample": f"{n1} nuclei of C1 (DataFrame in, DataFrame out)", "cores": 1}
+    # (ii) a4-a5: per-polygon morphology (numpy restatement of the GEOS / moment formulas; shapely is absent)
+    n2 = 200_000
+    off, xy = synth.make_polygons(n2, synth.SEEDS["C3"], v_fixed=32)
+    dt, _ = clock(lambda: omorph.polygon_features_csr(off, xy))
+    out["polygon_morphology_numpy"] = {"polygons_per_s": n2 / dt, "sample": f"{n2} polygons x 32 vertices of C3 (vectorised numpy, no per-polygon GEOS object)", "cores": 1}
+    # (iii) a6: cKDTree build + query(k+1), one worker and all workers
+    n3 = 1_000_000
+    c3, t3, _ = synth.make_points(n3, synth.SEEDS["C2"])
+    dt_b, tree = clock(lambda: cKDTree(c3))
+    dt1, _ = clock(lambda: tree.query(c3[:200_000], 9, workers=1))
+    dta, _ = clock(lambda: tree.query(c3, 9, workers=-1))
+    out["ckdtree_knn_k8"] = {"build_s": dt_b, "query_nuclei_per_s_1_worker": 200_000 / dt1, "query_nuclei_per_s_all_workers": n3 / dta,
+                             "sample": "tree over the 1M-nuclei slide; 200k queries with workers=1, 1M with workers=-1"}
+    # (iv) a7: the notebook's undirected-union loop (networkx has_edge / add_edge per directed edge)
+    n4 = 50_000
+    idx, dist = ograph.knn(c3[:n4], 8)
+    dt, _ = clock(lambda: ograph.undirected_union_networkx(idx, dist))
+    out["knn_union_networkx_loop"] = {"nuclei_per_s": n4 / dt, "sample": f"{n4} nuclei, k=8 (cell 11 loop)", "cores": 1}
+    return out
+
+
 def cpu_sample(n, seed):
     from path_gene_multimodal_b200 import synth
 
@@ -344,6 +390,7 @@ def run_ours(args, rank, world, local_rank):
                 "sample": "the full 1M-nuclei slide once: scipy cKDTree + query_ball_tree + the notebook's i<j Python loop + "
                           "np.linalg.norm + numpy composition/degree (oracle/graph.py); same edges as the GPU run",
                 "seconds": dt, "host_cores_available": len(os.sched_getaffinity(0))}
+            line["cpu_stages"] = cpu_stage_timings()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
