@@ -263,7 +263,7 @@ int pg_raster_props(pg_handle* h, int32_t height, int32_t width, const int32_t* 
  * ipynb:2950 (cell 23: pd.get_dummies(type, prefix="type"), features = one-hot columns then the *_z columns).
  * feat float64 [n_feat][n] (one contiguous column per feature), type int32 [n], onehot_values int32 [n_onehot]
  * (the distinct type values, ascending) -> x float32 [n][n_onehot + n_feat] row-major, stats float64
- * [n_feat][2] = {mean, sigma} (device).  Deterministic (fixed-order pairwise merge of moments). */
+ * [n_feat][2] = {mean, sigma} (device); n_feat <= 256.  Deterministic (pandas' two-pass mean / variance, fixed-order sums). */
 int pg_node_features(pg_handle* h, int32_t n, int32_t n_feat, const double* feat, const int32_t* type,
                      const int32_t* onehot_values, int32_t n_onehot, float* x, double* stats,
                      pg_stream stream);

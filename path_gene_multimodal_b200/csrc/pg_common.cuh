@@ -104,11 +104,12 @@ struct pg_kernel_scope {
 #define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
 #define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])
-#define PG_MISC_FEAT_TICKET 208  // uint32 CTA ticket of feature_stats_kernel (zero between launches)
+#define PG_MISC_FEAT_TICKET 4608  // uint32 [PG_FEAT_MAX_COLS] CTA tickets of feature_stats_kernel, one per column (zero between launches)
+#define PG_FEAT_MAX_COLS 256
 #define PG_MISC_ACC 256       // pg_stats_acc: degree-statistics accumulators kept in their reset state
 #define PG_MISC_ACC_HIST 512  // int32 [PG_ACC_HIST_MAX] histogram accumulators (all zero between launches)
 #define PG_ACC_HIST_MAX 1024
-#define PG_MISC_BYTES (PG_MISC_ACC_HIST + 4 * PG_ACC_HIST_MAX)
+#define PG_MISC_BYTES (PG_MISC_FEAT_TICKET + 4 * PG_FEAT_MAX_COLS)
 
 // accumulators behind the fused degree statistics: every CTA adds its share, the last CTA to finish
 // copies them to the caller's pg_degree_stats / hist and puts them back into the reset state, so no

@@ -4,11 +4,8 @@
 // :2950 (cell 23: pd.get_dummies(type, prefix="type") one-hot columns in ascending type order, features =
 // one-hot columns followed by the *_z columns).
 //
-// Two launches, no atomics on floats, so the result does not depend on scheduling:
-//   stats    a fixed grid; every thread folds its strided share of a column into (count, mean, M2) and the
-//            partials are merged pairwise (Chan et al.) lane -> warp -> CTA in a fixed order; the CTA's partial
-//            goes to the workspace and the LAST CTA to finish (a ticket) merges the G partials of every column
-//            in index order and leaves mean / sigma where the next launch and the caller find them.
+// Three launches, no atomics on floats, so the result does not depend on scheduling:
+//   stats x2 pandas' own two-pass mean / variance (see feature_stats_kernel), all columns per launch;
 //   assemble one thread per output element of x [N, n_onehot + n_feat] (row-major float32, coalesced stores).
 #include <algorithm>
 #include "pg_common.cuh"
@@ -17,81 +14,49 @@ namespace {
 
 constexpr int TPB = 256;
 
-struct moments {
-  double n, mean, m2;
-};
-
-__device__ __forceinline__ moments merge(const moments& a, const moments& b) {
-  if (b.n == 0.0) return a;
-  if (a.n == 0.0) return b;
-  moments r;
-  r.n = a.n + b.n;
-  const double d = b.mean - a.mean;
-  r.mean = a.mean + d * (b.n / r.n);
-  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
-  return r;
-}
-
-__device__ __forceinline__ moments shfl_xor(const moments& v, int lane_mask) {
-  moments r;
-  r.n = __shfl_xor_sync(0xffffffffu, v.n, lane_mask);
-  r.mean = __shfl_xor_sync(0xffffffffu, v.mean, lane_mask);
-  r.m2 = __shfl_xor_sync(0xffffffffu, v.m2, lane_mask);
-  return r;
-}
-
-// feat is column-major [n_feat][n]; partial is [n_feat][gridDim.x]; stats_out is [n_feat][2] = {mean, sigma}
+// One reduction pass over every column (blockIdx.y = column): PASS 0 accumulates (count, sum) of the non-NaN
+// values, PASS 1 the squared deviations from the mean PASS 0 left in stats_out - pandas' own two-pass nanvar.
+// Fixed order throughout: a thread's strided share, a shuffle tree, the warps of the CTA in index order, and the
+// CTA partials in index order by the last CTA of the column (ticket); nothing depends on scheduling.
+template <int PASS>
 __global__ void __launch_bounds__(TPB)
-feature_stats_kernel(const double* __restrict__ feat, int n, int n_feat, moments* __restrict__ partial,
-                     unsigned int* ticket, double* __restrict__ stats_out) {
-  __shared__ moments s_part[TPB / 32];
+feature_stats_kernel(const double* __restrict__ feat, int n, double2* __restrict__ partial, unsigned int* tickets,
+                     double* __restrict__ stats_out) {
+  __shared__ double s_a[TPB / 32], s_b[TPB / 32];
   __shared__ bool s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = 0; c < n_feat; ++c) {
-    const double* col = feat + (int64_t)c * n;
-    moments m{0.0, 0.0, 0.0};
-    for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-      const double v = col[i];
-      if (v == v) {  // pandas skips NaN in both mean and std
-        m.n += 1.0;
-        const double d = v - m.mean;
-        m.mean += d / m.n;
-        m.m2 += d * (v - m.mean);
-      }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y;
+  const double* col = feat + (int64_t)c * n;
+  const double mean = PASS == 1 ? stats_out[2 * c] : 0.0;
+  double a = 0.0, b = 0.0;  // PASS 0: count, sum; PASS 1: count, sum of squared deviations
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    const double v = col[i];
+    if (v == v) {  // pandas skips NaN in both mean and std
+      a += 1.0;
+      if (PASS == 0) b += v;
+      else { const double d = v - mean; b += d * d; }
     }
-    // lane l merges with lane l ^ d: written so that both sides compute the same value (lower lane first)
+  }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const moments o = shfl_xor(m, d);
-      m = (lane & d) ? merge(o, m) : merge(m, o);
-    }
-    if (lane == 0) s_part[warp] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      moments t = s_part[0];
-      for (int w = 1; w < TPB / 32; ++w) t = merge(t, s_part[w]);
-      partial[(int64_t)c * gridDim.x + blockIdx.x] = t;
-    }
-    __syncthreads();
-  }
-  __threadfence();
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+  if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int c = threadIdx.x; c < n_feat; c += TPB) {
-    const volatile moments* p = partial + (int64_t)c * gridDim.x;
-    moments t{0.0, 0.0, 0.0};
-    for (unsigned int g = 0; g < gridDim.x; ++g) {
-      moments q;
-      q.n = p[g].n; q.mean = p[g].mean; q.m2 = p[g].m2;
-      t = merge(t, q);
-    }
-    const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
-    stats_out[2 * c] = t.n > 0.0 ? t.mean : nan_;
-    stats_out[2 * c + 1] = t.n > 0.0 ? sqrt(t.m2 / t.n) : nan_;  // ddof = 0
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) { ta += s_a[w]; tb += s_b[w]; }
+    partial[(int64_t)c * gridDim.x + blockIdx.x] = make_double2(ta, tb);
+    __threadfence();
+    s_last = atomicAdd(&tickets[c], 1u) == gridDim.x - 1;
   }
-  if (threadIdx.x == 0) *ticket = 0u;  // re-armed for the next call
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const volatile double2* p = partial + (int64_t)c * gridDim.x;
+  double ta = 0.0, tb = 0.0;
+  for (unsigned int g = 0; g < gridDim.x; ++g) { ta += p[g].x; tb += p[g].y; }
+  const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
+  if (PASS == 0) stats_out[2 * c] = ta > 0.0 ? tb / ta : nan_;
+  else stats_out[2 * c + 1] = ta > 0.0 ? sqrt(tb / ta) : nan_;  // ddof = 0
+  tickets[c] = 0u;  // re-armed for the next launch
 }
 
 __global__ void __launch_bounds__(TPB)
@@ -114,6 +79,32 @@ feature_assemble_kernel(const double* __restrict__ feat, const int32_t* __restri
   x[e] = v;
 }
 
+// the same for narrow matrices (width <= TILE_WIDTH_MAX): a CTA owns TPB consecutive rows; thread t computes row t
+// column by column (coalesced reads of type / feat, no integer division) into a shared-memory tile whose
+// TPB x width floats are then written out as one contiguous, fully coalesced range of x
+constexpr int TILE_WIDTH_MAX = 40;
+__global__ void __launch_bounds__(TPB)
+feature_assemble_tile_kernel(const double* __restrict__ feat, const int32_t* __restrict__ type,
+                             const int32_t* __restrict__ onehot_values, int n, int n_feat, int n_onehot,
+                             const double* __restrict__ stats, float* __restrict__ x) {
+  extern __shared__ float s_tile[];  // [TPB][width], row stride = width (odd widths are conflict-free as they are)
+  const int width = n_onehot + n_feat;
+  const int row0 = blockIdx.x * TPB, i = row0 + threadIdx.x;
+  if (i < n) {
+    float* mine = s_tile + threadIdx.x * width;
+    const int ty = n_onehot ? type[i] : 0;
+    for (int c = 0; c < n_onehot; ++c) mine[c] = ty == onehot_values[c] ? 1.0f : 0.0f;
+    for (int f = 0; f < n_feat; ++f) {
+      const double mu = stats[2 * f], sigma = stats[2 * f + 1];
+      mine[n_onehot + f] = (sigma == 0.0 || sigma != sigma) ? 0.0f : (float)((feat[(int64_t)f * n + i] - mu) / sigma);
+    }
+  }
+  __syncthreads();
+  const int rows = min(TPB, n - row0);
+  float* dst = x + (int64_t)row0 * width;
+  for (int e = threadIdx.x; e < rows * width; e += TPB) dst[e] = s_tile[e];
+}
+
 }  // namespace
 
 extern "C" int pg_node_features(pg_handle* h, int32_t n, int32_t n_feat, const double* feat, const int32_t* type,
@@ -128,16 +119,23 @@ extern "C" int pg_node_features(pg_handle* h, int32_t n, int32_t n_feat, const d
   PG_REQUIRE(h, n_onehot == 0 || (type && onehot_values), "pg_node_features: type / onehot_values is NULL");
   PG_REQUIRE(h, (int64_t)n * (n_feat + n_onehot) == 0 || x, "pg_node_features: x is NULL");
   if (n_feat > 0) {
-    const int grid = n > 0 ? std::min(pg_div_up(n, TPB), h->sm_count * 4) : 1;
-    int rc = pg_reserve(h, h->cell_of, (size_t)n_feat * grid * sizeof(moments) + 64);
+    PG_REQUIRE(h, n_feat <= PG_FEAT_MAX_COLS, "pg_node_features: at most %d feature columns", PG_FEAT_MAX_COLS);
+    const int gx = n > 0 ? std::max(1, std::min(pg_div_up(n, TPB * 4), h->sm_count * 8 / n_feat + 1)) : 1;
+    int rc = pg_reserve(h, h->cell_of, (size_t)n_feat * gx * sizeof(double2) + 64);
     if (rc) return rc;
-    unsigned int* ticket = (unsigned int*)((char*)h->misc.p + PG_MISC_FEAT_TICKET);
-    PG_LAUNCH(h, s, "feature_stats_kernel", feature_stats_kernel<<<grid, TPB, 0, s>>>(feat, n, n_feat, (moments*)h->cell_of.p, ticket, stats));
+    unsigned int* tickets = (unsigned int*)((char*)h->misc.p + PG_MISC_FEAT_TICKET);
+    const dim3 grid(gx, n_feat);
+    PG_LAUNCH(h, s, "feature_stats_kernel<0>", feature_stats_kernel<0><<<grid, TPB, 0, s>>>(feat, n, (double2*)h->cell_of.p, tickets, stats));
+    PG_LAUNCH(h, s, "feature_stats_kernel<1>", feature_stats_kernel<1><<<grid, TPB, 0, s>>>(feat, n, (double2*)h->cell_of.p, tickets, stats));
     PG_LAUNCH_CHECK(h);
   }
   const int64_t elems = (int64_t)n * (n_feat + n_onehot);
   if (elems > 0) {
     PG_REQUIRE(h, elems / TPB < 0x7fffffff, "pg_node_features: feature matrix too large");
+    const int width = n_feat + n_onehot;
+    if (width <= TILE_WIDTH_MAX)
+      PG_LAUNCH(h, s, "feature_assemble_tile_kernel", feature_assemble_tile_kernel<<<pg_div_up(n, TPB), TPB, (size_t)TPB * width * sizeof(float), s>>>(feat, type, onehot_values, n, n_feat, n_onehot, stats, x));
+    else
     PG_LAUNCH(h, s, "feature_assemble_kernel", feature_assemble_kernel<<<pg_div_up(elems, TPB), TPB, 0, s>>>(feat, type, onehot_values, n, n_feat, n_onehot, stats, x));
     PG_LAUNCH_CHECK(h);
   }

@@ -46,6 +46,12 @@ res = {}
 for _ in range(reps):
     flush.zero_()
     res = eng.map_morph(d_off, d_p, nuc_tile, tile_x, tile_y, cen, bb, write_polygons=True, out=res)
+# K10 / K12 (not on the bench path): node features of 1M nuclei x 10 columns, region properties of a 4096^2 map
+feat = torch.rand((10, n), dtype=torch.float64, device=dev)
+eng.node_features(feat, d_ty, torch.arange(1, 6, dtype=torch.int32, device=dev))
+lab = (torch.arange(4096 * 4096, device=dev, dtype=torch.int32).reshape(4096, 4096) // 16 % 4096 // 16 +
+       (torch.arange(4096, device=dev, dtype=torch.int32) // 16)[:, None] * 256 + 1).contiguous()
+eng.raster_props(lab, 65536)
 torch.cuda.synchronize()
 eng.check_overflow()
 print("capture ok", eng.launches)

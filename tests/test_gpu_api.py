@@ -218,6 +218,22 @@ def test_node_feature_matrix_against_the_notebook_cells(n):
     np.testing.assert_allclose(got["std"], [df[c].std(ddof=0) for c in cols], rtol=1e-9, atol=1e-12, equal_nan=True)
 
 
+def test_node_feature_matrix_wide():
+    # more columns than the shared-memory tile path takes: the per-element kernel
+    from oracle import features as ofeat
+    from path_gene_multimodal_b200 import node_feature_matrix
+
+    rng = np.random.default_rng(3)
+    n = 5000
+    cols = [f"f{j}" for j in range(60)]
+    df = pd.DataFrame(rng.normal(size=(n, 60)) * rng.uniform(0.1, 50, size=60) + rng.uniform(-100, 100, size=60), columns=cols)
+    df["type"] = rng.integers(1, 6, size=n)
+    want, want_cols = ofeat.node_features(df, cont_cols=cols)
+    got = node_feature_matrix(df, cont_cols=cols)
+    assert got["columns"] == want_cols and got["x"].shape == (n, 65)
+    np.testing.assert_allclose(got["x"], want, rtol=1e-5, atol=1e-6)
+
+
 def test_assemble_graph_data_cells_23_to_27():
     from oracle import features as ofeat
     from path_gene_multimodal_b200 import assemble_graph_data
