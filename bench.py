@@ -60,7 +60,8 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed regions (device-resident steps, then the
+    end-to-end steps) run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -75,7 +76,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -298,7 +299,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = eng.launches - l0
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    clocks = sampler.stop()
     eng.check_overflow()
     total_ms = float(sum(step_ms))
     assert int(out["row_ptr"][-1]) == e_und
@@ -324,6 +324,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
     if dist is not None:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

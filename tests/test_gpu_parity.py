@@ -480,3 +480,60 @@ def test_knn_union_small_and_empty(engine):
     e0 = engine.knn_union(torch.empty((0, 3), dtype=torch.int32, device="cuda"),
                           torch.empty((0, 3), dtype=torch.float32, device="cuda"), hist_len=4)
     assert e0["row_ptr"].tolist() == [0] and e0["edges"].shape == (0, 2) and e0["hist"].tolist() == [0, 0, 0, 0]
+
+
+# ---------------------------------------------------------------- seeded fuzz against the brute-force oracles
+def _fuzz_points(rng, n, kind):
+    if kind == "uniform":
+        xy = rng.random((n, 2)) * rng.choice([50.0, 500.0, 5000.0])
+    elif kind == "clustered":                                   # tight clumps in a large empty frame (real tissue)
+        c = rng.random((max(1, n // 40), 2)) * 4000.0
+        xy = c[rng.integers(0, len(c), size=n)] + rng.normal(scale=rng.choice([1.0, 15.0]), size=(n, 2))
+    elif kind == "lattice":                                     # exact ties everywhere
+        s = int(np.ceil(np.sqrt(n)))
+        g = np.stack(np.meshgrid(np.arange(s), np.arange(s)), axis=-1).reshape(-1, 2)[:n].astype(np.float64)
+        xy = g * rng.choice([1.0, 7.5, 25.0])
+    elif kind == "duplicates":
+        base = rng.random((max(2, n // 5), 2)) * 300.0
+        xy = base[rng.integers(0, len(base), size=n)]
+    else:                                                       # a line: degenerate bounding box
+        xy = np.stack([rng.random(n) * 1000.0, np.full(n, 3.25)], axis=1)
+    return np.ascontiguousarray(xy[rng.permutation(n)], dtype=np.float64)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_radius_and_knn_against_bruteforce(engine, seed):
+    rng = np.random.default_rng(1000 + seed)
+    for case in range(14):
+        kind = ["uniform", "clustered", "lattice", "duplicates", "line"][(seed + case) % 5]
+        n = int(rng.choice([2, 3, 17, 64, 257, 900, 1500]))
+        xy = _fuzz_points(rng, n, kind)
+        types = rng.integers(0, 8, size=n).astype(np.int32)     # types outside 1..5 are counted in the degree only
+        span = max(np.ptp(xy[:, 0]), np.ptp(xy[:, 1]), 1.0)
+        r = float(rng.choice([0.0, 1.0, 7.5, 25.0, 0.05 * span, 0.3 * span]))
+        cell = None if rng.random() < 0.5 else float(max(r, 1e-3) * rng.choice([0.4, 1.0, 2.7]))
+        ref = ograph.radius_graph_bruteforce(xy, r)
+        g = _radius(engine, xy, types, r, upper=True, cell=cell)
+        tag = (seed, case, kind, n, r, cell)
+        assert np.array_equal(g["edges"].cpu().numpy(), ref["edges"]), tag
+        assert np.array_equal(g["dist64"].cpu().numpy(), ref["dist"]), tag
+        assert np.array_equal(g["degree"].cpu().numpy(), np.diff(ref["row_ptr"])), tag
+        assert np.array_equal(g["nbr_count"].cpu().numpy(), ograph.composition(ref["row_ptr"], ref["col"], types, 5)), tag
+        s = _radius(engine, xy, types, r, upper=False, cell=cell)
+        assert np.array_equal(s["col"].cpu().numpy(), ref["col"]) and np.array_equal(s["row_ptr"].cpu().numpy(), ref["row_ptr"]), tag
+        if n >= 3:
+            k = int(rng.choice([1, 2, 5, 8, 13, 16, 20, 40]))
+            k = min(k, n - 1)
+            from path_gene_multimodal_b200.engine import default_knn_cell
+
+            kcell = default_knn_cell(n, span * span, k) * float(rng.choice([0.5, 1.0, 3.0]))
+            engine.grid_build(dev(xy), dev(types), None, kcell, None)
+            kn = engine.knn(k, dist_dtype=torch.float64)
+            idx, dist = ograph.knn_bruteforce(xy, k)
+            assert np.array_equal(kn["knn_idx"].cpu().numpy(), idx), tag + (k,)
+            assert np.array_equal(kn["dist"].cpu().numpy(), dist), tag + (k,)
+            fu = engine.knn_union(kn["knn_idx"], kn["dist"], types=dev(types), n_types=5, symmetric_dist=True)
+            e, w, rp, col, _ = ograph.undirected_union(idx, dist)
+            assert np.array_equal(fu["edges"].cpu().numpy(), e) and np.array_equal(fu["edge_w"].cpu().numpy(), w), tag + (k,)
+            assert np.array_equal(fu["nbr_count"].cpu().numpy(), ograph.composition(rp, col, types, 5)), tag + (k,)
+    engine.check_overflow()
