@@ -170,6 +170,31 @@ def cpu_stage_timings():
     return out
 
 
+def table_api_timings(device):
+    """The a1-a3 drop-in through its two public entry points, end to end from HOST tables on one GPU: the reference's
+    DataFrame format (one Python list per vertex in and out - the format, not the kernel, sets the pace) and the
+    Arrow table (list<list<double>> = CSR buffers, no Python object per nucleus)."""
+    import pyarrow as pa
+
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei, add_wsi_coords_to_table, synth
+
+    n = 50_000
+    tab = synth.make_table(n, synth.SEEDS["C1"], dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    tb = pa.Table.from_pandas(nuc, preserve_index=False)
+    out = {}
+    for name, fn, arg in (("add_wsi_coords_to_nuclei(DataFrame)", add_wsi_coords_to_nuclei, nuc),
+                          ("add_wsi_coords_to_table(Arrow)", add_wsi_coords_to_table, tb)):
+        fn(arg, tiles, device=device)
+        t0 = time.perf_counter()
+        reps = 2 if "DataFrame" in name else 10
+        for _ in range(reps):
+            fn(arg, tiles, device=device)
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"nuclei_per_s": n / dt, "ms": dt * 1e3, "sample": f"{n} nuclei of C1, host table in, host table out"}
+    return out
+
+
 def cpu_sample(n, seed):
     from path_gene_multimodal_b200 import synth
 
@@ -392,6 +417,7 @@ def run_ours(args, rank, world, local_rank):
                           "np.linalg.norm + numpy composition/degree (oracle/graph.py); same edges as the GPU run",
                 "seconds": dt, "host_cores_available": len(os.sched_getaffinity(0))}
             line["cpu_stages"] = cpu_stage_timings()
+            line["table_api_e2e"] = table_api_timings(local_rank)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
