@@ -100,7 +100,7 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
-#define PG_MISC_KNN_RETRY 76  // int32 x 2: points the 3x3 select pass handed on ([0]), points the 5x5 pass handed to the ring pass ([1])
+#define PG_MISC_KNN_RETRY 76  // int32: points the kNN select pass handed to the ring pass
 #define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
 #define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])

@@ -164,54 +164,27 @@ __device__ __forceinline__ void walk3x3(const pg_grid_view& g, int cx, int cy, F
   }
 }
 
-// every candidate of the (2R+1)^2 block, any R: one run per column and strip touched, four loads in flight
-template <class F>
-__device__ __forceinline__ void walk_block_any(const pg_grid_view& g, int cx, int cy, int R, F&& f) {
-  const int pad = g.n;
-  pg_visit_block(g, cx, cy, R, [&](int b, int e) {
-    for (int j = b; j < e; j += 4) {
-      const int p1 = j + 1 < e ? j + 1 : pad, p2 = j + 2 < e ? j + 2 : pad, p3 = j + 3 < e ? j + 3 : pad;
-      const pg_rec r0 = pg_ld_rec(g.rec + j), r1 = pg_ld_rec(g.rec + p1);
-      const pg_rec r2 = pg_ld_rec(g.rec + p2), r3 = pg_ld_rec(g.rec + p3);
-      f(r0); f(r1); f(r2); f(r3);
-    }
-  });
-}
-
 constexpr int SEL_BINS = 16;
 
-// R == 1: every point, 3x3 block (three merged runs); R > 1: the points of `list`, (2R+1)^2 block.
-template <int KMAX, int R>
+template <int KMAX>
 __global__ void __launch_bounds__(TPB)
-knn_select_kernel(pg_grid_view g, int k, knn_out o, const int32_t* list, const int32_t* list_count,
-                  int32_t* retry, int32_t* retry_count) {
+knn_select_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* retry_count) {
   constexpr int S = KMAX + KMAX / 2;  // survivors a thread can park
   __shared__ double s_d2[S][TPB];
   __shared__ int s_id[S][TPB];
   const int tid = threadIdx.x;
   pg_pdl_launch();
   pg_pdl_wait();
-  int p = blockIdx.x * TPB + tid;
-  if (R == 1) {
-    if (p >= g.n) return;
-  } else {
-    if (p >= *(volatile const int32_t*)list_count) return;
-    p = list[p];
-  }
+  const int p = blockIdx.x * TPB + tid;
+  if (p >= g.n) return;
   const pg_rec me = pg_ld_rec_ordered(g.rec + p);
   if (me.row >= g.n_query) return;  // halo points own no row
   const int cx = pg_cell_coord(me.x, g.x0, g.inv_cell, g.nx);
   const int cy = pg_cell_coord(me.y, g.y0, g.inv_cell, g.ny);
-  const double bound = block_bound(g, me.x, me.y, cx, cy, R);
-  auto walk = [&](auto&& f) __attribute__((always_inline)) {
-    if (R == 1) walk3x3(g, cx, cy, f); else walk_block_any(g, cx, cy, R, f);
-  };
+  const double bound = block_bound(g, me.x, me.y, cx, cy, 1);
+  auto walk = [&](auto&& f) __attribute__((always_inline)) { walk3x3(g, cx, cy, f); };
   bool ok = bound > 0.0 && bound < 1e300;  // infinite: the block covers the grid (tiny inputs) - ring pass
-  // the histogram spans [0, bound^2); for the 5x5 block that is narrowed to 1.75 cells (cells are ~1.15 expected
-  // k-th distances wide, so the k-th neighbour of a retried point sits well inside and the bins stay fine enough
-  // for the survivors to fit); a point whose k-th neighbour is farther still goes on to the ring pass
-  const double reach = R == 1 ? bound : fmin(bound, 1.75 * g.cell);
-  const double bound2 = ok ? reach * reach : 0.0;
+  const double bound2 = ok ? bound * bound : 0.0;  // the histogram spans [0, bound^2)
   const double inv_binw = ok ? (double)SEL_BINS / bound2 : 0.0;
   ok = ok && inv_binw < 1e300;
 
@@ -340,8 +313,7 @@ knn_ring_kernel(pg_grid_view g, int k, knn_out o, const int32_t* list, const int
 
 __global__ void knn_prepare_kernel(int32_t* halo_ok, int32_t* retry_count) {
   if (halo_ok) *halo_ok = 1;
-  retry_count[0] = 0;
-  retry_count[1] = 0;
+  *retry_count = 0;
 }
 
 }  // namespace
@@ -370,13 +342,12 @@ extern "C" int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64,
     int32_t* retry = (int32_t*)h->knn_retry.p;
     // 3x3 select over every point -> retry list -> ring pass over the list. (Tried and measured slower at the ~6 %
     // retry rate of a 1.15 d_k cell: a 5x5 select pass over the list, and one warp per retried point - see DESIGN.md.)
-    const int32_t* no_list = nullptr;
     const int ring_blocks = std::min(blocks, h->sm_count * 8);
     if (k <= 8) {
-      PG_LAUNCH(h, s, "knn_select_kernel<8>", pg_launch_pdl(6, knn_select_kernel<8, 1>, blocks, TPB, s, v, (int)k, o, no_list, no_list, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_select_kernel<8>", pg_launch_pdl(6, knn_select_kernel<8>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
       PG_LAUNCH(h, s, "knn_ring_kernel<8>", pg_launch_pdl(7, knn_ring_kernel<8, topk<8>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
     } else {
-      PG_LAUNCH(h, s, "knn_select_kernel<16>", pg_launch_pdl(6, knn_select_kernel<16, 1>, blocks, TPB, s, v, (int)k, o, no_list, no_list, retry, retry_count));
+      PG_LAUNCH(h, s, "knn_select_kernel<16>", pg_launch_pdl(6, knn_select_kernel<16>, blocks, TPB, s, v, (int)k, o, retry, retry_count));
       PG_LAUNCH(h, s, "knn_ring_kernel<16>", pg_launch_pdl(7, knn_ring_kernel<16, topk<16>>, ring_blocks, TPB, s, v, (int)k, o, (const int32_t*)retry, (const int32_t*)retry_count));
     }
   } else if (k <= 32) {
