@@ -246,9 +246,9 @@ def kernel_bytes(name, n, e_und, cells):
     table = {
         "histogram_kernel": 16 * n + 4 * cells,                       # xy in; cell counters
         "scan_kernel": 8 * cells,                                     # counters in, cell starts out
-        "scatter_kernel": 16 * n + 4 * n + 4 * cells + 32 * n + 4 * n,  # xy, type, cursors in; 32-byte records + positions out
+        "scatter_kernel": 16 * n + 4 * n + 4 * cells + 32 * n,        # xy, type, cursors in; 32-byte records out
         "radius_walk_kernel": 32 * n + 4 * cells + 32 * n + 16 * e_und,  # records, cell starts in; per-point meta + parked entries out
-        "radius_rows_kernel": 4 * n + 32 * n + 4 * n + 4 * n + 4 * N_TYPES * n + 4 * n,  # pos, meta in; row_ptr, degree, nbr_count, row_off out
+        "radius_rows_kernel": 32 * n + 4 * n + 4 * n + 4 * N_TYPES * n + 4 * n,  # meta in; row_ptr, degree, nbr_count, row_off out
         "radius_gather_kernel": 8 * n + 16 * e_und + 4 * e_und + 4 * e_und + 16 * e_und,  # row_ptr, row_off, entries in; col, dist32, edges out
     }
     return table.get(name)
