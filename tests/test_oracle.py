@@ -216,3 +216,45 @@ def test_raster_oracle_on_analytic_shapes():
     assert abs(p["orientation"][1]) == np.pi / 2                                        # long axis along the columns
     assert abs(p["perimeter"][2] / (2 * np.pi * 12) - 1) < 0.05 and p["eccentricity"][2] < 0.05
     assert abs(p["area"][2] / (np.pi * 144) - 1) < 0.03
+
+
+def test_contour_oracle_cycle_rule_equals_literal_assembly():
+    # groundwork for SURVEY 8f-3 (second half, not built yet): the closed form the CUDA kernel will use - a contour
+    # starts at the to-point of its last segment in square order, contours are numbered by their first segment -
+    # reproduces skimage's dictionary bookkeeping (restated literally in oracle/contours.py) on random masks with
+    # holes, several components and border contact; and the exact-arithmetic Douglas-Peucker is a valid member of
+    # the family of results the float version can produce (same end points, every dropped vertex within tolerance)
+    from oracle import contours as oc
+
+    rng = np.random.default_rng(4)
+    rr0, cc0 = np.mgrid[0:48, 0:48]
+    for it in range(120):
+        h, w = int(rng.integers(4, 40)), int(rng.integers(4, 40))
+        rr, cc = rr0[:h, :w], cc0[:h, :w]
+        m = np.zeros((h, w), dtype=bool)
+        for _ in range(int(rng.integers(1, 5))):
+            cy, cx = rng.uniform(-2, h + 2), rng.uniform(-2, w + 2)
+            a, b, th = rng.uniform(2, 12), rng.uniform(1.5, 7), rng.uniform(0, np.pi)
+            y, x = rr - cy, cc - cx
+            u, v = x * np.cos(th) + y * np.sin(th), -x * np.sin(th) + y * np.cos(th)
+            m |= (u / a) ** 2 + (v / b) ** 2 <= 1
+        if rng.random() < 0.5:
+            m[rng.integers(0, h), rng.integers(0, w)] ^= True
+        cs = oc.find_contours(m)
+        got = oc.longest_contour_by_cycles(m)
+        if not cs:
+            assert got is None
+            continue
+        want = max(cs, key=lambda c: c.shape[0])
+        assert want.shape == got.shape and np.array_equal(want, got), it
+        poly = np.stack([want[:, 1], want[:, 0]], axis=1)
+        ex = oc.approximate_polygon_exact(poly, 0.5)
+        assert np.array_equal(ex[0], poly[0]) and np.array_equal(ex[-1], poly[-1]) and len(ex) <= len(poly)
+        fl = oc.approximate_polygon_float(poly, 0.5)
+        assert abs(len(ex) - len(fl)) <= max(4, len(fl) // 4)          # same simplification up to tie choices
+    # a 3 x 3 square: the 12-segment ring collapses to its 4 diagonal corners cut at the half-pixel + closing vertex
+    sq = np.zeros((7, 7), dtype=bool)
+    sq[2:5, 2:5] = True
+    c = oc.find_contours(sq)[0]
+    assert len(c) == 13 and np.array_equal(c[0], c[-1])
+    assert oc.instance_polygons(sq.astype(np.int32))[1][0] == oc.instance_polygons(sq.astype(np.int32))[1][-1]
