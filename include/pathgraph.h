@@ -258,6 +258,21 @@ typedef struct {
 int pg_raster_props(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map,
                     int32_t n_labels, const pg_raster_out* out, pg_stream stream);
 
+/* ---- K13: instance map -> one polygon per instance: aggregated_hovernet_run.py:183-198 -
+ * find_contours(inst_map == id, 0.5), the longest contour, (x, y) = (col, row), approximate_polygon(tolerance).
+ * area / bbox are pg_raster_props outputs for the same map. count: poly_off int32 [n_labels + 1] (device, 16-byte
+ * aligned; labels without pixels get empty rings); total: vertices to allocate (one host synchronisation, two more
+ * inside count for the scratch); fill: poly_xy float64 [total][2], closed rings (first == last vertex) as skimage
+ * returns them. Douglas-Peucker decisions are taken in exact integer arithmetic on the half-pixel lattice (a distance
+ * equal to the tolerance is not "greater"; the first maximum splits) - skimage's float evaluation breaks such ties
+ * by libm rounding. fill must follow its count on the same handle (the contours wait in the workspace). */
+int pg_instance_contours_count(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map,
+                               int32_t n_labels, const int32_t* area, const int32_t* bbox, double tolerance,
+                               int32_t* poly_off, pg_stream stream);
+int pg_instance_contours_total(pg_handle* h, int64_t* total);
+int pg_instance_contours_fill(pg_handle* h, int32_t n_labels, const int32_t* poly_off, double* poly_xy,
+                              pg_stream stream);
+
 /* ---- K10: node features for the GNN input.  hovernet_tile_inference.ipynb:2903 (cell 21:
  * z = (v - mean) / std(ddof=0), NaN-skipping statistics, a column with sigma 0 / NaN becomes all 0.0) and
  * ipynb:2950 (cell 23: pd.get_dummies(type, prefix="type"), features = one-hot columns then the *_z columns).

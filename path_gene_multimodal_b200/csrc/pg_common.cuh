@@ -68,6 +68,9 @@ struct pg_handle {
   int32_t radius_flags = 0;
   cudaStream_t last_stream = nullptr;
   int32_t sm_count = 148;
+  int32_t contour_labels = -1;   // labels of the last pg_instance_contours_count (-1: none), for the fill call
+  bool contour_empty = false;
+  int64_t contour_raw = 0;
   double morph_mean_verts = 0;  // pg_map_morph_hint: expected vertices per ring (sizes K1's shared-memory slabs)
   // launch accounting / optional per-kernel CUDA-event timing (pg_profile_*)
   int64_t launches = 0;
@@ -102,7 +105,7 @@ struct pg_kernel_scope {
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
 #define PG_MISC_KNN_RETRY 76  // int32: points the kNN select pass handed to the ring pass
 #define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
-#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper; [4..5] uint64 overflow-region entries the last count pass needed
+#define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper [3] contour scans; [4..5] uint64 overflow-region entries the last count pass needed
 #define PG_MISC_TMPCUR 192    // uint64 allocation cursor of tmp_ent's overflow region (zero between count passes: the row pass moves it to TOTALS[4..5])
 #define PG_MISC_FEAT_TICKET 4608  // uint32 [PG_FEAT_MAX_COLS] CTA tickets of feature_stats_kernel, one per column (zero between launches)
 #define PG_FEAT_MAX_COLS 256

@@ -420,6 +420,25 @@ class Engine:
                                              C.byref(ro), self._stream()))
         return res
 
+    # ---- K13 -----------------------------------------------------------------------------------
+    def instance_contours(self, inst_map, n_labels, area, bbox, tolerance=0.5):
+        """One simplified contour polygon per label of an int32 instance map (pg_instance_contours_*).
+
+        ``area`` / ``bbox`` come from ``raster_props`` on the same map. Returns poly_off int32 [n_labels+1] and
+        poly_xy float64 [M,2] (x, y), closed rings."""
+        hgt, wid = int(inst_map.shape[0]), int(inst_map.shape[1])
+        n = int(n_labels)
+        off = self._empty((n + 1,), torch.int32)
+        self._check(self.lib.pg_instance_contours_count(
+            self._h, hgt, wid, self._p(inst_map, torch.int32, "inst_map"), n, self._p(area, torch.int32, "area"),
+            self._p(bbox, torch.int32, "bbox"), float(tolerance), self._p(off, torch.int32, "poly_off"), self._stream()))
+        total = C.c_int64()
+        self._check(self.lib.pg_instance_contours_total(self._h, C.byref(total)))
+        xy = self._empty((int(total.value), 2), torch.float64)
+        self._check(self.lib.pg_instance_contours_fill(self._h, n, self._p(off, torch.int32, "poly_off"),
+                                                       self._p(xy, torch.float64, "poly_xy"), self._stream()))
+        return {"poly_off": off, "poly_xy": xy}
+
     # ---- K11 -----------------------------------------------------------------------------------
     def clustering(self, row_ptr, col):
         """Triangles through each node and the local clustering coefficient over a symmetric CSR (pg_clustering)."""

@@ -3,8 +3,8 @@
 Reference call sites: ``regionprops(inst_map)`` at aggregated_hovernet_run.py:172-181 (per-instance
 ``bounding_box = [x_min, y_min, x_max, y_max]``) and ``regionprops_table(inst_map, properties=...)`` at
 hovernet_tile_inference.ipynb:2415-2429 (cell 18).  One CUDA pass pair over the map (pg_raster_props) replaces
-skimage's per-region Python loop; ``solidity`` (convex hull) and the contour polygons (find_contours +
-approximate_polygon, :183-198) are not built yet and are left out rather than approximated.
+skimage's per-region Python loop, and one thread per instance traces and simplifies its contour polygon
+(pg_instance_contours_*, :183-198).  ``solidity`` (convex hull) is not built and is left out rather than approximated.
 """
 from __future__ import annotations
 
@@ -68,3 +68,40 @@ def instance_bounding_boxes(inst_map, device=None) -> dict:
     df = raster_regionprops(inst_map, device=device)
     return {int(l): [int(c0), int(r0), int(c1), int(r1)]
             for l, r0, c0, r1, c1 in zip(df["label"], df["bbox-0"], df["bbox-1"], df["bbox-2"], df["bbox-3"])}
+
+
+def instance_polygons_csr(inst_map, tolerance: float = 0.5, device=None):
+    """(labels int64 [K], poly_off int32 [K+1], poly_xy float64 [M,2]) - the polygon of every label present, as CSR:
+    ``find_contours(inst_map == id, 0.5)`` -> longest contour -> (x, y) -> ``approximate_polygon(tolerance)`` of
+    aggregated_hovernet_run.py:183-198, one CUDA thread per instance (pg_instance_contours_*). Rings are closed
+    (first == last vertex) like skimage's; Douglas-Peucker ties are decided in exact arithmetic."""
+    m = np.asarray(inst_map)
+    if m.ndim == 3:
+        m = m[0]
+    if m.ndim != 2:
+        raise ValueError("inst_map must be 2-D")
+    eng = get_engine(device)
+    n_labels = int(m.max()) if m.size else 0
+    if n_labels <= 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int32), np.zeros((0, 2))
+    with torch.cuda.device(eng.device):
+        d_m = _host.to_device(_host.as_int32(m, "inst_map"), np.int32, eng.device)
+        rp = eng.raster_props(d_m, n_labels)
+        res = eng.instance_contours(d_m, n_labels, rp["area"], rp["bbox"], tolerance)
+        host = _host.to_host_many({"off": res["poly_off"], "xy": res["poly_xy"], "area": rp["area"]})
+    nv = np.diff(host["off"].astype(np.int64))
+    keep = (host["area"] > 0) & (nv > 0)
+    lab = np.nonzero(keep)[0]
+    xy_idx = np.concatenate([np.arange(host["off"][l], host["off"][l + 1]) for l in lab]) if len(lab) else np.zeros(0, dtype=np.int64)
+    off = np.zeros(len(lab) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(nv[lab])
+    return (lab + 1).astype(np.int64), off, np.ascontiguousarray(host["xy"][xy_idx.astype(np.int64)]).reshape(-1, 2)
+
+
+def instance_polygons(inst_map, tolerance: float = 0.5, device=None) -> dict:
+    """``poly_dict`` of aggregated_hovernet_run.py:183-198: inst_id -> list of [x, y]."""
+    from .nuclei_wsi import csr_to_polygons
+
+    labels, off, xy = instance_polygons_csr(inst_map, tolerance, device)
+    rings = csr_to_polygons(off, xy)
+    return {int(l): rings[i] for i, l in enumerate(labels)}

@@ -334,3 +334,44 @@ def test_raster_regionprops_against_restated_skimage(shape):
     np.testing.assert_allclose(morph["compactness"].to_numpy(), 4 * np.pi * a / np.clip(p_, 1, None) ** 2, rtol=1e-12)
     stacked = raster_regionprops(m[None])                        # (1, H, W) maps are squeezed like the reference does
     assert stacked["label"].tolist() == got["label"].tolist()
+
+
+@pytest.mark.parametrize("shape,n", [((521, 521), 120), ((64, 37), 9), ((2, 2), 1), ((1, 9), 1)])
+def test_instance_polygons_against_restated_skimage(shape, n):
+    # SURVEY 8f-3, second half: find_contours + longest + approximate_polygon(0.5) per instance
+    # (aggregated_hovernet_run.py:183-198), one CUDA thread per instance, exact-arithmetic tie rule
+    from oracle import contours as ocont
+    from oracle import morphology as omorph2
+    from path_gene_multimodal_b200 import instance_polygons, instance_polygons_csr
+
+    if shape[0] > 2:
+        m = _blob_map(*shape, n=n, seed=shape[1] + 1)
+        m[10:13, 20:23][1, 1] = 0 if m[11, 21] else m[11, 21]             # (keeps the map as is; holes come from overwrites)
+        m[30:37, 3:10] = n + 3                                             # a square ...
+        m[32:35, 5:8] = 0                                                  # ... with a hole: two contours, the outer is longer
+    else:
+        m = np.ones(shape, dtype=np.int32)
+    want = ocont.instance_polygons(m, 0.5, exact=True)
+    got = instance_polygons(m)
+    assert sorted(got) == sorted(want)
+    for lab in want:
+        assert got[lab] == want[lab], lab                                  # same vertices, same order, same start
+        if len(want[lab]) > 1:
+            assert got[lab][0] == got[lab][-1] or _touches_border(m, lab)  # closed unless cut by the image border
+    labels, off, xy = instance_polygons_csr(m)
+    assert labels.tolist() == sorted(want) and off[-1] == len(xy) == sum(len(v) for v in want.values())
+    if shape[0] > 100:
+        # the polygons are what the morphology kernel consumes: areas stay close to the pixel counts
+        feat = omorph2.polygon_features_csr(off, xy)
+        px = np.array([(m == l).sum() for l in labels], dtype=np.float64)
+        big = px > 60
+        assert np.all(np.abs(feat["area"][big] / px[big] - 1) < 0.25)
+        # float vs exact Douglas-Peucker: same simplification up to tie choices (documented divergence)
+        fl = ocont.instance_polygons(m, 0.5, exact=False)
+        same = sum(fl[l] == want[l] for l in want)
+        assert same >= len(want) // 2
+
+
+def _touches_border(m, lab):
+    rr, cc = np.nonzero(m == lab)
+    return rr.min() == 0 or cc.min() == 0 or rr.max() == m.shape[0] - 1 or cc.max() == m.shape[1] - 1
