@@ -258,6 +258,14 @@ typedef struct {
 int pg_raster_props(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map,
                     int32_t n_labels, const pg_raster_out* out, pg_stream stream);
 
+/* solidity = area / convex area (skimage regionprops: convex_hull_image of the region - the hull of the pixels' diamond
+ * corners, rasterised with its border - cell 18's fourth property). area / bbox: pg_raster_props outputs of the same map.
+ * convex_area int32 [n_labels], solidity float64 [n_labels] (NaN for absent labels); either may be NULL. Exact integer
+ * arithmetic; one host synchronisation (workspace size). */
+int pg_raster_solidity(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map, int32_t n_labels,
+                       const int32_t* area, const int32_t* bbox, int32_t* convex_area, double* solidity,
+                       pg_stream stream);
+
 /* ---- K13: instance map -> one polygon per instance: aggregated_hovernet_run.py:183-198 -
  * find_contours(inst_map == id, 0.5), the longest contour, (x, y) = (col, row), approximate_polygon(tolerance).
  * area / bbox are pg_raster_props outputs for the same map. count: poly_off int32 [n_labels + 1] (device, 16-byte

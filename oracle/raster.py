@@ -25,12 +25,40 @@ def _perimeter(image):
     return float(hist @ weights)
 
 
+def _convex_area(img):
+    """np.sum(skimage.morphology.convex_hull_image(img)): hull (qhull) of the pixels' diamond corners
+    (r +- 1/2, c), (r, c +- 1/2), then every pixel centre inside the hull or on its border (grid_points_in_poly
+    with include_borders=True). The inside test is done here in integers on doubled coordinates."""
+    from scipy.spatial import ConvexHull
+
+    rr, cc = np.nonzero(img)
+    pts = np.concatenate([np.stack([2 * rr + dr, 2 * cc + dc], axis=1) for dr, dc in ((-1, 0), (1, 0), (0, -1), (0, 1))])
+    pts = np.unique(pts, axis=0)
+    hull = ConvexHull(pts.astype(np.float64))
+    v = pts[hull.vertices].astype(np.int64)          # counter-clockwise
+    if len(v) >= 3:
+        a = v
+        b = np.roll(v, -1, axis=0)
+        area2 = np.sum(a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0])
+        if area2 < 0:
+            v = v[::-1]
+    h, w = img.shape
+    gr, gc = np.mgrid[0:h, 0:w]
+    p = np.stack([2 * gr.ravel(), 2 * gc.ravel()], axis=1).astype(np.int64)
+    inside = np.ones(len(p), dtype=bool)
+    for i in range(len(v)):
+        a, b = v[i], v[(i + 1) % len(v)]
+        cross = (b[0] - a[0]) * (p[:, 1] - a[1]) - (b[1] - a[1]) * (p[:, 0] - a[0])
+        inside &= cross >= 0
+    return int(inside.sum())
+
+
 def regionprops(inst_map):
     """dict of arrays, one entry per label present (ascending)."""
     m = np.asarray(inst_map)
     labels = [int(l) for l in np.unique(m) if l > 0]
     out = {k: [] for k in ("label", "area", "bbox", "centroid", "perimeter", "eccentricity", "major_axis_length",
-                           "minor_axis_length", "orientation")}
+                           "minor_axis_length", "orientation", "solidity")}
     for l in labels:
         rows, cols = np.nonzero(m == l)
         r0, r1, c0, c1 = rows.min(), rows.max() + 1, cols.min(), cols.max() + 1
@@ -57,4 +85,5 @@ def regionprops(inst_map):
         out["major_axis_length"].append(4 * np.sqrt(l1))
         out["minor_axis_length"].append(4 * np.sqrt(l2))
         out["orientation"].append(orient)
+        out["solidity"].append(area / _convex_area(img))
     return {k: np.array(v) for k, v in out.items()}

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pg_clustering": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
     "pg_type_interactions": (C.c_int, [vp, i32, vp, vp, i32, vp, vp]),
     "pg_raster_props": (C.c_int, [vp, i32, i32, vp, i32, C.POINTER(PgRasterOut), vp]),
+    "pg_raster_solidity": (C.c_int, [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
     "pg_instance_contours_count": (C.c_int, [vp, i32, i32, vp, i32, vp, vp, f64, vp, vp]),
     "pg_instance_contours_total": (C.c_int, [vp, C.POINTER(i64)]),
     "pg_instance_contours_fill": (C.c_int, [vp, i32, vp, vp, vp]),

@@ -143,6 +143,103 @@ raster_finish_kernel(const raster_acc* __restrict__ acc, int n_labels, pg_raster
   if (o.perimeter) o.perimeter[i] = per;
 }
 
+// ---- solidity = area / area of the convex hull image (skimage convex_hull_image: the hull of the pixels' diamond
+// corners (r +- 1/2, c), (r, c +- 1/2), rasterised including its border). One thread per instance, doubled integer
+// coordinates, everything exact: per doubled row the extent [lo, hi] of the diamond points, the hull's left / right
+// chains by a monotone-chain stack over the rows, then per pixel row the integer columns between the two chains.
+__global__ void __launch_bounds__(TPB)
+raster_rows_kernel(const int32_t* __restrict__ area, const int32_t* __restrict__ bbox, int n_labels, int32_t* __restrict__ need) {
+  const int l = blockIdx.x * TPB + threadIdx.x;
+  if (l >= n_labels) return;
+  need[l] = area[l] > 0 ? 4 * (2 * (bbox[4 * l + 2] - bbox[4 * l]) + 1) : 0;
+}
+
+__device__ __forceinline__ long long floor_div(long long a, long long b) {  // b > 0
+  long long q = a / b;
+  return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(TPB)
+raster_solidity_kernel(const int32_t* __restrict__ m, int h, int w, const int32_t* __restrict__ area,
+                       const int32_t* __restrict__ bbox, int n_labels, const int32_t* __restrict__ off,
+                       int32_t* __restrict__ scratch, int32_t* __restrict__ convex_area, double* __restrict__ solidity) {
+  const int l = blockIdx.x * TPB + threadIdx.x;
+  if (l >= n_labels) return;
+  const double nan_ = __longlong_as_double(0x7ff8000000000000ll);
+  if (area[l] <= 0) {
+    if (convex_area) convex_area[l] = 0;
+    if (solidity) solidity[l] = nan_;
+    return;
+  }
+  const int lab = l + 1;
+  const int r0 = bbox[4 * l], c0 = bbox[4 * l + 1], r1 = bbox[4 * l + 2], c1 = bbox[4 * l + 3];
+  const int nd = 2 * (r1 - r0) + 1;  // doubled rows 2 r0 - 1 .. 2 (r1 - 1) + 1, index j = R - (2 r0 - 1)
+  int32_t* lo = scratch + off[l];
+  int32_t* hi = lo + nd;
+  int32_t* sl = hi + nd;  // hull stacks (row indices)
+  int32_t* sr = sl + nd;
+  const int NONE_LO = 0x7fffffff, NONE_HI = -0x7fffffff;
+  for (int j = 0; j < nd; ++j) { lo[j] = NONE_LO; hi[j] = NONE_HI; }
+  for (int r = r0; r < r1; ++r) {
+    const int32_t* row = m + (int64_t)r * w;
+    int cmin = -1, cmax = -1;
+    for (int c = c0; c < c1; ++c)
+      if (row[c] == lab) { if (cmin < 0) cmin = c; cmax = c; }
+    if (cmin < 0) continue;
+    const int j = 2 * (r - r0);
+    lo[j] = min(lo[j], 2 * cmin); hi[j] = max(hi[j], 2 * cmax);
+    lo[j + 1] = min(lo[j + 1], 2 * cmin - 1); hi[j + 1] = max(hi[j + 1], 2 * cmax + 1);
+    lo[j + 2] = min(lo[j + 2], 2 * cmin); hi[j + 2] = max(hi[j + 2], 2 * cmax);
+  }
+  // monotone chains over the rows that hold points: left = lower convex envelope of (j, lo), right = upper of (j, hi)
+  int nl = 0, nr = 0;
+  for (int j = 0; j < nd; ++j) {
+    if (lo[j] == NONE_LO) continue;
+    while (nl >= 2) {
+      const long long ax = sl[nl - 2], bx = sl[nl - 1];
+      const long long cr = (bx - ax) * ((long long)lo[j] - lo[ax]) - ((long long)lo[bx] - lo[ax]) * (j - ax);
+      if (cr <= 0) --nl; else break;  // b on or above the chord a -> j: not a vertex of the lower envelope
+    }
+    sl[nl++] = j;
+    while (nr >= 2) {
+      const long long ax = sr[nr - 2], bx = sr[nr - 1];
+      const long long cr = (bx - ax) * ((long long)hi[j] - hi[ax]) - ((long long)hi[bx] - hi[ax]) * (j - ax);
+      if (cr >= 0) --nr; else break;
+    }
+    sr[nr++] = j;
+  }
+  // pixel rows: doubled row R = 2 r has index j = 2 (r - r0) + 1; count the columns c with L(j) <= 2 c <= U(j)
+  long long count = 0;
+  int il = 0, ir = 0;
+  const int j_first = sl[0], j_last = sl[nl - 1];
+  for (int r = r0; r < r1; ++r) {
+    const int j = 2 * (r - r0) + 1;
+    if (j < j_first || j > j_last) continue;
+    while (il + 1 < nl - 1 && sl[il + 1] <= j) ++il;
+    while (ir + 1 < nr - 1 && sr[ir + 1] <= j) ++ir;
+    long long c_lo, c_hi;
+    {
+      const long long a = sl[il], b = sl[min(il + 1, nl - 1)];
+      if (b == a) c_lo = -floor_div(-(long long)lo[a], 2);
+      else {
+        const long long den = b - a, num = (long long)lo[a] * den + ((long long)lo[b] - lo[a]) * (j - a);
+        c_lo = -floor_div(-num, 2 * den);  // ceil(num / (2 den))
+      }
+    }
+    {
+      const long long a = sr[ir], b = sr[min(ir + 1, nr - 1)];
+      if (b == a) c_hi = floor_div((long long)hi[a], 2);
+      else {
+        const long long den = b - a, num = (long long)hi[a] * den + ((long long)hi[b] - hi[a]) * (j - a);
+        c_hi = floor_div(num, 2 * den);
+      }
+    }
+    if (c_hi >= c_lo) count += c_hi - c_lo + 1;
+  }
+  if (convex_area) convex_area[l] = (int32_t)count;
+  if (solidity) solidity[l] = count > 0 ? (double)area[l] / (double)count : nan_;
+}
+
 }  // namespace
 
 extern "C" int pg_raster_props(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map, int32_t n_labels,
@@ -168,6 +265,35 @@ extern "C" int pg_raster_props(pg_handle* h, int32_t height, int32_t width, cons
     PG_LAUNCH(h, s, "raster_perimeter_kernel", raster_perimeter_kernel<<<blocks, TPB, 0, s>>>(inst_map, border, height, width, n_labels, acc));
   }
   PG_LAUNCH(h, s, "raster_finish_kernel", raster_finish_kernel<<<pg_div_up(n_labels, TPB), TPB, 0, s>>>(acc, n_labels, *out));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+extern "C" int pg_raster_solidity(pg_handle* h, int32_t height, int32_t width, const int32_t* inst_map, int32_t n_labels,
+                                  const int32_t* area, const int32_t* bbox, int32_t* convex_area, double* solidity,
+                                  pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, height >= 0 && width >= 0 && n_labels >= 0, "pg_raster_solidity: bad argument");
+  if (n_labels == 0) return PG_OK;
+  PG_REQUIRE(h, inst_map && area && bbox, "pg_raster_solidity: NULL argument");
+  int rc;
+  const size_t per = (((size_t)n_labels + 8) * sizeof(int32_t) + 15) & ~(size_t)15;
+  if ((rc = pg_reserve(h, h->row_count, 2 * per))) return rc;
+  int32_t* need = (int32_t*)h->row_count.p;
+  int32_t* off = (int32_t*)((char*)h->row_count.p + per);
+  int32_t* totals = (int32_t*)((char*)h->misc.p + PG_MISC_TOTALS);
+  const int blocks = pg_div_up(n_labels, TPB);
+  PG_LAUNCH(h, s, "raster_rows_kernel", raster_rows_kernel<<<blocks, TPB, 0, s>>>(area, bbox, n_labels, need));
+  PG_LAUNCH_CHECK(h);
+  if ((rc = pg_scan_i32(h, need, off, n_labels, s, totals + 3))) return rc;
+  PG_CUDA(h, cudaMemcpyAsync(&h->pinned[10], totals + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA(h, cudaStreamSynchronize(s));
+  if ((rc = pg_reserve(h, h->rank, ((size_t)h->pinned[10] + 16) * sizeof(int32_t)))) return rc;
+  PG_LAUNCH(h, s, "raster_solidity_kernel", raster_solidity_kernel<<<blocks, TPB, 0, s>>>(inst_map, height, width, area, bbox, n_labels, off,
+                                                                                             (int32_t*)h->rank.p, convex_area, solidity));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

@@ -404,7 +404,7 @@ class Engine:
         return {"nbr_count": nbr, "degree": degree, "stats": st, "hist": hist}
 
     # ---- K12 -----------------------------------------------------------------------------------
-    def raster_props(self, inst_map, n_labels):
+    def raster_props(self, inst_map, n_labels, solidity=False):
         """skimage-regionprops quantities of an int32 instance map [H,W] for labels 1..n_labels (pg_raster_props)."""
         hgt, wid = int(inst_map.shape[0]), int(inst_map.shape[1])
         n = int(n_labels)
@@ -418,6 +418,13 @@ class Engine:
             setattr(ro, name, self._p(res[name], torch.float64, name))
         self._check(self.lib.pg_raster_props(self._h, hgt, wid, self._p(inst_map, torch.int32, "inst_map"), n,
                                              C.byref(ro), self._stream()))
+        if solidity and n > 0:
+            res["convex_area"] = self._empty((n,), torch.int32)
+            res["solidity"] = self._empty((n,), torch.float64)
+            self._check(self.lib.pg_raster_solidity(
+                self._h, hgt, wid, self._p(inst_map, torch.int32, "inst_map"), n, self._p(res["area"], torch.int32, "area"),
+                self._p(res["bbox"], torch.int32, "bbox"), self._p(res["convex_area"], torch.int32, "convex_area"),
+                self._p(res["solidity"], torch.float64, "solidity"), self._stream()))
         return res
 
     # ---- K13 -----------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ Reference call sites: ``regionprops(inst_map)`` at aggregated_hovernet_run.py:17
 ``bounding_box = [x_min, y_min, x_max, y_max]``) and ``regionprops_table(inst_map, properties=...)`` at
 hovernet_tile_inference.ipynb:2415-2429 (cell 18).  One CUDA pass pair over the map (pg_raster_props) replaces
 skimage's per-region Python loop, and one thread per instance traces and simplifies its contour polygon
-(pg_instance_contours_*, :183-198).  ``solidity`` (convex hull) is not built and is left out rather than approximated.
+(pg_instance_contours_*, :183-198); ``solidity`` comes from an exact convex-hull rasterisation (pg_raster_solidity).
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ from .polygon_morphology import derived_columns, zscore_columns
 
 def raster_regionprops(inst_map, device=None) -> pd.DataFrame:
     """``regionprops_table`` columns for every label present (ascending, like skimage): ``label, area, perimeter,
-    eccentricity, major_axis_length, minor_axis_length, orientation, centroid-0, centroid-1, bbox-0 .. bbox-3``."""
+    eccentricity, major_axis_length, minor_axis_length, orientation, solidity, centroid-0, centroid-1, bbox-0 .. bbox-3``."""
     m = np.asarray(inst_map)
     if m.ndim == 3:  # aggregated_hovernet_run.py:165-166
         m = m[0]
@@ -28,13 +28,13 @@ def raster_regionprops(inst_map, device=None) -> pd.DataFrame:
     eng = get_engine(device)
     n_labels = int(m.max()) if m.size else 0
     cols = ["label", "area", "perimeter", "eccentricity", "major_axis_length", "minor_axis_length", "orientation",
-            "centroid-0", "centroid-1", "bbox-0", "bbox-1", "bbox-2", "bbox-3"]
+            "solidity", "centroid-0", "centroid-1", "bbox-0", "bbox-1", "bbox-2", "bbox-3"]
     if n_labels <= 0:
         return pd.DataFrame({c: np.zeros(0, dtype=np.int64 if c in ("label", "area") or c.startswith("bbox") else np.float64)
                              for c in cols})
     with torch.cuda.device(eng.device):
         d_m = _host.to_device(_host.as_int32(m, "inst_map"), np.int32, eng.device)
-        res = _host.to_host_many(eng.raster_props(d_m, n_labels))
+        res = _host.to_host_many(eng.raster_props(d_m, n_labels, solidity=True))
     keep = res["area"] > 0
     lab = np.nonzero(keep)[0] + 1
     df = pd.DataFrame({
@@ -45,6 +45,7 @@ def raster_regionprops(inst_map, device=None) -> pd.DataFrame:
         "major_axis_length": res["major_axis"][keep],
         "minor_axis_length": res["minor_axis"][keep],
         "orientation": res["orientation"][keep],
+        "solidity": res["solidity"][keep],
         "centroid-0": res["centroid"][keep, 0], "centroid-1": res["centroid"][keep, 1],
     })
     for c in range(4):
@@ -54,10 +55,10 @@ def raster_regionprops(inst_map, device=None) -> pd.DataFrame:
 
 def raster_morphology_table(inst_map, zscore: bool = False, device=None) -> pd.DataFrame:
     """``morph_df`` of cell 18 (ipynb:2415-2456) from the raster, as the reference computes it: ``inst_id, area,
-    perimeter, eccentricity, major_axis_length, minor_axis_length, orientation`` + the derived ``perimeter_area,
-    compactness, roundness, elongation`` (+ ``*_z`` of cell 21).  ``solidity`` is absent (see module docstring)."""
+    perimeter, eccentricity, solidity, major_axis_length, minor_axis_length, orientation`` + the derived
+    ``perimeter_area, compactness, roundness, elongation`` (+ ``*_z`` of cell 21)."""
     df = raster_regionprops(inst_map, device=device)
-    out = df[["label", "area", "perimeter", "eccentricity", "major_axis_length", "minor_axis_length", "orientation"]].rename(
+    out = df[["label", "area", "perimeter", "eccentricity", "solidity", "major_axis_length", "minor_axis_length", "orientation"]].rename(
         columns={"label": "inst_id"})
     out = derived_columns(out)
     return zscore_columns(out) if zscore else out

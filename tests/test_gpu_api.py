@@ -319,6 +319,7 @@ def test_raster_regionprops_against_restated_skimage(shape):
     np.testing.assert_allclose(got["perimeter"].to_numpy(), want["perimeter"], rtol=1e-13)
     for name in ("eccentricity", "major_axis_length", "minor_axis_length"):
         np.testing.assert_allclose(got[name].to_numpy(), want[name], rtol=1e-9, atol=1e-7, err_msg=name)
+    assert np.array_equal(got["solidity"].to_numpy(), want["solidity"])           # integer counts: exact
     # orientation is ill-defined for (near-)isotropic regions; compare where the tensor is anisotropic
     aniso = want["eccentricity"] > 1e-3
     np.testing.assert_allclose(got["orientation"].to_numpy()[aniso], want["orientation"][aniso], rtol=1e-7, atol=1e-9)
@@ -329,7 +330,7 @@ def test_raster_regionprops_against_restated_skimage(shape):
     r0, c0, r1, c1 = want["bbox"][0]
     assert boxes[l0] == [c0, r0, c1, r1]                        # [x_min, y_min, x_max, y_max], aggregated_hovernet_run.py:179-180
     morph = raster_morphology_table(m, zscore=True)
-    assert {"inst_id", "perimeter_area", "compactness", "roundness", "elongation", "area_z"} <= set(morph.columns)
+    assert {"inst_id", "solidity", "perimeter_area", "compactness", "roundness", "elongation", "area_z", "solidity_z"} <= set(morph.columns)
     a, p_ = want["area"], want["perimeter"]
     np.testing.assert_allclose(morph["compactness"].to_numpy(), 4 * np.pi * a / np.clip(p_, 1, None) ** 2, rtol=1e-12)
     stacked = raster_regionprops(m[None])                        # (1, H, W) maps are squeezed like the reference does

@@ -216,6 +216,11 @@ def test_raster_oracle_on_analytic_shapes():
     assert abs(p["orientation"][1]) == np.pi / 2                                        # long axis along the columns
     assert abs(p["perimeter"][2] / (2 * np.pi * 12) - 1) < 0.05 and p["eccentricity"][2] < 0.05
     assert abs(p["area"][2] / (np.pi * 144) - 1) < 0.03
+    assert p["solidity"][0] == 1.0 and p["solidity"][1] == 1.0 and 0.93 < p["solidity"][2] <= 1.0   # convex shapes
+    ell = np.zeros((9, 9), dtype=np.int32)
+    ell[1:8, 1:3] = 1
+    ell[6:8, 1:8] = 1                                   # an L: 7x2 + 2x5 = 24 pixels; its hull image has 2+3+4+5+6+7+7 = 34
+    assert oraster.regionprops(ell)["solidity"][0] == 24 / 34
 
 
 def test_contour_oracle_cycle_rule_equals_literal_assembly():
