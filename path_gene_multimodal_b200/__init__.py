@@ -13,7 +13,8 @@ Public surface (reference-style module-level functions; see DESIGN.md / INTEGRAT
     add_wsi_coords_to_table, process_nuclei_file          (nuclei_io: Parquet / CSV <-> SoA / CSR)
     node_feature_matrix, assemble_graph_data, to_pyg      (graph_features: z-scores + one-hot -> x, PyG Data)
     raster_regionprops, raster_morphology_table,
-    instance_bounding_boxes, instance_polygons            (raster_props: skimage regionprops / contour polygons of an inst_map)
+    instance_bounding_boxes, instance_polygons,
+    tile_nuclei_table                                     (raster_props: skimage regionprops / contour polygons of an inst_map)
 Everything computes in libpathgraph.so (csrc/, C ABI in include/pathgraph.h); no CPU fallback.
 """
 __version__ = "0.1.0"
@@ -32,7 +33,7 @@ _EXPORTS = {
     "node_feature_matrix": "graph_features", "assemble_graph_data": "graph_features", "to_pyg": "graph_features",
     "raster_regionprops": "raster_props", "raster_morphology_table": "raster_props",
     "instance_bounding_boxes": "raster_props", "instance_polygons": "raster_props",
-    "instance_polygons_csr": "raster_props",
+    "instance_polygons_csr": "raster_props", "tile_nuclei_table": "raster_props",
     "Engine": "engine", "get_engine": "engine",
 }
 

@@ -106,3 +106,36 @@ def instance_polygons(inst_map, tolerance: float = 0.5, device=None) -> dict:
     labels, off, xy = instance_polygons_csr(inst_map, tolerance, device)
     rings = csr_to_polygons(off, xy)
     return {int(l): rings[i] for i, l in enumerate(labels)}
+
+
+# PanNuke type ids of the HoverNeXt checkpoint the reference uses (aggregated_hovernet_run.py:76-82)
+TYPE_NAMES = {1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}
+
+
+def tile_nuclei_table(class_info: dict, inst_map, png_path, type_names: dict = TYPE_NAMES, device=None) -> pd.DataFrame:
+    """Steps 1 and 3-5 of ``run_hovernet_on_tile`` (aggregated_hovernet_run.py:135-223) from HoverNeXt's two outputs:
+    ``class_info`` (class_inst.json: ``{inst_id: [type, [0, cx, cy]]}``) and the instance map (pinst_pp).
+
+    Returns the reference's ``final_df``: ``nuc_id, inst_id, type, type_name, bounding_box, centroid, polygon,
+    tile_name, tile_path``; ``bounding_box`` / ``polygon`` are ``None`` for an id that is not in the map (``dict.get``
+    semantics of :200-201). The per-instance masking loop becomes two CUDA passes (K12 + K13)."""
+    import uuid
+    from pathlib import Path
+
+    rows = []
+    for key, val in class_info.items():                       # :140-157
+        _, cx, cy = val[1]
+        rows.append({"inst_id": int(key), "type": int(val[0]), "centroid": [float(cx), float(cy)]})
+    if not rows:
+        return pd.DataFrame()
+    df = pd.DataFrame(rows)
+    bbox_dict = instance_bounding_boxes(inst_map, device=device)
+    poly_dict = instance_polygons(inst_map, device=device)
+    df["bounding_box"] = df["inst_id"].map(bbox_dict.get)     # :200-201
+    df["polygon"] = df["inst_id"].map(poly_dict.get)
+    df["type_name"] = df["type"].map(type_names)              # :204-205
+    df["nuc_id"] = df["inst_id"].apply(lambda _: uuid.uuid4().hex)
+    png_path = Path(png_path)
+    df["tile_name"] = png_path.stem                            # :208-209
+    df["tile_path"] = str(png_path)
+    return df[["nuc_id", "inst_id", "type", "type_name", "bounding_box", "centroid", "polygon", "tile_name", "tile_path"]]

@@ -376,3 +376,34 @@ def test_instance_polygons_against_restated_skimage(shape, n):
 def _touches_border(m, lab):
     rr, cc = np.nonzero(m == lab)
     return rr.min() == 0 or cc.min() == 0 or rr.max() == m.shape[0] - 1 or cc.max() == m.shape[1] - 1
+
+
+def test_tile_nuclei_table_feeds_the_wsi_map():
+    # run_hovernet_on_tile's table (aggregated_hovernet_run.py:135-223) from an instance map, then straight into the
+    # a1-a3 drop-in: the two halves of the script path meet
+    from oracle import contours as ocont
+    from oracle import raster as oraster
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei, tile_nuclei_table
+
+    m = _blob_map(96, 80, n=14, seed=2)
+    props = oraster.regionprops(m)
+    labels = [int(l) for l in props["label"]]
+    info = {str(l): [1 + l % 5, [0, float(c[1]), float(c[0])]] for l, c in zip(labels, props["centroid"])}
+    info["9999"] = [2, [0, 1.0, 1.0]]                                       # listed by the classifier, absent from the map
+    df = tile_nuclei_table(info, m, "/data/out/patches/1016_508.png")
+    assert list(df.columns) == ["nuc_id", "inst_id", "type", "type_name", "bounding_box", "centroid", "polygon", "tile_name", "tile_path"]
+    polys = ocont.instance_polygons(m)
+    for _, row in df.iterrows():
+        l = row["inst_id"]
+        if l == 9999:
+            assert row["bounding_box"] is None and row["polygon"] is None
+            continue
+        r0, c0, r1, c1 = props["bbox"][labels.index(l)]
+        assert row["bounding_box"] == [c0, r0, c1, r1] and row["polygon"] == polys[l]
+        assert row["type_name"] in ("neoplastic", "inflammatory", "connective", "dead", "epithelial")
+    assert df["tile_name"].iloc[0] == "1016_508" and df["nuc_id"].nunique() == len(df)
+    tiles = pd.DataFrame({"png_path": ["/data/out/patches/1016_508.png"], "x": [1016], "y": [508]})
+    wsi = add_wsi_coords_to_nuclei(df[df["inst_id"] != 9999], tiles)
+    first = wsi.iloc[0]
+    assert first["wsi_polygon"][0] == [first["polygon"][0][0] + 1016.0, first["polygon"][0][1] + 508.0]
+    assert first["wsi_bbox_xmin"] == first["bounding_box"][0] + 1016
