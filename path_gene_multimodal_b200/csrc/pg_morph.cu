@@ -333,6 +333,8 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   // rings (mean from pg_map_morph_hint - the Python layer knows M) get 32 rings of the mean length + 40 % spread
   int slab_verts = SLAB_VERTS_MIN;
   if (h->morph_mean_verts > 33.0) slab_verts = (int)std::ceil(46.0 * h->morph_mean_verts) + 2;
+  else if (h->morph_mean_verts > 0.0 && h->morph_mean_verts <= 23.0)  // short rings: smaller slabs, one more CTA per SM
+    slab_verts = std::max(512, (int)std::ceil(46.0 * h->morph_mean_verts) + 2);
   slab_verts = std::min(slab_verts, (int)(SLAB_BYTES_MAX / (WARPS * sizeof(V2))));
   slab_verts &= ~1;  // whole 16-byte units per warp
   const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
