@@ -6,7 +6,9 @@
 Every slide (PG_SLIDE_N nuclei, seed 1004 + slide index, ragged float32 rings) goes through the whole nuclei-table
 pass from HOST arrays (page-locked): H2D of the table, tile->WSI map + morphology, kNN k=8 + undirected union + i<j edges +
 composition, radius r=50 px graph with composition / degree statistics, D2H of per-slide summaries only (the
-graphs stay on the GPU that built them, as each LSF job of the reference keeps its own slide). Rank 0 prints one
+graphs stay on the GPU that built them, as each LSF job of the reference keeps its own slide). PG_LANES slides
+(default 2) are in flight per GPU, each on its own stream / handle / host thread, so one slide's H2D overlaps the
+other's kernels. Rank 0 prints one
 line with the max-over-ranks wall time and a checksum that must not depend on the number of GPUs."""
 import os
 import sys
@@ -18,7 +20,7 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from path_gene_multimodal_b200 import _host, sharding, synth  # noqa: E402
-from path_gene_multimodal_b200.engine import default_knn_cell, get_engine, radius_cell  # noqa: E402
+from path_gene_multimodal_b200.engine import Engine, default_knn_cell, get_engine, radius_cell  # noqa: E402
 
 
 def main():
@@ -33,7 +35,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_slides = int(os.environ.get("PG_SLIDES", 64))
     n = int(os.environ.get("PG_SLIDE_N", 500_000))
-    eng = get_engine(local)
+    lanes = int(os.environ.get("PG_LANES", 2))   # slides in flight per GPU: one engine (handle) + stream + host thread each
+    engines = [get_engine(local)] + [Engine(local) for _ in range(lanes - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
     mine = sharding.assign_slides(n_slides, world, sizes=[n] * n_slides)[rank]
     # host tables in page-locked memory, as a loader that reads Parquet straight into pinned buffers would leave
     # them (generation and pinning untimed); _host.to_device then DMAs from them without a staging copy
@@ -49,7 +53,7 @@ def main():
             setattr(tab, name, pin(getattr(tab, name)))
         tables[s] = tab
 
-    def one_slide(s):
+    def one_slide(s, eng):
         tab = tables[s]
         side_px = float(tab.n_tiles_side * 508)
         t_off = _host.to_device(tab.poly_off, np.int32, dev)
@@ -72,13 +76,44 @@ def main():
                 "area_sum": float(mm["area"].double().sum().item()), "knn_deg_sum": int(comp["degree"].sum().item()),
                 "radius_mean_degree": st["mean"], "nbr_sum": int(rg["nbr_count"].sum().item())}
 
-    one_slide(mine[0])                                                            # warm-up (allocations, first launches)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def lane_worker(lane, slides):
+        # one host thread per lane: its slides run on its own stream and handle, so the H2D of one slide overlaps
+        # the kernels (and the host reads of totals) of the other
+        torch.cuda.set_device(local)
+        out = {}
+        with torch.cuda.stream(streams[lane]):
+            for s in slides:
+                out[s] = one_slide(s, engines[lane])
+        streams[lane].synchronize()
+        return out
+
+    def run_mine():
+        with ThreadPoolExecutor(max_workers=lanes) as ex:
+            parts = list(ex.map(lane_worker, range(lanes), [mine[i::lanes] for i in range(lanes)]))
+        merged = {}
+        for d in parts:
+            merged.update(d)
+        return merged
+
+    for lane in range(lanes):                                                     # warm-up (allocations, first launches)
+        with torch.cuda.stream(streams[lane]):
+            one_slide(mine[0], engines[lane])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = sharding.slide_parallel(n_slides, one_slide, rank, world, sizes=[n] * n_slides)
+    local_res = run_mine()
     torch.cuda.synchronize()
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local_res)
+        res = {}
+        for d in gathered:
+            res.update(d)
+    else:
+        res = local_res
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
