@@ -15,9 +15,10 @@ def to_device(arr, dtype: np.dtype, device: torch.device, name: str = "array") -
     a = np.ascontiguousarray(arr, dtype=dtype)
     if a.size == 0:
         return torch.empty(a.shape, dtype=_torch_dtype(dtype), device=device)
-    t = torch.from_numpy(a)
-    if t.is_pinned():  # caller already staged it (e.g. pinned_empty): DMA straight from it
-        return t.to(device, non_blocking=True)
+    if a.flags.writeable:  # (a read-only view cannot be page-locked memory of ours; torch would also warn about it)
+        t = torch.from_numpy(a)
+        if t.is_pinned():  # caller already staged it (e.g. pinned_empty): DMA straight from it
+            return t.to(device, non_blocking=True)
     pinned = torch.empty(a.shape, dtype=_torch_dtype(dtype), pin_memory=True)  # torch caches pinned blocks
     pinned.numpy()[...] = a
     return pinned.to(device, non_blocking=True)
