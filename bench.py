@@ -249,6 +249,7 @@ def kernel_bytes(name, n, e_und, cells):
         "scatter_kernel": 16 * n + 4 * n + 4 * cells + 32 * n,        # xy, type, cursors in; 32-byte records out
         "radius_walk_kernel": 32 * n + 4 * cells + 32 * n + 16 * e_und,  # records, cell starts in; per-point meta + parked entries out
         "radius_rows_kernel": 32 * n + 4 * n + 4 * n + 4 * N_TYPES * n + 4 * n,  # meta in; row_ptr, degree, nbr_count, row_off out
+        "radius_rows_gather_kernel": 32 * n + 4 * n + 4 * n + 4 * N_TYPES * n + 16 * e_und + 24 * e_und,  # meta, entries in; row_ptr, degree, nbr_count, col, dist32, edges out
         "radius_gather_kernel": 8 * n + 16 * e_und + 4 * e_und + 4 * e_und + 16 * e_und,  # row_ptr, row_off, entries in; col, dist32, edges out
     }
     return table.get(name)

@@ -152,6 +152,16 @@ int pg_radius_total(pg_handle* h, int64_t* total);
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
                    int64_t* edges_i64, int64_t* edge_index, float* edge_attr, int64_t n_edges,
                    int64_t capacity, pg_stream stream);
+
+/* The same graph in ONE call when the caller provides the outputs up front (capacity in entries): the fill pass
+ * runs inside the row pass of the count (each CTA gathers the rows it has just scanned), so row offsets never
+ * travel through memory and one launch disappears. Rows that do not fit `capacity` are dropped and reported by
+ * pg_check_overflow; the valid prefix of col / dist / edges is row_ptr[n_query]. edge_index / edge_attr need the
+ * exact total and stay with pg_radius_count + pg_radius_total + pg_radius_fill. */
+int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree,
+                    int32_t* nbr_count, int32_t n_types, pg_degree_stats* stats, int32_t* hist,
+                    int32_t hist_len, int32_t* col, float* dist32, double* dist64, int64_t* edges_i64,
+                    int64_t capacity, pg_stream stream);
 /* synchronises; PG_ERR_CAPACITY if any fill since the last check overflowed its buffers */
 int pg_check_overflow(pg_handle* h);
 

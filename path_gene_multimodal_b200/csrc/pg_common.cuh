@@ -52,6 +52,9 @@ struct pg_handle {
     bool valid = false;
     double r = 0; int32_t flags = 0; int32_t* row_ptr = nullptr; int32_t* degree = nullptr; int32_t* nbr_count = nullptr;
     int32_t n_types = 0; pg_degree_stats* stats = nullptr; int32_t* hist = nullptr; int32_t hist_len = 0;
+    // pg_radius_graph: the fill pass fused into the row pass (outputs known at count time)
+    bool fused = false; int32_t* col = nullptr; float* dist32 = nullptr; double* dist64 = nullptr; int64_t* edges = nullptr;
+    int64_t capacity = 0;
   } last_count;
   pg_buf knn_retry;    // int32 [N]     cell-order positions of the points the kNN block pass could not finish
   pg_buf row_count;    // int32 [N+1]   per-row counts before the scan (K7)

@@ -255,6 +255,63 @@ radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
   st_meta(o.meta + me.row, m);  // in ROW order: a scattered full-sector store here buys the row pass coalesced loads
 }
 
+struct fill_out {
+  int32_t* __restrict__ col;
+  float* __restrict__ dist32;
+  double* __restrict__ dist64;
+  long long* __restrict__ edges;
+  long long* __restrict__ edge_index;
+  float* __restrict__ edge_attr;
+  long long n_edges;
+};
+
+__device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int my_id, int key, double d2) {
+  const double d = sqrt(d2);
+  o.col[pos] = key;
+  if (o.dist32) o.dist32[pos] = (float)d;
+  if (o.dist64) o.dist64[pos] = d;
+  if (o.edges) *reinterpret_cast<longlong2*>(o.edges + 2 * pos) = make_longlong2(my_id, key);
+  if (o.edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
+    o.edge_index[pos] = my_id; o.edge_index[o.n_edges + pos] = key;
+    o.edge_index[2 * o.n_edges + pos] = key; o.edge_index[3 * o.n_edges + pos] = my_id;
+  }
+  if (o.edge_attr) { o.edge_attr[pos] = (float)d; o.edge_attr[o.n_edges + pos] = (float)d; }  // ipynb:3041-3042
+}
+
+// The gather of 32 consecutive rows by one warp = one contiguous range [rp(lane 0), end) of the outputs, one lane
+// per output entry. rp / off / id / my_cnt: the values of the lane's row.
+__device__ __forceinline__ void gather_rows32(int rp, int end, int off, int id, int my_cnt, const pg_tmp_ent* tmp,
+                                              const fill_out& o, long long capacity, int32_t* overflow) {
+  const int lane = threadIdx.x & 31;
+  const int begin = __shfl_sync(0xffffffffu, rp, 0);
+  for (int p0 = begin; p0 < end; p0 += 32) {
+    const int p = p0 + lane;
+    int k = 0;  // the last row of the 32 that starts at or before p (empty rows share their start with the next row)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, rp, k + step);
+      if (v <= p) k += step;
+    }
+    const int roff = __shfl_sync(0xffffffffu, off, k);
+    const int rcnt = __shfl_sync(0xffffffffu, my_cnt, k);
+    const int rbase = __shfl_sync(0xffffffffu, rp, k);
+    const int rid = __shfl_sync(0xffffffffu, id, k);
+    if (p >= end) continue;
+    if ((long long)rbase + rcnt > capacity || roff < 0) {
+      atomicExch(overflow, 1);  // the row does not fit the caller's buffers (or never got parked): dropped, reported
+      continue;
+    }
+    const pg_tmp_ent* src = tmp + roff;
+    const pg_tmp_ent e = src[p - rbase];
+    int rank = 0;  // ids are distinct, so the place of an entry in its row is the number of smaller ids
+    for (int u = 0; u < rcnt; u += 4) {
+      const int i0 = src[u].id, i1 = src[min(u + 1, rcnt - 1)].id, i2 = src[min(u + 2, rcnt - 1)].id, i3 = src[min(u + 3, rcnt - 1)].id;
+      rank += (i0 < e.id) + (u + 1 < rcnt && i1 < e.id) + (u + 2 < rcnt && i2 < e.id) + (u + 3 < rcnt && i3 < e.id);
+    }
+    emit_entry(o, (long long)rbase + rank, rid, e.id, e.d2);
+  }
+}
+
 struct rows_out {
   int32_t* __restrict__ row_ptr;
   int32_t* __restrict__ degree;
@@ -275,10 +332,21 @@ struct rows_out {
 // (tile = blockIdx.x: CTAs are dispatched in index order, so a tile only waits on tiles that are running or done).
 // The statistics are reduced between publishing the tile's aggregate and reading the predecessors', i.e. inside
 // the look-back wait.
+struct rows_gather {  // GATHER: the fill pass for the tile's own rows, fused in (outputs given at count time)
+  const pg_tmp_ent* tmp;
+  const int32_t* row_gid;
+  fill_out fo;
+  long long capacity;
+  int32_t* overflow;
+};
+
+template <bool GATHER>
 __global__ void __launch_bounds__(TPB_ROWS)
-radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_out o) {
+radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_out o, rows_gather gx) {
   using TS = pg_tile_scan<TPB_ROWS>;
   __shared__ typename TS::smem_t sm;
+  __shared__ int s_rp[GATHER ? ROWS_TILE + 1 : 1];
+  __shared__ int s_off[GATHER ? ROWS_TILE : 1];
   __shared__ int s_hist[PG_ACC_HIST_MAX];
   __shared__ int s_mn, s_mx, s_last;
   __shared__ unsigned long long s_sum, s_sq;
@@ -307,7 +375,7 @@ radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_o
 
   // ---- everything that does not need the tile's prefix: row_off, degree, type counts, statistics
   if (full) {
-    *reinterpret_cast<int4*>(o.row_off + row0) = make_int4(m[0].off, m[1].off, m[2].off, m[3].off);
+    if (!GATHER) *reinterpret_cast<int4*>(o.row_off + row0) = make_int4(m[0].off, m[1].off, m[2].off, m[3].off);
     if (o.degree) *reinterpret_cast<int4*>(o.degree + row0) = make_int4(m[0].deg, m[1].deg, m[2].deg, m[3].deg);
     if (o.nbr_count) {
       if (o.n_types == PG_PACKED_TYPES) {  // 4 rows x 5 counts = 80 contiguous, 16-byte aligned bytes
@@ -330,7 +398,7 @@ radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_o
     for (int i = 0; i < ROWS_ITEMS; ++i) {
       const int row = row0 + i;
       if (row < n_query) {
-        o.row_off[row] = m[i].off;
+        if (!GATHER) o.row_off[row] = m[i].off;
         if (o.degree) o.degree[row] = m[i].deg;
         if (o.nbr_count)
 #pragma unroll
@@ -387,6 +455,24 @@ radius_rows_kernel(int n_query, const pg_pt_meta* meta, pg_scan_state st, rows_o
       if (row0 + i < n_query) o.row_ptr[row0 + i] = v[i] + base;
   }
 
+  if (GATHER) {
+    // ---- the tile's rows are complete: gather their parked entries now (the warp-per-32-rows gather of the fill pass)
+#pragma unroll
+    for (int i = 0; i < ROWS_ITEMS; ++i) { s_rp[tid * ROWS_ITEMS + i] = v[i] + base; s_off[tid * ROWS_ITEMS + i] = m[i].off; }
+    if (tid == TPB_ROWS - 1) s_rp[ROWS_TILE] = (base - thread_off) + tile_sum;  // tile prefix + tile total
+    __syncthreads();
+    const int lane = tid & 31;
+    for (int g = tid >> 5; g < ROWS_TILE / 32; g += TPB_ROWS / 32) {
+      const int r0 = tile * ROWS_TILE + g * 32;
+      if (r0 >= n_query) break;  // warp-uniform
+      const int row = r0 + lane;
+      const bool has_row = row < n_query;
+      const int rp = s_rp[g * 32 + lane], rp1 = s_rp[g * 32 + lane + 1], end = s_rp[g * 32 + 32];
+      gather_rows32(rp, end, has_row ? s_off[g * 32 + lane] : -1, has_row ? (gx.row_gid ? gx.row_gid[row] : row) : 0,
+                    rp1 - rp, gx.tmp, gx.fo, gx.capacity, gx.overflow);
+    }
+  }
+
   // ---- CTA -> accumulators; the last CTA to get here publishes them and re-arms the accumulators
   if (want_stats) {
     if (tid == 0) {
@@ -433,30 +519,7 @@ __global__ void empty_graph_kernel(int32_t* row_ptr, int32_t* total_copy, pg_deg
     for (int i = threadIdx.x; i < hist_len; i += blockDim.x) hist[i] = 0;
 }
 
-struct fill_out {
-  int32_t* __restrict__ col;
-  float* __restrict__ dist32;
-  double* __restrict__ dist64;
-  long long* __restrict__ edges;
-  long long* __restrict__ edge_index;
-  float* __restrict__ edge_attr;
-  long long n_edges;
-};
-
-__device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int my_id, int key, double d2) {
-  const double d = sqrt(d2);
-  o.col[pos] = key;
-  if (o.dist32) o.dist32[pos] = (float)d;
-  if (o.dist64) o.dist64[pos] = d;
-  if (o.edges) *reinterpret_cast<longlong2*>(o.edges + 2 * pos) = make_longlong2(my_id, key);
-  if (o.edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
-    o.edge_index[pos] = my_id; o.edge_index[o.n_edges + pos] = key;
-    o.edge_index[2 * o.n_edges + pos] = key; o.edge_index[3 * o.n_edges + pos] = my_id;
-  }
-  if (o.edge_attr) { o.edge_attr[pos] = (float)d; o.edge_attr[o.n_edges + pos] = (float)d; }  // ipynb:3041-3042
-}
-
-// The gather: one warp per 32 consecutive rows = one contiguous range of the outputs, one lane per output entry.
+// The stand-alone gather (pg_radius_fill): one warp per 32 consecutive rows.
 __global__ void __launch_bounds__(TPB_GATHER)
 radius_gather_kernel(int n_query, const int32_t* row_ptr, const int32_t* row_off,
                      const pg_tmp_ent* tmp, const int32_t* row_gid,
@@ -471,36 +534,9 @@ radius_gather_kernel(int n_query, const int32_t* row_ptr, const int32_t* row_off
   const int rp = row_ptr[min(row, n_query)];
   const int off = has_row ? row_off[row] : -1;
   const int id = has_row ? (row_gid ? row_gid[row] : row) : 0;
-  const int begin = __shfl_sync(0xffffffffu, rp, 0);
   const int end = row_ptr[min(r0 + 32, n_query)];
   const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
-  const int my_cnt = (lane == 31 ? end : rp_next) - rp;
-  for (int p0 = begin; p0 < end; p0 += 32) {
-    const int p = p0 + lane;
-    int k = 0;  // the last row of the 32 that starts at or before p (empty rows share their start with the next row)
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int v = __shfl_sync(0xffffffffu, rp, k + step);
-      if (v <= p) k += step;
-    }
-    const int roff = __shfl_sync(0xffffffffu, off, k);
-    const int rcnt = __shfl_sync(0xffffffffu, my_cnt, k);
-    const int rbase = __shfl_sync(0xffffffffu, rp, k);
-    const int rid = __shfl_sync(0xffffffffu, id, k);
-    if (p >= end) continue;
-    if ((long long)rbase + rcnt > capacity || roff < 0) {
-      atomicExch(overflow, 1);  // the row does not fit the caller's buffers (or never got parked): dropped, reported
-      continue;
-    }
-    const pg_tmp_ent* src = tmp + roff;
-    const pg_tmp_ent e = src[p - rbase];
-    int rank = 0;  // ids are distinct, so the place of an entry in its row is the number of smaller ids
-    for (int u = 0; u < rcnt; u += 4) {
-      const int i0 = src[u].id, i1 = src[min(u + 1, rcnt - 1)].id, i2 = src[min(u + 2, rcnt - 1)].id, i3 = src[min(u + 3, rcnt - 1)].id;
-      rank += (i0 < e.id) + (u + 1 < rcnt && i1 < e.id) + (u + 2 < rcnt && i2 < e.id) + (u + 3 < rcnt && i3 < e.id);
-    }
-    emit_entry(o, (long long)rbase + rank, rid, e.id, e.d2);
-  }
+  gather_rows32(rp, end, off, id, (lane == 31 ? end : rp_next) - rp, tmp, o, capacity, overflow);
 }
 
 static inline int ring_radius(double r, const pg_grid& gr) {
@@ -584,7 +620,17 @@ int launch_count_pass(pg_handle* h, cudaStream_t s) {
   pg_scan_state st;
   int rc = pg_scan_prepare(h, tiles, TPB_ROWS, s, &st);
   if (rc) return rc;
-  PG_LAUNCH(h, s, "radius_rows_kernel", pg_launch_pdl(4, radius_rows_kernel, tiles, TPB_ROWS, s, nq, (const pg_pt_meta*)h->pt_meta.p, st, o));
+  rows_gather gx{};
+  if (a.fused) {
+    gx.tmp = (const pg_tmp_ent*)h->tmp_ent.p;
+    gx.row_gid = gr.has_gid ? (const int32_t*)h->s_gid.p : nullptr;
+    gx.fo = fill_out{a.col, a.dist32, a.dist64, (long long*)a.edges, nullptr, nullptr, 0};
+    gx.capacity = (long long)a.capacity;
+    gx.overflow = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
+    PG_LAUNCH(h, s, "radius_rows_gather_kernel", pg_launch_pdl(4, radius_rows_kernel<true>, tiles, TPB_ROWS, s, nq, (const pg_pt_meta*)h->pt_meta.p, st, o, gx));
+  } else {
+    PG_LAUNCH(h, s, "radius_rows_kernel", pg_launch_pdl(4, radius_rows_kernel<false>, tiles, TPB_ROWS, s, nq, (const pg_pt_meta*)h->pt_meta.p, st, o, gx));
+  }
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
@@ -625,6 +671,41 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   auto& a = h->last_count;
   a.r = r; a.flags = flags; a.row_ptr = row_ptr; a.degree = degree; a.nbr_count = nbr_count; a.n_types = n_types;
   a.stats = stats; a.hist = hist; a.hist_len = hist_len;
+  a.fused = false;
+  if ((rc = size_tmp(h))) return rc;
+  if ((rc = launch_count_pass(h, s))) return rc;
+  a.valid = true;
+  return PG_OK;
+}
+
+int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree, int32_t* nbr_count,
+                    int32_t n_types, pg_degree_stats* stats, int32_t* hist, int32_t hist_len, int32_t* col,
+                    float* dist32, double* dist64, int64_t* edges_i64, int64_t capacity, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  h->last_count.valid = false;
+  if (!h->grid.built) return pg_set_error(h, PG_ERR_STATE, "pg_radius_graph: call pg_grid_build first");
+  PG_REQUIRE(h, r >= 0 && std::isfinite(r), "pg_radius_graph: r must be finite and >= 0");
+  PG_REQUIRE(h, row_ptr != nullptr, "pg_radius_graph: row_ptr is NULL");
+  PG_REQUIRE(h, flags == PG_RADIUS_SYMMETRIC || flags == PG_RADIUS_UPPER, "pg_radius_graph: bad flags %d", flags);
+  PG_REQUIRE(h, !nbr_count || (n_types >= 1 && n_types <= PG_MAX_TYPES), "pg_radius_graph: n_types must be in 1..%d", PG_MAX_TYPES);
+  PG_REQUIRE(h, !hist || hist_len >= 1, "pg_radius_graph: hist_len must be >= 1");
+  PG_REQUIRE(h, capacity >= 0 && (capacity == 0 || col != nullptr), "pg_radius_graph: capacity < 0 or col is NULL");
+  PG_REQUIRE(h, (((uintptr_t)row_ptr | (uintptr_t)degree | (uintptr_t)nbr_count | (uintptr_t)edges_i64) & 15) == 0,
+             "pg_radius_graph: row_ptr / degree / nbr_count / edges must be 16-byte aligned");
+  const pg_grid& gr = h->grid;
+  int rc;
+  if ((rc = pg_reserve(h, h->pt_meta, ((size_t)gr.n + 1) * sizeof(pg_pt_meta)))) return rc;
+  if ((rc = pg_reserve(h, h->row_off, ((size_t)gr.n_query + 8) * sizeof(int32_t)))) return rc;
+  if (capacity > h->tmp_ovf_hint) h->tmp_ovf_hint = capacity;  // as pg_radius_reserve
+  h->radius_r = r;
+  h->radius_flags = flags;
+  auto& a = h->last_count;
+  a.r = r; a.flags = flags; a.row_ptr = row_ptr; a.degree = degree; a.nbr_count = nbr_count; a.n_types = n_types;
+  a.stats = stats; a.hist = hist; a.hist_len = hist_len;
+  a.fused = true; a.col = col; a.dist32 = dist32; a.dist64 = dist64; a.edges = edges_i64; a.capacity = capacity;
   if ((rc = size_tmp(h))) return rc;
   if ((rc = launch_count_pass(h, s))) return rc;
   a.valid = true;

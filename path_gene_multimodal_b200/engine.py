@@ -249,6 +249,21 @@ class Engine:
         nbr = get("nbr_count", (nq, n_types), torch.int32) if compose else None
         st = get("stats", (4,), torch.int64) if stats else None
         hist = get("hist", (hist_len,), torch.int32) if (stats and hist_len) else None
+        if capacity is not None and not want_edge_index:
+            # outputs known up front: one call, the fill pass fused into the row pass (pg_radius_graph)
+            cap = int(capacity)
+            col = get("col", (cap,), torch.int32)
+            d32 = get("dist32", (cap,), torch.float32) if want_dist32 else None
+            d64 = get("dist64", (cap,), torch.float64) if want_dist64 else None
+            edges = get("edges", (cap, 2), torch.int64) if want_edges else None
+            self._check(self.lib.pg_radius_graph(
+                self._h, float(r), 1 if upper else 0, self._p(row_ptr, torch.int32, "row_ptr"),
+                self._p(degree, torch.int32, "degree"), self._p(nbr, torch.int32, "nbr_count"), int(n_types),
+                self._p(st, torch.int64, "stats"), self._p(hist, torch.int32, "hist"),
+                int(hist_len) if hist is not None else 0, self._p(col, torch.int32, "col"),
+                self._p(d32, torch.float32, "dist32"), self._p(d64, torch.float64, "dist64"),
+                self._p(edges, torch.int64, "edges"), cap, self._stream()))
+            return res
         if capacity is not None:
             self._check(self.lib.pg_radius_reserve(self._h, int(capacity)))
         self._check(self.lib.pg_radius_count(self._h, float(r), 1 if upper else 0,

@@ -306,6 +306,28 @@ def test_radius_capacity_overflow(engine):
     engine.check_overflow()  # flag is cleared by the check
 
 
+@pytest.mark.parametrize("upper", [True, False])
+def test_radius_single_call_equals_count_fill(engine, upper):
+    # pg_radius_graph (outputs given up front: the fill fused into the row pass) against count -> total -> fill
+    from path_gene_multimodal_b200.engine import radius_cell
+
+    for n, seed, r, with_gid in ((70_000, 31, 50.0, False), (3_000, 32, 200.0, True), (1, 33, 5.0, False), (0, 34, 5.0, False)):
+        xy, types, _ = synth.make_points(max(n, 1), seed)
+        xy, types = xy[:n], types[:n]
+        gid = dev(np.random.default_rng(seed).permutation(n).astype(np.int32) + 7) if with_gid else None
+        engine.grid_build(dev(xy) if n else torch.empty((0, 2), dtype=torch.float64, device="cuda"),
+                          dev(types) if n else torch.empty((0,), dtype=torch.int32, device="cuda"), gid, radius_cell(r), None)
+        a = engine.radius_graph(r, upper=upper, want_dist32=True, want_dist64=True, want_edges=True)
+        e = int(a["total"])
+        b = engine.radius_graph(r, upper=upper, want_dist32=True, want_dist64=True, want_edges=True, capacity=e + 100)
+        engine.check_overflow()
+        assert torch.equal(a["row_ptr"], b["row_ptr"]) and int(b["row_ptr"][-1]) == e
+        for name in ("col", "dist32", "dist64", "edges"):
+            assert torch.equal(a[name], b[name][:e]), (name, n, upper)
+        for name in ("degree", "nbr_count", "stats", "hist"):
+            assert torch.equal(a[name], b[name]), (name, n, upper)
+
+
 # ---------------------------------------------------------------- kNN + union + composition
 def _check_knn(engine, coords, types, k, cell=None, bounds=None):
     from path_gene_multimodal_b200.engine import default_knn_cell
@@ -413,6 +435,13 @@ def test_full_size_c2_against_scipy(engine):
     assert bool((e[:, 0] < e[:, 1]).all())
     key = e[:, 0] * len(xy) + e[:, 1]
     assert bool((key[1:] > key[:-1]).all())          # strictly sorted by (i, j)
+    # the single-call path the bench times (outputs given up front, fill fused into the row pass): same graph
+    cap = len(ref["edges"]) + 1000
+    f = engine.radius_graph(50.0, upper=True, n_types=5, want_dist32=True, want_edges=True, capacity=cap)
+    engine.check_overflow()
+    n_e = len(ref["edges"])
+    assert int(f["row_ptr"][-1]) == n_e and torch.equal(f["edges"][:n_e], g["edges"]) and torch.equal(f["dist32"][:n_e], g["dist32"])
+    assert torch.equal(f["degree"], g["degree"]) and torch.equal(f["nbr_count"], g["nbr_count"]) and torch.equal(f["row_ptr"], g["row_ptr"])
 
 
 def test_full_size_c1_knn_against_scipy(engine):
