@@ -347,7 +347,6 @@ def test_instance_polygons_against_restated_skimage(shape, n):
 
     if shape[0] > 2:
         m = _blob_map(*shape, n=n, seed=shape[1] + 1)
-        m[10:13, 20:23][1, 1] = 0 if m[11, 21] else m[11, 21]             # (keeps the map as is; holes come from overwrites)
         m[30:37, 3:10] = n + 3                                             # a square ...
         m[32:35, 5:8] = 0                                                  # ... with a hole: two contours, the outer is longer
     else:
