@@ -36,17 +36,21 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu for sm_100a and link libpathgraph.so next to this file."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
+    """Compile csrc/*.cu for sm_100a and link libpathgraph.so next to this file.
+
+    ``defines`` / ``out``: an experimental variant (-DNAME=VALUE ...) linked to another path; select it at run
+    time with PG_LIBPATH (profiles/ uses this to time compile-time alternatives in one GPU session)."""
+    lib_path = Path(out) if out else LIB_PATH
+    if not force and not out and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    obj_dir = PKG_DIR / "build"
-    obj_dir.mkdir(exist_ok=True)
+    obj_dir = PKG_DIR / "build" / (lib_path.stem if out else "")
+    obj_dir.mkdir(exist_ok=True, parents=True)
 
     def compile_one(src: str) -> Path:
         obj = obj_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH.with_suffix(".so.tmp")
+    tmp = lib_path.with_suffix(".so.tmp")
     # static cudart: the library carries its own runtime and shares the primary context (and so
     # the stream handles) with torch's
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *map(str, objs), "-o", str(tmp),
@@ -66,8 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -182,7 +182,9 @@ static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 // Consecutive cells - and so consecutive points of the cell-ordered array - sweep a strip column by column,
 // which keeps the neighbourhoods of a warp's / CTA's points in a compact, roughly square patch (L1 reuse),
 // and the rows cy-1..cy+1 of one column are one contiguous run of the array unless they cross a strip edge.
+#ifndef PG_STRIP_LOG
 #define PG_STRIP_LOG 5
+#endif
 #define PG_STRIP (1 << PG_STRIP_LOG)
 
 #ifdef __CUDACC__
