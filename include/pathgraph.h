@@ -129,6 +129,11 @@ int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0,
 int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64, float* dist32,
            double x_lo, double x_hi, int32_t* halo_ok, pg_stream stream);
 
+/* knn_neighbor_coords of cell 11 (ipynb:1838-1840, copied back at :1950): out_xy f64 [n_rows,k,2] = the
+ * coordinates of every list entry, xy f64 [n_points,2] indexed by the ids in knn_idx (NaN for ids outside it). */
+int pg_knn_neighbor_coords(pg_handle* h, int32_t n_rows, int32_t k, const int32_t* knn_idx, const double* xy,
+                           int32_t n_points, double* out_xy, pg_stream stream);
+
 /* ---- K6 (+K8 fused): radius graph, two-pass CSR; cKDTree.query_ball_tree + the i<j loop +
  * np.linalg.norm (ipynb:2964-2975, ipynb:3041-3042).
  * count pass: row_ptr int32 [n_query+1] (exclusive scan of per-row counts, total in the last slot),
@@ -144,14 +149,16 @@ int pg_radius_reserve(pg_handle* h, int64_t entries);
 /* synchronises `stream`, returns row_ptr[n_query] of the last count pass */
 int pg_radius_total(pg_handle* h, int64_t* total);
 /* fill pass: col int32 [capacity] ascending per row, dist32 / dist64 (either may be NULL),
- * edges_i64 int64 [capacity,2] rows (i, j) (NULL = skip; the notebook's `edges` when flags=UPPER).
+ * edges_i64 int64 [capacity,2] rows (i, j) (NULL = skip; the notebook's `edges` when flags=UPPER);
+ * edges_i32 the same rows as int32 [capacity,2] (NULL = skip) - half the bytes for callers that move
+ * the edge list over PCIe and widen it where it is consumed.
  * With flags=UPPER and the exact total n_edges = E (from pg_radius_total) the notebook's packed
  * tensors can be written directly: edge_index int64 [2,2E] = hstack(edges.T, edges[:, ::-1].T)
  * (ipynb:3021) and edge_attr float32 [2E] = concat(d, d) (ipynb:3041-3042); NULL = skip.
  * Rows that would pass `capacity` are dropped and pg_check_overflow reports it. */
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
-                   int64_t* edges_i64, int64_t* edge_index, float* edge_attr, int64_t n_edges,
-                   int64_t capacity, pg_stream stream);
+                   int64_t* edges_i64, int32_t* edges_i32, int64_t* edge_index, float* edge_attr,
+                   int64_t n_edges, int64_t capacity, pg_stream stream);
 
 /* The same graph in ONE call when the caller provides the outputs up front (capacity in entries): the fill pass
  * runs inside the row pass of the count (each CTA gathers the rows it has just scanned), so row offsets never
@@ -161,7 +168,7 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
 int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree,
                     int32_t* nbr_count, int32_t n_types, pg_degree_stats* stats, int32_t* hist,
                     int32_t hist_len, int32_t* col, float* dist32, double* dist64, int64_t* edges_i64,
-                    int64_t capacity, pg_stream stream);
+                    int32_t* edges_i32, int64_t capacity, pg_stream stream);
 /* synchronises; PG_ERR_CAPACITY if any fill since the last check overflowed its buffers */
 int pg_check_overflow(pg_handle* h);
 

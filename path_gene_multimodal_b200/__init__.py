@@ -8,7 +8,8 @@ Public surface (reference-style module-level functions; see DESIGN.md / INTEGRAT
     build_knn_graph, build_radius_graph,
     neighbour_type_composition, degree_stats,
     filter_graph_by_type, clustering_coefficients,
-    type_interaction_matrix                               (cell_graph)
+    type_interaction_matrix, knn_graph_frame              (cell_graph)
+    to_networkx                                           (interop: nx.Graph keyed by nuc_id, cell 11)
     read_nuclei_table, write_nuclei_table, table_to_soa,
     add_wsi_coords_to_table, process_nuclei_file          (nuclei_io: Parquet / CSV <-> SoA / CSR)
     node_feature_matrix, assemble_graph_data, to_pyg      (graph_features: z-scores + one-hot -> x, PyG Data)
@@ -27,7 +28,8 @@ _EXPORTS = {
     "build_knn_graph": "cell_graph", "build_radius_graph": "cell_graph",
     "neighbour_type_composition": "cell_graph", "degree_stats": "cell_graph",
     "filter_graph_by_type": "cell_graph", "clustering_coefficients": "cell_graph",
-    "type_interaction_matrix": "cell_graph",
+    "type_interaction_matrix": "cell_graph", "knn_graph_frame": "cell_graph", "to_networkx": "interop",
+    "edge_index_from_edges": "graph_features",
     "read_nuclei_table": "nuclei_io", "write_nuclei_table": "nuclei_io", "table_to_soa": "nuclei_io",
     "add_wsi_coords_to_table": "nuclei_io", "process_nuclei_file": "nuclei_io",
     "node_feature_matrix": "graph_features", "assemble_graph_data": "graph_features", "to_pyg": "graph_features",

@@ -65,11 +65,12 @@ SIGNATURES = {
     "pg_grid_build": (C.c_int, [vp, i32, i32, vp, vp, vp, f64, C.POINTER(f64), vp]),
     "pg_grid_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),
     "pg_knn": (C.c_int, [vp, i32, vp, vp, vp, f64, f64, vp, vp]),
+    "pg_knn_neighbor_coords": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp]),
     "pg_radius_count": (C.c_int, [vp, f64, i32, vp, vp, vp, i32, vp, vp, i32, vp]),
-    "pg_radius_graph": (C.c_int, [vp, f64, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, i64, vp]),
+    "pg_radius_graph": (C.c_int, [vp, f64, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, i64, vp]),
     "pg_radius_reserve": (C.c_int, [vp, i64]),
     "pg_radius_total": (C.c_int, [vp, C.POINTER(i64)]),
-    "pg_radius_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+    "pg_radius_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
     "pg_launch_count": (C.c_int64, [vp]),
     "pg_profile_enable": (C.c_int, [vp, C.c_int]),
     "pg_profile_count": (C.c_int, [vp]),

@@ -19,7 +19,8 @@ import torch
 from . import _host
 from .engine import default_knn_cell, get_engine, radius_cell
 
-TYPE_NAMES = {1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}
+TYPE_NAMES = {1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}       # ipynb:1774-1780
+CLASS_COLORS = {1: "tab:red", 2: "tab:green", 3: "tab:blue", 4: "tab:gray", 5: "tab:orange"}           # ipynb:1782-1788
 
 
 def _prep(coords, types, eng):
@@ -47,13 +48,14 @@ def _bounds(c):
 
 
 def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected: bool = True,
-                    bounds=None, cell_size: float | None = None, device=None) -> dict:
+                    bounds=None, cell_size: float | None = None, device=None, neighbor_coords: bool = False) -> dict:
     """kNN graph of cell 11.
 
     Returns ``knn_neighbors`` int64 [N,k] (ascending ``(d^2, index)``, self excluded by index),
     ``knn_neighbor_distances`` float64 [N,k] and, with ``undirected``: ``edges`` int64 [E,2] (``i<j``,
     sorted), ``weight`` float64 [E], symmetric CSR ``row_ptr`` / ``col`` / ``csr_weight``, ``degree`` int32 [N],
     ``nbr_count`` int32 [N,n_types] (when ``types`` is given) and ``degree_stats``.
+    ``neighbor_coords`` adds ``knn_neighbor_coords`` float64 [N,k,2] (the (x, y) of every list entry, ipynb:1838-1840).
     Raises ``ValueError`` when ``k >= N`` (as cKDTree-backed KNN does for k+1 > N).
     """
     eng = get_engine(device)
@@ -73,6 +75,8 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
         kn = eng.knn(k, dist_dtype=torch.float64)
         out = {"knn_neighbors": _host.to_host(kn["knn_idx"]).astype(np.int64),
                "knn_neighbor_distances": _host.to_host(kn["dist"])}
+        if neighbor_coords:
+            out["knn_neighbor_coords"] = _host.to_host(eng.knn_neighbor_coords(kn["knn_idx"], d_xy))
         eng.grid_check()
         if undirected:
             # union + i<j edges + composition + degree statistics: one fused pass chain (pg_knn_union_*)
@@ -92,15 +96,21 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
 
 
 def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mpp: float | None = None,
-                       symmetric_csr: bool = False, bounds=None, device=None) -> dict:
+                       symmetric_csr: bool = False, bounds=None, device=None, outputs: str = "notebook") -> dict:
     """Radius graph of cells 23-26: ``d(i, j) <= r`` (inclusive, like query_ball_tree), ``i < j``.
 
     ``mpp`` scales pixel coordinates to micrometres first (``x_um = x_px * mpp``, ipynb:2046).
-    Returns ``edges`` int64 [E,2] sorted by (i, j); ``edge_index`` int64 [2,2E] = hstack(edges.T,
-    edges[:, ::-1].T) (the reference's vstack yields [4,E]; see SURVEY B-3); ``edge_attr`` float32 [2E,1];
-    ``dist`` float32 [E]; ``degree`` int32 [N]; ``nbr_count`` int32 [N,n_types] (with ``types``);
+    ``outputs="notebook"`` (default) returns ``edges`` int64 [E,2] sorted by (i, j); ``edge_index`` int64 [2,2E] =
+    hstack(edges.T, edges[:, ::-1].T) (the reference's vstack yields [4,E]; see SURVEY B-3); ``edge_attr`` float32
+    [2E,1]; ``dist`` float32 [E]; ``degree`` int32 [N]; ``nbr_count`` int32 [N,n_types] (with ``types``);
     ``degree_stats``; and with ``symmetric_csr`` also ``row_ptr`` / ``col`` / ``csr_dist``.
+    ``outputs="compact"`` returns the same graph without the redundant int64 tensors: ``edges`` int32 [E,2],
+    ``dist`` float32 [E], ``degree``, ``nbr_count``, ``degree_stats`` - a third of the bytes that cross PCIe (the
+    notebook tensors are ``graph_features.edge_index_from_edges(edges, dist)`` away, on whichever device consumes
+    them), and the whole call is one enqueue + one synchronisation once the handle has seen a slide of this kind.
     """
+    if outputs not in ("notebook", "compact"):
+        raise ValueError("outputs must be 'notebook' or 'compact'")
     eng = get_engine(device)
     c = np.asarray(coords, dtype=np.float64)
     if mpp is not None:
@@ -110,26 +120,66 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
         raise ValueError("r must be finite and >= 0")
     with torch.cuda.device(eng.device):
         eng.grid_build(d_xy, d_t, None, radius_cell(r), bounds)  # bounds=None: min/max reduced on the device
-        g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=False, want_edge_index=True)
-        e = int(g["total"])
-        host = _host.to_host_many({"edge_index": g["edge_index"], "edge_attr": g["edge_attr"], "degree": g["degree"],
-                                   "nbr_count": g["nbr_count"] if d_t is not None else None,
-                                   "stats": g["stats"], "hist": g["hist"]})
-        out = {
-            "edges": host["edge_index"][:, :e].T,      # view: rows (i, j), i < j, sorted by (i, j)
-            "dist": host["edge_attr"][:e, 0],
-            "edge_index": host["edge_index"],
-            "edge_attr": host["edge_attr"],
-            "degree": host["degree"],
-            "degree_stats": eng.decode_stats(host["stats"], host["hist"]),
-        }
-        if d_t is not None:
-            out["nbr_count"] = host["nbr_count"]
+        if outputs == "compact":
+            out = _radius_compact(eng, c.shape[0], r, n_types, d_t is not None)
+        else:
+            g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=False, want_edge_index=True)
+            e = int(g["total"])
+            host = _host.to_host_many({"edge_index": g["edge_index"], "edge_attr": g["edge_attr"], "degree": g["degree"],
+                                       "nbr_count": g["nbr_count"] if d_t is not None else None,
+                                       "stats": g["stats"], "hist": g["hist"]})
+            out = {
+                "edges": host["edge_index"][:, :e].T,      # view: rows (i, j), i < j, sorted by (i, j)
+                "dist": host["edge_attr"][:e, 0],
+                "edge_index": host["edge_index"],
+                "edge_attr": host["edge_attr"],
+                "degree": host["degree"],
+                "degree_stats": eng.decode_stats(host["stats"], host["hist"]),
+            }
+            if d_t is not None:
+                out["nbr_count"] = host["nbr_count"]
         if symmetric_csr:
             s = eng.radius_graph(r, upper=False, compose=False, stats=False, want_dist32=True)
             out["row_ptr"] = _host.to_host(s["row_ptr"]).astype(np.int64)
             out["col"] = _host.to_host(s["col"]).astype(np.int64)
             out["csr_dist"] = _host.to_host(s["dist32"])
+    return out
+
+
+def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool) -> dict:
+    """The compact output set. With a capacity hint from an earlier slide (edges per nucleus seen on this handle)
+    the build is pg_radius_graph - outputs given up front, nothing read back in between - followed by ONE batch of
+    device-to-host copies and one synchronisation; the valid prefix is cut on the host. Without a hint, or when the
+    hint proves too small, the exact count -> total -> fill sequence runs (and leaves a hint behind)."""
+    hint = getattr(eng, "_radius_edges_per_point", None)
+    for attempt in range(2):
+        if hint is not None and attempt == 0 and n > 0:
+            cap = int(hint * 1.15 * n) + 4096
+            prev = getattr(eng, "_radius_cap", 0)
+            if cap <= prev < 2 * cap:
+                cap = prev  # same buffers as the last slide of this kind
+            eng._radius_cap = cap
+            g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=True, want_edges32=True,
+                                 capacity=cap, out=getattr(eng, "_radius_compact_out", None))
+            eng._radius_compact_out = {k: v for k, v in g.items() if k in ("col", "dist32", "edges32")}  # reused scratch
+        else:
+            g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=True, want_edges32=True)
+            cap = int(g["total"])
+        host = _host.to_host_many({"edges": g["edges32"], "dist": g["dist32"], "degree": g["degree"],
+                                   "nbr_count": g["nbr_count"] if has_types else None, "stats": g["stats"],
+                                   "hist": g["hist"], "row_end": g["row_ptr"][-1:]})
+        e = int(host["row_end"][0])
+        if e <= cap:
+            break
+        eng.lib.pg_check_overflow(eng._h)  # clears the overflow flag the undersized pass has raised
+        hint = None
+    if n > 0:
+        eng._radius_edges_per_point = max(e / n, 1e-3)
+    eng.grid_check()
+    out = {"edges": host["edges"][:e], "dist": host["dist"][:e], "degree": host["degree"],
+           "degree_stats": eng.decode_stats(host["stats"], host["hist"])}
+    if has_types:
+        out["nbr_count"] = host["nbr_count"]
     return out
 
 
@@ -188,3 +238,46 @@ def type_interaction_matrix(types, nbr_count, n_types: int = 5, device=None) -> 
         d_t = _host.to_device(_host.as_int32(types, "types"), np.int32, eng.device)
         d_c = _host.to_device(_host.as_int32(nbr_count, "nbr_count"), np.int32, eng.device)
         return _host.to_host(eng.type_interactions(d_t, d_c, n_types))
+
+
+def knn_graph_frame(final_df, k: int = 5, centroid_col: str = "centroid", centroid_order: str = "yx",
+                    type_col: str | None = None, device=None):
+    """Cell 11 at DataFrame level (ipynb:1766-1951): returns ``(df, graph)``.
+
+    ``df`` is a copy of ``final_df`` with the columns the notebook copies back (:1945-1951): ``type_id``, ``color``,
+    ``knn_neighbors`` (list of k row positions), ``knn_neighbor_coords`` (list of (x, y) tuples),
+    ``knn_neighbor_points`` (shapely Points when shapely is importable, else the same tuples) and
+    ``knn_neighbor_distances`` (list of k floats).  ``centroid`` cells are [y, x] as HoverNeXt stores them (the
+    notebook builds ``Point(c[1], c[0])``, :1799); pass ``centroid_order="xy"`` for already swapped data.
+    ``graph`` is the dict of ``build_knn_graph`` (edges, weights, degree, composition);
+    ``interop.to_networkx(graph, df)`` makes the notebook's ``G_knn``."""
+    import pandas as pd
+
+    df = final_df.copy()
+    c = np.array(df[centroid_col].tolist(), dtype=np.float64).reshape(-1, 2)
+    coords = np.ascontiguousarray(c[:, ::-1]) if centroid_order == "yx" else c
+    if "type_id" not in df.columns:                                  # ipynb:1807-1813
+        if type_col is None and "type_name" in df.columns:
+            name_to_id = {v: kk for kk, v in TYPE_NAMES.items()}
+            df["type_id"] = df["type_name"].map(name_to_id)
+        elif (type_col or "type") in df.columns:
+            df["type_id"] = df[type_col or "type"]
+        else:
+            raise ValueError("No type_name or type column found to map cell types.")
+    tid = pd.to_numeric(df["type_id"], errors="coerce")
+    types = tid.fillna(0).astype(np.int64).to_numpy()
+    g = build_knn_graph(coords, k=k, types=types, device=device, neighbor_coords=True)
+    df["knn_neighbors"] = pd.Series(g["knn_neighbors"].tolist(), index=df.index, dtype=object)
+    nc = g["knn_neighbor_coords"]
+    as_tuples = [[(float(x), float(y)) for x, y in row] for row in nc.tolist()]
+    df["knn_neighbor_coords"] = pd.Series(as_tuples, index=df.index, dtype=object)
+    try:
+        from shapely.geometry import Point  # the notebook's type; absent here -> the coordinate tuples stand in
+
+        df["knn_neighbor_points"] = pd.Series([[Point(x, y) for x, y in row] for row in as_tuples], index=df.index, dtype=object)
+    except ImportError:
+        df["knn_neighbor_points"] = df["knn_neighbor_coords"]
+    df["knn_neighbor_distances"] = pd.Series(g["knn_neighbor_distances"].tolist(), index=df.index, dtype=object)
+    df["color"] = [CLASS_COLORS.get(int(t), "black") if np.isfinite(t) else "black" for t in tid.to_numpy(dtype=np.float64)]
+    g["pos"] = coords
+    return df, g

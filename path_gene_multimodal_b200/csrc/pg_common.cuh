@@ -54,6 +54,7 @@ struct pg_handle {
     int32_t n_types = 0; pg_degree_stats* stats = nullptr; int32_t* hist = nullptr; int32_t hist_len = 0;
     // pg_radius_graph: the fill pass fused into the row pass (outputs known at count time)
     bool fused = false; int32_t* col = nullptr; float* dist32 = nullptr; double* dist64 = nullptr; int64_t* edges = nullptr;
+    int32_t* edges32 = nullptr;
     int64_t capacity = 0;
   } last_count;
   pg_buf knn_retry;    // int32 [N]     cell-order positions of the points the kNN block pass could not finish
@@ -74,6 +75,7 @@ struct pg_handle {
   int32_t contour_labels = -1;   // labels of the last pg_instance_contours_count (-1: none), for the fill call
   bool contour_empty = false;
   int64_t contour_raw = 0;
+  size_t morph_smem_set[2][2] = {{0, 0}, {0, 0}};  // K1: dynamic shared memory opted in on this handle's device, per [T][EXTRA]
   double morph_mean_verts = 0;  // pg_map_morph_hint: expected vertices per ring (sizes K1's shared-memory slabs)
   // launch accounting / optional per-kernel CUDA-event timing (pg_profile_*)
   int64_t launches = 0;

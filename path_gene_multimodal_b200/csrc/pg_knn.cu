@@ -311,6 +311,16 @@ knn_ring_kernel(pg_grid_view g, int k, knn_out o, const int32_t* list, const int
   }
 }
 
+// knn_neighbor_coords of cell 11 (ipynb:1838-1840): out[i][s] = xy[knn_idx[i][s]], one thread per list entry
+__global__ void __launch_bounds__(256)
+knn_coords_kernel(const int32_t* __restrict__ idx, const double2* __restrict__ xy, int64_t entries, int32_t n_points, double2* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= entries) return;
+  const int j = idx[e];
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  out[e] = (j >= 0 && j < n_points) ? xy[j] : make_double2(nan, nan);
+}
+
 __global__ void knn_prepare_kernel(int32_t* halo_ok, int32_t* retry_count) {
   if (halo_ok) *halo_ok = 1;
   *retry_count = 0;
@@ -355,6 +365,22 @@ extern "C" int pg_knn(pg_handle* h, int32_t k, int32_t* knn_idx, double* dist64,
   } else {
     PG_LAUNCH(h, s, "knn_ring_kernel<64>", pg_launch_pdl(7, knn_ring_kernel<64, topk_local<64>>, blocks, TPB, s, v, (int)k, o, (const int32_t*)nullptr, (const int32_t*)nullptr));
   }
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+extern "C" int pg_knn_neighbor_coords(pg_handle* h, int32_t n_rows, int32_t k, const int32_t* knn_idx, const double* xy,
+                                      int32_t n_points, double* out_xy, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n_rows >= 0 && k >= 1 && n_points >= 0, "pg_knn_neighbor_coords: bad sizes");
+  PG_REQUIRE(h, n_rows == 0 || (knn_idx && xy && out_xy), "pg_knn_neighbor_coords: NULL array");
+  PG_REQUIRE(h, (((uintptr_t)xy | (uintptr_t)out_xy) & 15) == 0, "pg_knn_neighbor_coords: xy / out must be 16-byte aligned");
+  const int64_t entries = (int64_t)n_rows * k;
+  if (entries == 0) return PG_OK;
+  PG_LAUNCH(h, s, "knn_coords_kernel", knn_coords_kernel<<<pg_div_up(entries, 256), 256, 0, s>>>(knn_idx, (const double2*)xy, entries, n_points, (double2*)out_xy));
   PG_LAUNCH_CHECK(h);
   return PG_OK;
 }

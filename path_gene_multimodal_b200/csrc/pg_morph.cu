@@ -88,7 +88,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Green's-theorem sums of one ring in a frame at one of its vertices.
 struct ring_sums {
   double S, Sx, Sy, Ixx, Iyy, Ixy;
-  float P;
+  float P;        // ring length: float32 edge lengths (each within an ulp) summed in float32 over at most 32 edges ...
+  double Pd;      // ... and those partial sums in float64, so the error does not grow with the ring (shapely's
+                  // p.length is float64: polygon_morphology.py:247-248 measures tissue islands of 10^4..10^5 vertices)
   double fx, fy;  // frame origin
 };
 
@@ -166,7 +168,7 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
   }
 
   ring_sums r;
-  r.S = r.Sx = r.Sy = r.Ixx = r.Iyy = r.Ixy = 0; r.P = 0; r.fx = r.fy = 0;
+  r.S = r.Sx = r.Sy = r.Ixx = r.Iyy = r.Ixy = 0; r.P = 0; r.Pd = 0; r.fx = r.fy = 0;
   T bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
 
   if (staged) {
@@ -196,6 +198,7 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
         edge_terms(r, xa, ya, xb, yb);
         const float dx = (float)(v.x - px), dy = (float)(v.y - py);
         r.P += sqrtf(dx * dx + dy * dy);
+        if ((k & 31) == 0) { r.Pd += (double)r.P; r.P = 0.f; }
         if (EXTRA) { bx0 = min(bx0, v.x); bx1 = max(bx1, v.x); by0 = min(by0, v.y); by1 = max(by1, v.y); }
         xa = xb; ya = yb; px = v.x; py = v.y;
       }
@@ -227,7 +230,7 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
       const int sx = __shfl_sync(0xffffffffu, itx, src);
       const int sy = __shfl_sync(0xffffffffu, ity, src);
       ring_sums a;
-      a.S = a.Sx = a.Sy = a.Ixx = a.Iyy = a.Ixy = 0; a.P = 0;
+      a.S = a.Sx = a.Sy = a.Ixx = a.Iyy = a.Ixy = 0; a.P = 0; a.Pd = 0;
       V2 v0; v0.x = 0; v0.y = 0;
       T mnx = 0, mny = 0, mxx = 0, mxy = 0;
       if (cnt > 0) {
@@ -242,13 +245,13 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
           const double xb = (double)vb.x - (double)v0.x, yb = (double)vb.y - (double)v0.y;
           edge_terms(a, xa, ya, xb, yb);
           const float dx = (float)(vb.x - va.x), dy = (float)(vb.y - va.y);
-          a.P += sqrtf(dx * dx + dy * dy);
+          a.Pd += (double)sqrtf(dx * dx + dy * dy);  // long rings live on this path: float64 accumulation throughout
           if (EXTRA) { mnx = min(mnx, va.x); mxx = max(mxx, va.x); mny = min(mny, va.y); mxy = max(mxy, va.y); }
         }
       }
       a.S = bfly_add(a.S); a.Sx = bfly_add(a.Sx); a.Sy = bfly_add(a.Sy);
       a.Ixx = bfly_add(a.Ixx); a.Iyy = bfly_add(a.Iyy); a.Ixy = bfly_add(a.Ixy);
-      a.P = bfly_addf(a.P);
+      a.Pd = bfly_add(a.Pd);
       if (EXTRA) { mnx = bfly_min(mnx); mny = bfly_min(mny); mxx = bfly_max(mxx); mxy = bfly_max(mxy); }
       if (sub == t) {
         r = a;
@@ -261,13 +264,13 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
   // ---- epilogue: one polygon per lane
   if (my_poly >= n) return;
   const double S = r.S, Sx = r.Sx, Sy = r.Sy, Ixx = r.Ixx, Iyy = r.Iyy, Ixy = r.Ixy, fx = r.fx, fy = r.fy;
-  const float P = r.P;
+  const double per = r.Pd + (double)r.P;
+  const float P = (float)per;
   const float nanf_ = __int_as_float(0x7fc00000);
   const double nand_ = __longlong_as_double(0x7ff8000000000000ll);
   const bool ok = nv >= 3;
   const double A = 0.5 * S;
   const double area = fabs(A);
-  const double per = (double)P;
   if (out.area) out.area[my_poly] = ok ? (float)area : nanf_;
   if (out.perimeter) out.perimeter[my_poly] = ok ? P : nanf_;
   if (out.circularity) {
@@ -339,10 +342,12 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   slab_verts &= ~1;  // whole 16-byte units per warp
   const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
   auto kern = extra ? map_morph_kernel<T, true> : map_morph_kernel<T, false>;
-  static size_t attr_set[2] = {0, 0};  // per instantiation of this template (T), per EXTRA: largest size opted in
-  if (smem > attr_set[extra]) {
+  // the opt-in above 48 KB of dynamic shared memory belongs to the DEVICE the handle lives on (cudaFuncSetAttribute
+  // acts on the current device only), so what has been granted is remembered per handle, not per process
+  size_t& granted = h->morph_smem_set[sizeof(T) == 8 ? 1 : 0][extra ? 1 : 0];
+  if (smem > granted) {
     PG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[extra] = smem;
+    granted = smem;
   }
   PG_LAUNCH(h, s, extra ? "map_morph_kernel<T, true>" : "map_morph_kernel<T, false>",
             kern<<<blocks, TPB, smem, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,

@@ -260,6 +260,7 @@ struct fill_out {
   float* __restrict__ dist32;
   double* __restrict__ dist64;
   long long* __restrict__ edges;
+  int32_t* __restrict__ edges32;
   long long* __restrict__ edge_index;
   float* __restrict__ edge_attr;
   long long n_edges;
@@ -271,6 +272,7 @@ __device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int
   if (o.dist32) o.dist32[pos] = (float)d;
   if (o.dist64) o.dist64[pos] = d;
   if (o.edges) *reinterpret_cast<longlong2*>(o.edges + 2 * pos) = make_longlong2(my_id, key);
+  if (o.edges32) *reinterpret_cast<int2*>(o.edges32 + 2 * pos) = make_int2(my_id, key);
   if (o.edge_index) {  // [2, 2E] = hstack(edges.T, edges[:, ::-1].T), ipynb:3021 (see SURVEY B-3)
     o.edge_index[pos] = my_id; o.edge_index[o.n_edges + pos] = key;
     o.edge_index[2 * o.n_edges + pos] = key; o.edge_index[3 * o.n_edges + pos] = my_id;
@@ -624,7 +626,7 @@ int launch_count_pass(pg_handle* h, cudaStream_t s) {
   if (a.fused) {
     gx.tmp = (const pg_tmp_ent*)h->tmp_ent.p;
     gx.row_gid = gr.has_gid ? (const int32_t*)h->s_gid.p : nullptr;
-    gx.fo = fill_out{a.col, a.dist32, a.dist64, (long long*)a.edges, nullptr, nullptr, 0};
+    gx.fo = fill_out{a.col, a.dist32, a.dist64, (long long*)a.edges, a.edges32, nullptr, nullptr, 0};
     gx.capacity = (long long)a.capacity;
     gx.overflow = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
     PG_LAUNCH(h, s, "radius_rows_gather_kernel", pg_launch_pdl(4, radius_rows_kernel<true>, tiles, TPB_ROWS, s, nq, (const pg_pt_meta*)h->pt_meta.p, st, o, gx));
@@ -680,7 +682,8 @@ int pg_radius_count(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
 
 int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int32_t* degree, int32_t* nbr_count,
                     int32_t n_types, pg_degree_stats* stats, int32_t* hist, int32_t hist_len, int32_t* col,
-                    float* dist32, double* dist64, int64_t* edges_i64, int64_t capacity, pg_stream stream) {
+                    float* dist32, double* dist64, int64_t* edges_i64, int32_t* edges_i32, int64_t capacity,
+                    pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   PG_CUDA(h, cudaSetDevice(h->device));
@@ -693,7 +696,7 @@ int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   PG_REQUIRE(h, !nbr_count || (n_types >= 1 && n_types <= PG_MAX_TYPES), "pg_radius_graph: n_types must be in 1..%d", PG_MAX_TYPES);
   PG_REQUIRE(h, !hist || hist_len >= 1, "pg_radius_graph: hist_len must be >= 1");
   PG_REQUIRE(h, capacity >= 0 && (capacity == 0 || col != nullptr), "pg_radius_graph: capacity < 0 or col is NULL");
-  PG_REQUIRE(h, (((uintptr_t)row_ptr | (uintptr_t)degree | (uintptr_t)nbr_count | (uintptr_t)edges_i64) & 15) == 0,
+  PG_REQUIRE(h, (((uintptr_t)row_ptr | (uintptr_t)degree | (uintptr_t)nbr_count | (uintptr_t)edges_i64 | (uintptr_t)edges_i32) & 15) == 0,
              "pg_radius_graph: row_ptr / degree / nbr_count / edges must be 16-byte aligned");
   const pg_grid& gr = h->grid;
   int rc;
@@ -705,7 +708,7 @@ int pg_radius_graph(pg_handle* h, double r, int32_t flags, int32_t* row_ptr, int
   auto& a = h->last_count;
   a.r = r; a.flags = flags; a.row_ptr = row_ptr; a.degree = degree; a.nbr_count = nbr_count; a.n_types = n_types;
   a.stats = stats; a.hist = hist; a.hist_len = hist_len;
-  a.fused = true; a.col = col; a.dist32 = dist32; a.dist64 = dist64; a.edges = edges_i64; a.capacity = capacity;
+  a.fused = true; a.col = col; a.dist32 = dist32; a.dist64 = dist64; a.edges = edges_i64; a.edges32 = edges_i32; a.capacity = capacity;
   if ((rc = size_tmp(h))) return rc;
   if ((rc = launch_count_pass(h, s))) return rc;
   a.valid = true;
@@ -749,7 +752,7 @@ int pg_radius_total(pg_handle* h, int64_t* total) {
 }
 
 int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* dist32, double* dist64,
-                   int64_t* edges_i64, int64_t* edge_index, float* edge_attr, int64_t n_edges,
+                   int64_t* edges_i64, int32_t* edges_i32, int64_t* edge_index, float* edge_attr, int64_t n_edges,
                    int64_t capacity, pg_stream stream) {
   if (!h) return PG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
@@ -762,10 +765,10 @@ int pg_radius_fill(pg_handle* h, const int32_t* row_ptr, int32_t* col, float* di
   PG_REQUIRE(h, capacity == 0 || col != nullptr, "pg_radius_fill: col is NULL");
   PG_REQUIRE(h, !(edge_index || edge_attr) || (h->radius_flags == PG_RADIUS_UPPER && n_edges >= 0 && n_edges <= capacity),
              "pg_radius_fill: edge_index / edge_attr need the UPPER count pass and 0 <= n_edges <= capacity");
-  PG_REQUIRE(h, ((uintptr_t)edges_i64 & 15) == 0, "pg_radius_fill: edges must be 16-byte aligned");
+  PG_REQUIRE(h, (((uintptr_t)edges_i64 | (uintptr_t)edges_i32) & 15) == 0, "pg_radius_fill: edges must be 16-byte aligned");
   const pg_grid& gr = h->grid;
   if (gr.n == 0 || gr.n_query == 0) return PG_OK;
-  fill_out o{col, dist32, dist64, (long long*)edges_i64, (long long*)edge_index, edge_attr, (long long)n_edges};
+  fill_out o{col, dist32, dist64, (long long*)edges_i64, edges_i32, (long long*)edge_index, edge_attr, (long long)n_edges};
   int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
   const int blocks = pg_div_up(gr.n_query, TPB_GATHER);
   PG_LAUNCH(h, s, "radius_gather_kernel", pg_launch_pdl(5, radius_gather_kernel, blocks, TPB_GATHER, s,

@@ -224,9 +224,19 @@ class Engine:
         res["dist"] = d64 if dist_dtype == torch.float64 else d32
         return res
 
+    def knn_neighbor_coords(self, knn_idx, xy):
+        """float64 [n,k,2]: coordinates of every kNN list entry (pg_knn_neighbor_coords)."""
+        n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
+        out = self._empty((n, k, 2), torch.float64)
+        self._check(self.lib.pg_knn_neighbor_coords(self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
+                                                    self._p(xy, torch.float64, "xy"), int(xy.shape[0]),
+                                                    self._p(out, torch.float64, "out"), self._stream()))
+        return out
+
     # ---- K6 + fused K8 ---------------------------------------------------------------------------
     def radius_graph(self, r, upper=False, n_types=5, compose=True, stats=True, hist_len=64, want_dist32=True,
-                     want_dist64=False, want_edges=False, want_edge_index=False, capacity=None, out=None):
+                     want_dist64=False, want_edges=False, want_edge_index=False, capacity=None, out=None,
+                     want_edges32=False):
         """Radius graph over the built grid: count (+composition / degree) -> scan -> fill.
 
         With ``capacity`` (entries) the whole sequence is enqueued without a host sync and the
@@ -234,6 +244,7 @@ class Engine:
         ``check_overflow()`` later.  Without it the total is read back and outputs are exact-size.
         ``want_edge_index`` (needs ``upper`` and the exact total) adds the notebook's packed tensors
         ``edge_index`` int64 [2,2E] and ``edge_attr`` float32 [2E,1], written by the fill kernel.
+        ``want_edges32``: the edge list as int32 [E,2] (``edges32``) - half the bytes of ``edges`` on the way to the host.
         """
         nq = self._nq
         res = dict(out) if out else {}
@@ -256,13 +267,14 @@ class Engine:
             d32 = get("dist32", (cap,), torch.float32) if want_dist32 else None
             d64 = get("dist64", (cap,), torch.float64) if want_dist64 else None
             edges = get("edges", (cap, 2), torch.int64) if want_edges else None
+            edges32 = get("edges32", (cap, 2), torch.int32) if want_edges32 else None
             self._check(self.lib.pg_radius_graph(
                 self._h, float(r), 1 if upper else 0, self._p(row_ptr, torch.int32, "row_ptr"),
                 self._p(degree, torch.int32, "degree"), self._p(nbr, torch.int32, "nbr_count"), int(n_types),
                 self._p(st, torch.int64, "stats"), self._p(hist, torch.int32, "hist"),
                 int(hist_len) if hist is not None else 0, self._p(col, torch.int32, "col"),
                 self._p(d32, torch.float32, "dist32"), self._p(d64, torch.float64, "dist64"),
-                self._p(edges, torch.int64, "edges"), cap, self._stream()))
+                self._p(edges, torch.int64, "edges"), self._p(edges32, torch.int32, "edges32"), cap, self._stream()))
             return res
         if capacity is not None:
             self._check(self.lib.pg_radius_reserve(self._h, int(capacity)))
@@ -282,6 +294,7 @@ class Engine:
         d32 = get("dist32", (cap,), torch.float32) if want_dist32 else None
         d64 = get("dist64", (cap,), torch.float64) if want_dist64 else None
         edges = get("edges", (cap, 2), torch.int64) if want_edges else None
+        edges32 = get("edges32", (cap, 2), torch.int32) if want_edges32 else None
         ei = ea = None
         if want_edge_index:
             if capacity is not None or not upper:
@@ -291,7 +304,7 @@ class Engine:
         self._check(self.lib.pg_radius_fill(self._h, self._p(row_ptr, torch.int32, "row_ptr"),
                                             self._p(col, torch.int32, "col"), self._p(d32, torch.float32, "dist32"),
                                             self._p(d64, torch.float64, "dist64"), self._p(edges, torch.int64, "edges"),
-                                            self._p(ei, torch.int64, "edge_index"), self._p(ea, torch.float32, "edge_attr"),
+                                            self._p(edges32, torch.int32, "edges32"), self._p(ei, torch.int64, "edge_index"), self._p(ea, torch.float32, "edge_attr"),
                                             cap if want_edge_index else 0, cap, self._stream()))
         return res
 

@@ -61,6 +61,21 @@ def assemble_graph_data(df: pd.DataFrame, r: float = 40.0, coord_cols=("x_um", "
             "edges": g["edges"], "pos": coords, "degree": g["degree"], "nbr_count": g.get("nbr_count")}
 
 
+def edge_index_from_edges(edges, dist):
+    """The notebook's packed tensors from a compact edge list (``build_radius_graph(outputs="compact")``):
+    ``edge_index`` int64 [2,2E] = hstack(edges.T, edges[:, ::-1].T) (ipynb:3021, SURVEY B-3) and ``edge_attr``
+    float32 [2E,1] = concat(d, d) (ipynb:3041-3042). numpy in, numpy out; torch tensors (any device) in, torch out -
+    so the widening to int64 happens where the graph is consumed, not before it crosses PCIe."""
+    if isinstance(edges, torch.Tensor):
+        e = edges.to(torch.int64)
+        ei = torch.cat([e.t(), e.flip(1).t()], dim=1).contiguous()
+        d = dist.to(torch.float32).reshape(-1, 1)
+        return ei, torch.cat([d, d], dim=0)
+    e = np.asarray(edges).astype(np.int64)
+    d = np.asarray(dist, dtype=np.float32).reshape(-1, 1)
+    return np.ascontiguousarray(np.hstack([e.T, e[:, ::-1].T])), np.concatenate([d, d], axis=0)
+
+
 def to_pyg(data: dict):
     """``torch_geometric.data.Data(x=, edge_index=, edge_attr=)`` of cell 27 (needs torch_geometric)."""
     try:

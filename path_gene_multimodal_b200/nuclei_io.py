@@ -18,6 +18,7 @@ The numeric body runs in pg_map_morph_* like the DataFrame entry point (no CPU f
 from __future__ import annotations
 
 import json
+import re
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -145,6 +146,8 @@ def _parse_list_strings(series: pd.Series):
     vals = series.to_numpy(dtype=object)
     null = pd.isna(vals)
     doc = "[" + ",".join("null" if z else str(v) for v, z in zip(vals, null)) + "]"
+    if "nan" in doc or "inf" in doc:  # repr(list) writes non-finite floats as nan / inf / -inf; JSON spells them differently
+        doc = re.sub(r"(?<![\w.])(-?)inf(?![\w.])", r"\1Infinity", re.sub(r"(?<![\w.])nan(?![\w.])", "NaN", doc))
     return json.loads(doc)
 
 

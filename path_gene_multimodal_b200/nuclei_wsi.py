@@ -32,7 +32,12 @@ def polygons_to_csr(polygons, dtype=np.float64):
     n = len(polygons)
     if n == 0:
         return np.zeros(1, dtype=np.int32), np.zeros((0, 2), dtype=dtype), np.zeros(0, dtype=bool)
-    arr = pa.array(polygons, type=pa.list_(pa.list_(pa.float64())), from_pandas=True)
+    try:
+        arr = pa.array(polygons, type=pa.list_(pa.list_(pa.float64())), from_pandas=True)
+    except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
+        # cells that are numpy arrays (what pd.read_parquet returns for list<list<double>>, including the
+        # reference's own *_nuclei_wsi.parquet): normalise ring by ring
+        return _polygons_to_csr_loop(polygons, dtype)
     is_none = np.asarray(arr.is_null().to_numpy(zero_copy_only=False), dtype=bool)
     off = np.asarray(arr.offsets.to_numpy(), dtype=np.int64)
     inner = arr.values  # list<double>, one entry per vertex
@@ -46,6 +51,27 @@ def polygons_to_csr(polygons, dtype=np.float64):
     off = off - base_v
     if m > _host.INT32_MAX:
         raise OverflowError("more than 2^31 polygon vertices")
+    return off.astype(np.int32), np.ascontiguousarray(xy, dtype=dtype), is_none
+
+
+def _polygons_to_csr_loop(polygons, dtype):
+    n = len(polygons)
+    is_none = np.zeros(n, dtype=bool)
+    off = np.zeros(n + 1, dtype=np.int64)
+    rings = []
+    for i, p in enumerate(polygons):
+        if p is None or (isinstance(p, float) and np.isnan(p)):
+            is_none[i] = True
+            off[i + 1] = off[i]
+            continue
+        a = np.asarray([np.asarray(v, dtype=np.float64) for v in p], dtype=np.float64) if len(p) else np.zeros((0, 2))
+        if a.ndim != 2 or (a.size and a.shape[1] != 2):
+            raise ValueError("polygon vertices must be [x, y] pairs")
+        rings.append(a.reshape(-1, 2))
+        off[i + 1] = off[i] + a.shape[0]
+    if off[-1] > _host.INT32_MAX:
+        raise OverflowError("more than 2^31 polygon vertices")
+    xy = np.concatenate(rings, axis=0) if rings else np.zeros((0, 2))
     return off.astype(np.int32), np.ascontiguousarray(xy, dtype=dtype), is_none
 
 
@@ -105,6 +131,7 @@ def add_wsi_coords_to_nuclei(
     tile_key_col_tiles: str = "png_path",
     morphology: bool = False,
     device=None,
+    centroid_order: str = "xy",
 ) -> pd.DataFrame:
     """Shift tile-local centroid / bounding_box / polygon by the tile's top-left (x, y).
 
@@ -112,9 +139,14 @@ def add_wsi_coords_to_nuclei(
     ``nuc_df`` with ``tile_key, tile_x, tile_y, centroid_x, centroid_y, wsi_centroid_x,
     wsi_centroid_y, bbox_*, wsi_bbox_*, wsi_polygon`` appended in that order; inputs are not
     modified; unmatched tile keys raise ``ValueError``.  Like the reference, ``centroid[0]`` is
-    treated as x (SURVEY B-1).  ``morphology=True`` additionally appends ``area, perimeter,
-    eccentricity, circularity`` from the same kernel launch.
+    treated as x (SURVEY B-1): HoverNeXt stores centroids as (y, x) (hovernet_plotting.py:65-66), so the
+    reference's ``wsi_centroid_x`` is really tile_x + y.  ``centroid_order="yx"`` is the opt-in fix: ``centroid[1]``
+    is x, ``centroid[0]`` is y, and the four centroid columns come out in true WSI axes (polygons and boxes are
+    (x, y) either way).  ``morphology=True`` additionally appends ``area, perimeter, eccentricity, circularity``
+    from the same kernel launch.  Tile offsets must be integral pixel values (int or float dtype).
     """
+    if centroid_order not in ("xy", "yx"):
+        raise ValueError("centroid_order must be 'xy' (the reference's reading) or 'yx' (HoverNeXt's storage order)")
     out = nuc_df.copy()
     n = len(out)
     # ---- :285-299 key join on the host (strings); stem once per distinct path
@@ -138,6 +170,8 @@ def add_wsi_coords_to_nuclei(
 
     # ---- host lists -> SoA / CSR
     cent = np.array(out["centroid"].tolist(), dtype=np.float64).reshape(-1, 2) if n else np.zeros((0, 2))
+    if centroid_order == "yx":
+        cent = np.ascontiguousarray(cent[:, ::-1])
     bb_raw = np.array(out["bounding_box"].tolist()).reshape(-1, 4) if n else np.zeros((0, 4), dtype=np.int64)
     bb = _host.as_int32(bb_raw, "bounding_box")
     poly_off, poly_xy, is_none = polygons_to_csr(out["polygon"])
@@ -153,9 +187,10 @@ def add_wsi_coords_to_nuclei(
     out["wsi_centroid_y"] = wsi_c[:, 1]
     for c, name in enumerate(["bbox_xmin", "bbox_ymin", "bbox_xmax", "bbox_ymax"]):
         out[name] = bb_raw[:, c]
-    wsi_b = res["wsi_bbox"].astype(np.result_type(bb_raw.dtype, tiles_x.dtype)) if n else np.zeros((0, 4), dtype=np.int64)
+    wsi_b = res["wsi_bbox"] if n else np.zeros((0, 4), dtype=np.int64)
     for c, name in enumerate(["wsi_bbox_xmin", "wsi_bbox_ymin", "wsi_bbox_xmax", "wsi_bbox_ymax"]):
-        out[name] = wsi_b[:, c]
+        # bbox + tile_x for the x columns, bbox + tile_y for the y columns: numpy's result dtype of each sum (:316-319)
+        out[name] = wsi_b[:, c].astype(np.result_type(bb_raw.dtype, (tiles_x if c % 2 == 0 else tiles_y).dtype))
     out["wsi_polygon"] = pd.Series(csr_to_polygons(poly_off, res["wsi_poly_xy"], is_none) if n else [],
                                    index=out.index, dtype=object)
     if morphology:

@@ -15,6 +15,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a machine without a GPU skips the gpu-marked tests instead of failing at the first one
+    (the product itself still fails loudly without a GPU: tests/test_host_cpu.py checks that)."""
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: gpu-marked tests run on the B200 box (pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_graph():
     return np.load(GOLDEN / "graph_small.npz")

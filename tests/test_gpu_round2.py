@@ -1,0 +1,162 @@
+"""GPU tests of the round-2 additions: compact radius outputs, the rest of the cell-11 surface (neighbour
+coordinates, nx.Graph keyed by nuc_id), centroid_order="yx", numpy-array table cells, the per-axis bbox dtype,
+float64 ring length on long rings, C3 parity at 250 k polygons, two engines in one process."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import graph as ograph
+from oracle import morphology as omorph
+from oracle import tile_to_wsi as omap
+from path_gene_multimodal_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_radius_compact_outputs_equal_notebook_outputs(golden_graph):
+    from path_gene_multimodal_b200 import build_radius_graph, edge_index_from_edges
+
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    full = build_radius_graph(coords, r=25.0, types=types)
+    for _ in range(3):  # first call: exact count -> fill; later calls: the one-enqueue path with a capacity hint
+        c = build_radius_graph(coords, r=25.0, types=types, outputs="compact")
+        assert c["edges"].dtype == np.int32 and np.array_equal(c["edges"], full["edges"])
+        assert c["dist"].dtype == np.float32 and np.array_equal(c["dist"], full["dist"])
+        assert np.array_equal(c["degree"], full["degree"]) and np.array_equal(c["nbr_count"], full["nbr_count"])
+        assert c["degree_stats"]["sum"] == full["degree_stats"]["sum"]
+        ei, ea = edge_index_from_edges(c["edges"], c["dist"])
+        assert ei.dtype == np.int64 and np.array_equal(ei, full["edge_index"]) and np.array_equal(ea, full["edge_attr"])
+    # a denser slide after a sparse one: the hint is too small once, the call must still be exact
+    xy, ty, _ = synth.make_points(30_000, seed=9)
+    a = build_radius_graph(xy, r=20.0, types=ty, outputs="compact")
+    b = build_radius_graph(xy, r=120.0, types=ty, outputs="compact")
+    ref = ograph.radius_graph(xy, 120.0)
+    assert np.array_equal(b["edges"], ref["edges"]) and len(a["edges"]) < len(b["edges"])
+    t_ei, t_ea = edge_index_from_edges(torch.from_numpy(b["edges"]).cuda(), torch.from_numpy(b["dist"]).cuda())
+    assert t_ei.dtype == torch.int64 and np.array_equal(t_ei.cpu().numpy(), ref["edge_index"])
+    assert np.array_equal(t_ea.cpu().numpy(), ref["edge_attr"])
+
+
+def test_knn_graph_frame_is_cell_11(golden_graph):
+    import networkx as nx
+
+    from path_gene_multimodal_b200 import knn_graph_frame, to_networkx
+
+    coords, types = golden_graph["coords"][:400], golden_graph["types"][:400]
+    n = len(coords)
+    final_df = pd.DataFrame({
+        "nuc_id": [f"{i:08x}" for i in range(n)],
+        "centroid": [[float(y), float(x)] for x, y in coords],                 # HoverNeXt order: [y, x]
+        "type_name": [{1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}[int(t)] for t in types],
+    })
+    df, g = knn_graph_frame(final_df, k=5)
+    idx, dist = ograph.knn(np.ascontiguousarray(coords), 5)
+    assert df["knn_neighbors"].tolist() == idx.tolist()
+    assert df["knn_neighbor_distances"].tolist() == dist.tolist()
+    assert df["knn_neighbor_coords"].iloc[7] == [(float(coords[j, 0]), float(coords[j, 1])) for j in idx[7]]
+    assert df["type_id"].tolist() == [int(t) for t in types] and df["color"].iloc[0].startswith("tab:")
+    assert "centroid" in final_df.columns and "knn_neighbors" not in final_df.columns  # the input is not modified
+    G = to_networkx(g, df)
+    # the literal cell-11 loop (networkx has_edge / add_edge), keyed by nuc_id
+    ref = nx.Graph()
+    ids = final_df["nuc_id"].tolist()
+    ref.add_nodes_from(ids)
+    for i in range(n):
+        for j, d in zip(idx[i], dist[i]):
+            a, b = ids[i], ids[int(j)]
+            if ref.has_edge(a, b):
+                ref.edges[a, b]["weight"] = min(ref.edges[a, b]["weight"], float(d))
+            else:
+                ref.add_edge(a, b, weight=float(d))
+    assert set(G.nodes) == set(ref.nodes) and G.number_of_edges() == ref.number_of_edges()
+    assert all(G.edges[u, v]["weight"] == ref.edges[u, v]["weight"] for u, v in ref.edges)
+    assert G.nodes[ids[3]]["type_id"] == int(types[3]) and G.nodes[ids[3]]["pos"] == (float(coords[3, 0]), float(coords[3, 1]))
+
+
+def test_centroid_order_yx_and_array_cells():
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    tab = synth.make_table(500, seed=31, dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    ref = add_wsi_coords_to_nuclei(nuc, tiles)
+    fix = add_wsi_coords_to_nuclei(nuc, tiles, centroid_order="yx")
+    cen = np.array(nuc["centroid"].tolist())
+    assert np.array_equal(fix["centroid_x"], cen[:, 1]) and np.array_equal(fix["centroid_y"], cen[:, 0])
+    assert np.array_equal(fix["wsi_centroid_x"], fix["tile_x"] + cen[:, 1])
+    assert np.array_equal(fix["wsi_centroid_y"], fix["tile_y"] + cen[:, 0])
+    assert fix["wsi_polygon"].tolist() == ref["wsi_polygon"].tolist() and np.array_equal(fix["wsi_bbox_xmin"], ref["wsi_bbox_xmin"])
+    with pytest.raises(ValueError):
+        add_wsi_coords_to_nuclei(nuc, tiles, centroid_order="zz")
+    # cells as numpy arrays (what pd.read_parquet hands back for list columns)
+    arr = nuc.copy()
+    arr["polygon"] = [None if p is None else np.array([np.array(v) for v in p], dtype=object) for p in nuc["polygon"]]
+    arr["centroid"] = [np.array(c) for c in nuc["centroid"]]
+    arr["bounding_box"] = [np.array(b) for b in nuc["bounding_box"]]
+    arr.loc[arr.index[5], "polygon"] = None
+    nuc2 = nuc.copy()
+    nuc2.loc[nuc2.index[5], "polygon"] = None
+    got, want = add_wsi_coords_to_nuclei(arr, tiles), add_wsi_coords_to_nuclei(nuc2, tiles)
+    assert got["wsi_polygon"].tolist() == want["wsi_polygon"].tolist() and got["wsi_polygon"].iloc[5] is None
+    assert np.array_equal(got["wsi_centroid_x"], want["wsi_centroid_x"])
+
+
+def test_wsi_bbox_dtype_follows_each_axis():
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    tab = synth.make_table(64, seed=32, dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    tiles = tiles.copy()
+    tiles["x"] = tiles["x"].astype(np.float64)          # e.g. after a CSV round trip; y stays int64
+    out = add_wsi_coords_to_nuclei(nuc, tiles)
+    exp = omap.add_wsi_coords_to_nuclei_oracle(nuc, tiles)
+    for c in ("wsi_bbox_xmin", "wsi_bbox_ymin", "wsi_bbox_xmax", "wsi_bbox_ymax", "tile_x", "tile_y"):
+        assert out[c].dtype == exp[c].dtype, c
+        assert np.array_equal(out[c].to_numpy(), exp[c].to_numpy()), c
+
+
+def test_ring_length_is_float64_accurate_on_long_rings():
+    from path_gene_multimodal_b200 import polygon_morphology_table
+
+    rng = np.random.default_rng(8)
+    rings = []
+    for nv in (50_000, 6_000, 900, 33, 5):
+        t = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        rad = 4000.0 * (1.0 + 0.3 * np.sin(7 * t)) + rng.uniform(-3, 3, nv)
+        rings.append(np.round(np.stack([20000 + rad * np.cos(t), 15000 + rad * np.sin(t)], axis=1) * 2) / 2)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in rings])]).astype(np.int32)
+    xy = np.concatenate(rings)
+    tab = polygon_morphology_table(xy, poly_off=off)
+    ref = omorph.polygon_features_csr(off, xy)
+    np.testing.assert_allclose(tab["perimeter_px"], ref["perimeter"], rtol=1e-6)   # float32 output of a float64 sum
+    np.testing.assert_allclose(tab["area_px2"], ref["area"], rtol=1e-6)
+    np.testing.assert_allclose(tab["centroid_x"], ref["centroid_x"], rtol=1e-9)
+
+
+def test_c3_parity_at_250k_polygons(engine):
+    n = 250_000
+    off, xy = synth.make_polygons(n, synth.SEEDS["C3"], v_fixed=32)
+    res = engine.map_morph(torch.from_numpy(off).cuda(), torch.from_numpy(xy).cuda(), write_polygons=False, extra=True)
+    ref = omorph.polygon_features_csr(off, xy)
+    for name, key in (("area", "area"), ("perimeter", "perimeter"), ("circularity", "circularity"),
+                      ("major_axis", "major_axis_length")):
+        np.testing.assert_allclose(res[name].cpu().numpy(), ref[key], rtol=1e-5, err_msg=name)
+    np.testing.assert_allclose(res["minor_axis"].cpu().numpy(), ref["minor_axis_length"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(res["eccentricity"].cpu().numpy(), ref["eccentricity"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(res["centroid_x"].cpu().numpy(), ref["centroid_x"], rtol=1e-9)
+
+
+def test_two_engines_in_one_process_share_nothing():
+    # K1's shared-memory opt-in is remembered per handle (it used to be a process-wide static): a second handle -
+    # on another device when there is one - must launch the float64 kernel (67 KB of dynamic shared memory) too
+    from path_gene_multimodal_b200.engine import Engine
+
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    tab = synth.make_table(3000, seed=33, dtype=np.float64)
+    ref = omorph.polygon_features_csr(tab.poly_off, tab.poly_xy)
+    for d in devs:
+        eng = Engine(d)
+        with torch.cuda.device(d):
+            res = eng.map_morph(torch.from_numpy(tab.poly_off).cuda(d), torch.from_numpy(tab.poly_xy).cuda(d), write_polygons=False)
+            np.testing.assert_allclose(res["area"].cpu().numpy(), ref["area"], rtol=1e-5)
+        eng.close()
