@@ -5,13 +5,22 @@ a 1M-nucleus synthetic WSI (BASELINE.json configs[1], "C2"), per GPU, weak-scale
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one slide:
-  pg_grid_build (histogram, look-back scan, counting-sort scatter) -> pg_radius_count (one neighbourhood walk with
-  fused neighbour-type counts, then the row pass: row_ptr scan + degree statistics) -> pg_radius_fill (gather of
-  the parked entries: edges i<j, float32 distances).
-`value`    : inputs resident in HBM, device time from CUDA events, L2 flushed between steps.
-`e2e`      : the public call build_radius_graph(host coords, ...) -> host arrays (H2D + kernels + D2H).
-`roofline` : the dominant kernel, timed inside the library with CUDA events on its own stream.
-`cpu_baseline` / `--impl reference`: the notebook's scipy path (oracle/graph.py) on the host cores.
+  pg_grid_build (histogram, look-back scan, counting-sort scatter) -> pg_radius_graph (one neighbourhood walk with
+  fused neighbour-type counts, then the row pass: row_ptr scan + degree statistics + gather of the parked entries:
+  edges i<j, float32 distances).
+`value`    : inputs resident in HBM, device time from CUDA events, L2 flushed between steps. The outputs are
+             pre-sized (capacity = 1.25 E from one exact pass before the timed region), so a step is one enqueue with
+             no host read; a caller who does not know E takes count -> total -> fill (one host sync, `e2e` below).
+`e2e`      : the public call build_radius_graph(host coords, ..., outputs="compact") -> host arrays (H2D + kernels +
+             D2H); `e2e_notebook` is the same call with the notebook's int64 edge_index / edge_attr tensors.
+`roofline` : SURVEY 8(d) bytes of the step (48 N + 8 E_dir) over the dominant kernel's launch time (CUDA events
+             inside the library, on its own stream); `roofline_step` the same bytes over the whole step;
+             `roofline_sweep` the step at 250 k / 1 M / 4 M / 16 M nuclei.
+`stages`   : other hot-path stages on one GPU and, with every --gpus N, the two multi-GPU workloads under this
+             process's clock: `c5_strip_sharded` (20 M nuclei, k=16 and r=50, x-strips + NCCL halo all-gather,
+             strong scaling, checksums against the single-GPU build) and `c4_cohort` (64 x 500 k nuclei slides from
+             page-locked host tables, slide-parallel), plus the host-link ceiling measured with all ranks copying at once.
+`cpu_baseline` / `--impl reference`: the notebook's scipy path (oracle/graph.py) on the host cores, full 1 M slide.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -203,30 +212,27 @@ def cpu_sample(n, seed):
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU path on the SAME config as the GPU arm: the full 1M-nuclei slide every step."""
     if rank != 0:
         return
-    # calibrate on a small slide, then size the per-step sample so K+W steps fit in ~150 s
-    xy, types, _ = cpu_sample(50_000, 77)
-    t0 = time.perf_counter()
-    reference_pipeline(xy, types, RADIUS)
-    rate = 50_000 / (time.perf_counter() - t0)
-    budget = 150.0 / max(args.steps + args.warmup, 1)
-    n = int(min(N_NUCLEI, max(50_000, rate * budget * 0.8)))
+    n = N_NUCLEI
     xy, types, side = cpu_sample(n, 1002)
+    n_edges = None
     for _ in range(args.warmup):
-        reference_pipeline(xy, types, RADIUS)
+        n_edges = reference_pipeline(xy, types, RADIUS)[0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_pipeline(xy, types, RADIUS)
+        n_edges = reference_pipeline(xy, types, RADIUS)[0]
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = (f"{n} nuclei per step (same density, r=50px) of the 1M-nuclei slide; scipy cKDTree.query_ball_tree + "
-              "the notebook's i<j Python loop + numpy composition/degree")
+    sample = (f"the full {n}-nuclei slide (seed 1002, r=50px) every step; scipy cKDTree.query_ball_tree + "
+              "the notebook's i<j Python loop + np.linalg.norm + numpy composition/degree")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "nuclei/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nuclei_per_step": n, "radius_px": RADIUS, "n_types": N_TYPES},
+        "config": {"workload": WORKLOAD, "nuclei_per_gpu": n, "nuclei_per_step": n, "radius_px": RADIUS, "n_types": N_TYPES,
+                   "undirected_edges": int(n_edges) if n_edges is not None else None},
         "cpu_baseline": {"value": val, "unit": "nuclei/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": len(os.sched_getaffinity(0)),
                          "note": "query_ball_tree has no workers parameter and the edge loop is GIL-bound: 1 thread is all it can use"},
@@ -255,6 +261,245 @@ def kernel_bytes(name, n, e_und, cells):
     return table.get(name)
 
 
+class C2Slide:
+    """One slide of the C2 workload resident on the device, with pre-sized outputs: step() = one pass of the hot path."""
+
+    def __init__(self, eng, dev, n, seed):
+        import torch
+
+        from path_gene_multimodal_b200 import synth
+        from path_gene_multimodal_b200.engine import radius_cell
+
+        self.eng, self.n = eng, n
+        self.xy_np, self.types_np, side = synth.make_points(n, seed)
+        self.bounds = (0.0, 0.0, float(side), float(side))
+        self.d_xy = torch.from_numpy(self.xy_np).to(dev)
+        self.d_ty = torch.from_numpy(self.types_np).to(dev)
+        self.cell = radius_cell(RADIUS)
+        eng.grid_build(self.d_xy, self.d_ty, None, self.cell, self.bounds)
+        g0 = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_edges=True)   # exact pass: E for the byte counts
+        self.e_und = int(g0["total"])
+        info = eng.grid_info()
+        self.cells = info["nx"] * info["ny"]
+        self.cap = int(self.e_und * 1.25) + 1024
+        self.out = {}
+
+    def step(self):
+        self.eng.grid_build(self.d_xy, self.d_ty, None, self.cell, self.bounds)
+        self.out = self.eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True,
+                                         capacity=self.cap, out=self.out)
+
+
+def timed_steps(fn, flush, steps, warmup):
+    """CUDA-event time of each of `steps` calls of fn, the L2 flushed (512 MB written) before every one."""
+    import torch
+
+    for _ in range(warmup):
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def link_ceiling(dev, dist, mb=64, reps=8):
+    """Pinned host <-> device copies with EVERY rank copying at the same time (one cudaMemcpyAsync per buffer): what
+    the host's PCIe / memory system gives each GPU when all of them are fed at once. GB/s per rank."""
+    import torch
+
+    from path_gene_multimodal_b200 import _host
+
+    nb = mb * 1000 * 1000
+    h_in = torch.from_numpy(_host.pinned_empty((nb,), np.uint8))
+    h_out = torch.from_numpy(_host.pinned_empty((nb,), np.uint8))
+    d_a = torch.empty(nb, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nb, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(dev)
+    out = {}
+    for name in ("h2d", "d2h", "both"):
+        for i in range(2):  # untimed
+            d_a.copy_(h_in, non_blocking=True)
+            h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        side.wait_event(e0)
+        for _ in range(reps):
+            if name in ("h2d", "both"):
+                d_a.copy_(h_in, non_blocking=True)
+            if name == "d2h":
+                h_out.copy_(d_b, non_blocking=True)
+            if name == "both":
+                with torch.cuda.stream(side):
+                    h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out[name + "_GBs_per_rank"] = nb * reps * (2 if name == "both" else 1) / ms / 1e6
+    out["buffer_MB"] = mb
+    return out
+
+
+def checksum_edges(e):
+    return int((e[:, 0] * 1000003 + e[:, 1]).sum().item()) if e.numel() else 0
+
+
+def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=2):
+    """BASELINE config 5: one 20M-nuclei slide, radius r=50 graph and kNN k=16 + undirected union, strip-sharded over
+    the ranks (equal-count x-strips, all-to-all partition of the row-partitioned table, ONE halo all-gather per build).
+    Strong scaling: the slide is fixed. Device time (CUDA events, max over ranks) of partition / radius / kNN builds;
+    order-independent checksums of every output are compared with the single-GPU build of the whole slide (rank 0)."""
+    import torch
+
+    from path_gene_multimodal_b200 import sharding, synth
+    from path_gene_multimodal_b200.engine import default_knn_cell, radius_cell
+
+    xy, ty, side = synth.make_points(n, synth.SEEDS["C5"])
+    bounds = (0.0, 0.0, float(side), float(side))
+    comm = sharding.TorchComm() if world > 1 else sharding.LocalComm()
+    rows = slice(rank * n // world, (rank + 1) * n // world)           # the table starts row-partitioned
+    l_xy, l_ty = torch.from_numpy(xy[rows]).to(dev), torch.from_numpy(ty[rows]).to(dev)
+    l_gid = torch.arange(rows.start, rows.stop, dtype=torch.int32, device=dev)
+
+    def timed(make):
+        best, res = None, None
+        for i in range(reps + 1):                                          # run 0 is untimed (allocations)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = sharding.run(make(), comm)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if dist is not None:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            if i > 0:
+                best = ms if best is None else min(best, ms)
+        return res, best
+
+    out = {"nuclei": n, "k": k, "radius_px": RADIUS, "world": world}
+    if world > 1:
+        edges, t_edges = timed(lambda: sharding.equal_count_edges(l_xy[:, 0].contiguous(), world, 0.0, float(side)))
+        part, t_part = timed(lambda: sharding.partition_by_strips(eng, l_xy, l_ty, l_gid, edges, rank, world))
+        s_xy, s_ty, s_gid = part
+        strip = sharding.strips_from_edges(edges)[rank]
+        out["partition_ms"] = t_edges + t_part
+    else:
+        s_xy, s_ty, s_gid = l_xy, l_ty, l_gid
+        strip = sharding.Strip(0.0, float(side), True, True)
+        out["partition_ms"] = 0.0
+    del l_xy, l_ty
+    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, RADIUS, strip, rank, world, bounds=bounds))
+    sums = {"radius_edges": int(rg["edges"].shape[0]), "radius_edge_hash": checksum_edges(rg["edges"]),
+            "radius_degree_hash": int(((s_gid.long() + 1) * rg["degree"].long()).sum().item()),
+            "radius_nbr_hash": int(((s_gid.long() + 1)[:, None] * rg["nbr_count"].long()).sum().item())}
+    del rg
+    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds))
+    slot = torch.arange(1, k + 1, device=dev, dtype=torch.int64)
+    sums.update({"knn_idx_hash": int((((s_gid.long() + 1)[:, None] * 31 + slot[None, :]) * (kg["knn_idx"].long() + 1)).sum().item()),
+                 "knn_dist_hash": int(((kg["dist"].view(torch.int64) >> 11) * slot[None, :]).sum().item()),
+                 "union_edges": int(kg["edges"].shape[0]), "union_edge_hash": checksum_edges(kg["edges"]),
+                 "union_weight_hash": int((kg["weight"].view(torch.int64) >> 11).sum().item()),
+                 "union_degree_hash": int(((s_gid.long() + 1) * kg["degree"].long()).sum().item())})
+    halo, ghosts = kg["halo"], kg["n_ghost"]
+    del kg
+    torch.cuda.empty_cache()
+    keys = sorted(sums)
+    vec = torch.tensor([sums[q] for q in keys], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)        # int64 sums wrap the same way on every world size
+    total = dict(zip(keys, vec.tolist()))
+    out.update({"radius_ms": t_rad, "knn_union_ms": t_knn, "total_ms": out["partition_ms"] + t_rad + t_knn,
+                "nuclei_per_s": n / ((t_rad + t_knn) / 1e3), "halo_px": halo, "ghosts_rank0": ghosts,
+                "radius_edges": total["radius_edges"], "union_edges": total["union_edges"],
+                "timing": "CUDA events around each sharded build (halo exchange, host reads of counts included), max over ranks, best of %d" % reps})
+    if rank == 0:
+        if world > 1:
+            # single-GPU build of the whole slide: the checksums every world size must reproduce
+            d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+            gid = torch.arange(n, dtype=torch.int64, device=dev)
+            eng.grid_build(d_xy, d_ty, None, radius_cell(RADIUS), bounds)
+            ref = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_edges=True)
+            want = {"radius_edges": int(ref["edges"].shape[0]), "radius_edge_hash": checksum_edges(ref["edges"]),
+                    "radius_degree_hash": int(((gid + 1) * ref["degree"].long()).sum().item()),
+                    "radius_nbr_hash": int(((gid + 1)[:, None] * ref["nbr_count"].long()).sum().item())}
+            del ref
+            eng.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, k), bounds)
+            kn = eng.knn(k, dist_dtype=torch.float64)
+            want.update({"knn_idx_hash": int((((gid + 1)[:, None] * 31 + slot[None, :]) * (kn["knn_idx"].long() + 1)).sum().item()),
+                         "knn_dist_hash": int(((kn["dist"].view(torch.int64) >> 11) * slot[None, :]).sum().item())})
+            un = eng.knn_union(kn["knn_idx"], kn["dist"], types=d_ty, n_types=N_TYPES, symmetric_dist=True, hist_len=0)
+            want.update({"union_edges": int(un["edges"].shape[0]), "union_edge_hash": checksum_edges(un["edges"]),
+                         "union_weight_hash": int((un["edge_w"].view(torch.int64) >> 11).sum().item()),
+                         "union_degree_hash": int(((gid + 1) * un["degree"].long()).sum().item())})
+            del un, kn, d_xy, d_ty
+            torch.cuda.empty_cache()
+            bad = [q for q in keys if total[q] != want[q]]
+            out["bit_identical_to_single_gpu"] = not bad
+            if bad:
+                out["mismatch"] = bad
+        else:
+            out["bit_identical_to_single_gpu"] = True   # this IS the single-GPU build
+        out["checksums"] = {q: total[q] for q in ("radius_edge_hash", "union_edge_hash", "knn_idx_hash")}
+    return out
+
+
+def c4_stage(dev, local_rank, dist, rank, world, n_slides=64, n=500_000, lanes=2):
+    """BASELINE config 4: 64 slides x 500k nuclei from page-locked HOST tables, slide-parallel over the ranks
+    (sharding.assign_slides), `lanes` slides in flight per GPU. Device time between the first enqueue and the last
+    completion, max over ranks; the digest of all per-slide summaries must not depend on the number of GPUs."""
+    import torch
+
+    from path_gene_multimodal_b200 import cohort, sharding, synth
+
+    mine = sharding.assign_slides(n_slides, world, sizes=[n] * n_slides)[rank]
+    cache, tables = {}, {}
+    for sl in mine:
+        tables[sl] = cohort.pin_table(synth.make_cohort_slide(sl, n), cache)
+    runner = cohort.CohortRunner(local_rank, lanes=lanes)
+    runner.run(mine[:lanes], tables.__getitem__)                        # warm-up: allocations, first launches
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    res, ms = runner.run(mine, tables.__getitem__)
+    runner.close()
+    h2d = sum(cohort.table_bytes(tables[sl]) for sl in mine)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res)
+        res = {}
+        for d in gathered:
+            res.update(d)
+    assert sorted(res) == list(range(n_slides))
+    return {"slides": n_slides, "nuclei_per_slide": n, "world": world, "lanes": lanes, "ms": ms,
+            "nuclei_per_s": n_slides * n / (ms / 1e3), "ms_per_slide_per_gpu": ms / max(len(mine), 1),
+            "h2d_bytes_per_slide": h2d // max(len(mine), 1), "digest": cohort.cohort_checksum(res),
+            "note": "slides dealt from 4 base tables (synth.make_cohort_slide); every slide = H2D of its table + map + morphology "
+                    "+ kNN-8 union + radius-50 graph + summary read; CUDA events, max over ranks"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -269,34 +514,15 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
     from path_gene_multimodal_b200 import _host, build_radius_graph, synth
-    from path_gene_multimodal_b200.engine import get_engine, radius_cell
+    from path_gene_multimodal_b200.engine import get_engine
 
     eng = get_engine(local_rank)
     peak, peak_src = measured_peak()
     n = N_NUCLEI
-    xy_np, types_np, side = synth.make_points(n, synth.SEEDS["C2"] + rank)   # one slide per rank (weak scaling)
-    bounds = (0.0, 0.0, float(side), float(side))
-    # pinned host copies (e2e input) and device-resident copies (value)
-    h_xy = _host.pinned_empty((n, 2), np.float64); h_xy[...] = xy_np
-    h_ty = _host.pinned_empty((n,), np.int32); h_ty[...] = types_np
-    d_xy = torch.from_numpy(h_xy).to(dev)
-    d_ty = torch.from_numpy(h_ty).to(dev)
-    cell = radius_cell(RADIUS)
-
-    # exact-size pass once: sizes the reusable output buffers and gives E for the byte counts
-    eng.grid_build(d_xy, d_ty, None, cell, bounds)
-    g0 = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_edges=True)
-    e_und = int(g0["total"])
-    info = eng.grid_info()
-    cells = info["nx"] * info["ny"]
-    cap = int(e_und * 1.25) + 1024
-    out = {}
-
-    def step():
-        nonlocal out
-        eng.grid_build(d_xy, d_ty, None, cell, bounds)
-        out = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True, capacity=cap, out=out)
-
+    slide = C2Slide(eng, dev, n, synth.SEEDS["C2"] + rank)              # one slide per rank (weak scaling)
+    e_und, cells = slide.e_und, slide.cells
+    h_xy = _host.pinned_empty((n, 2), np.float64); h_xy[...] = slide.xy_np   # pinned host copies: the e2e input
+    h_ty = _host.pinned_empty((n,), np.int32); h_ty[...] = slide.types_np
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -305,29 +531,20 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step()
+    warm = max(args.warmup, 3)
+    timed_steps(slide.step, flush, 0, warm)
     eng.check_overflow()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = eng.launches
-    evs = []
     barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        evs.append((e0, e1))
+    step_ms = timed_steps(slide.step, flush, args.steps, 0)
     barrier()
     launches = eng.launches - l0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
     eng.check_overflow()
     total_ms = float(sum(step_ms))
-    assert int(out["row_ptr"][-1]) == e_und
+    assert int(slide.out["row_ptr"][-1]) == e_und
     if dist is not None:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -335,43 +552,75 @@ def run_ours(args, rank, world, local_rank):
     value = world * n * args.steps / (total_ms / 1e3)
 
     # ---- e2e: public host API, pinned host inputs, H2D + kernels + D2H inside the timed region
-    res = None
-    for _ in range(3):
-        res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=bounds, device=local_rank)
-    assert res["edges"].shape[0] == e_und
-    barrier()
-    e2e_steps = max(3, min(args.steps, 20))
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=bounds, device=local_rank)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    def e2e(outputs):
+        res = None
+        for _ in range(3):
+            res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=slide.bounds, device=local_rank, outputs=outputs)
+        assert res["edges"].shape[0] == e_und
+        barrier()
+        steps = max(3, min(args.steps, 20))
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = build_radius_graph(h_xy, r=RADIUS, types=h_ty, n_types=N_TYPES, bounds=slide.bounds, device=local_rank, outputs=outputs)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        wall = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if outputs == "compact":
+            cap = int(getattr(eng, "_radius_cap", e_und))   # the one-enqueue path copies its whole capacity (hint x 1.15) and cuts on the host
+            d2h = cap * (8 + 4) + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4 + 4
+        else:
+            d2h = res["edge_index"].nbytes + res["edge_attr"].nbytes + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4
+        return {"value": world * n * steps / (ms / 1e3), "unit": "nuclei/s", "h2d_bytes_per_step": int(h_xy.nbytes + h_ty.nbytes),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / steps, "wall_ms_per_step": wall / steps, "steps": steps}
+
+    e2e_c = e2e("compact")
+    e2e_c["api"] = ("path_gene_multimodal_b200.build_radius_graph(host coords, r, types, outputs='compact') -> host edges int32 [E,2] / "
+                    "dist float32 [E] / degree / nbr_count / degree_stats")
+    e2e_n = e2e("notebook")
+    e2e_n["api"] = "the same call with outputs='notebook': host edge_index int64 [2,2E] / edge_attr float32 [2E,1] / degree / nbr_count"
     clocks = sampler.stop()
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_val = world * n * e2e_steps / (e2e_ms / 1e3)
-    h2d = h_xy.nbytes + h_ty.nbytes
-    d2h = res["edge_index"].nbytes + res["edge_attr"].nbytes + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4
 
     line = {
-        "metric": METRIC, "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nuclei_per_gpu": n, "radius_px": RADIUS, "n_types": N_TYPES,
+        "config": {"workload": WORKLOAD, "nuclei_per_gpu": n, "nuclei_per_step": n, "radius_px": RADIUS, "n_types": N_TYPES,
                    "undirected_edges": e_und, "grid_cells": cells, "parallelism": f"slide-parallel x{world} (one slide per GPU, no data-path collective)",
-                   "l2": "512 MB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step, summed, max over ranks"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "nuclei/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps, "steps": e2e_steps,
-                "api": "path_gene_multimodal_b200.build_radius_graph(host coords, r, types) -> host edge_index/edge_attr/degree/nbr_count"},
-        "gpu_launches": int(launches),
+                   "l2": "512 MB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step, summed, max over ranks",
+                   "outputs": "pre-sized (capacity 1.25 E from one exact pass before the timed region): a step is one enqueue, no host read; "
+                              "callers without E take count -> total -> fill (see e2e)"},
+        "clocks": clocks, "e2e": e2e_c, "e2e_notebook": e2e_n, "gpu_launches": int(launches),
     }
+
+    # ---- host-link ceiling with every rank copying at once, then e2e as a fraction of it
+    link = link_ceiling(dev, dist)
+    floor_ms = (e2e_c["h2d_bytes_per_step"] / link["h2d_GBs_per_rank"] + e2e_c["d2h_bytes_per_step"] / link["d2h_GBs_per_rank"]) / 1e6
+    line["host_link"] = dict(link, e2e_copy_floor_ms=floor_ms, e2e_frac_of_copy_floor=floor_ms / e2e_c["ms_per_step"],
+                             note="pinned cudaMemcpyAsync, all ranks at once; e2e_copy_floor = this step's H2D + D2H bytes at those rates, "
+                                  "one after the other as the call issues them")
+
+    # ---- the two multi-GPU workloads of BASELINE configs[3..4] under this process's clock
+    stages_mg = {}
+    del flush
+    torch.cuda.empty_cache()
+    try:
+        stages_mg["c5_strip_sharded"] = c5_stage(eng, dev, dist, rank, world)
+    except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
+        stages_mg["c5_strip_sharded"] = {"error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.empty_cache()
+    try:
+        stages_mg["c4_cohort"] = c4_stage(dev, local_rank, dist, rank, world)
+    except Exception as exc:  # noqa: BLE001
+        stages_mg["c4_cohort"] = {"error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.empty_cache()
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     if rank == 0:
         # ---- per-kernel timing inside the library (CUDA events on the launching stream), L2 flushed
@@ -379,7 +628,7 @@ def run_ours(args, rank, world, local_rank):
         reps = 10
         for _ in range(reps):
             flush.zero_()
-            step()
+            slide.step()
         recs = eng.profile_records()
         eng.profile(False)
         per = {}
@@ -388,28 +637,41 @@ def run_ours(args, rank, world, local_rank):
         avg = {k: sum(v) / len(v) for k, v in per.items()}
         share = {k: sum(v) / reps for k, v in per.items()}  # ms per step
         dom = max(share, key=share.get)
-        kb = kernel_bytes(dom, n, e_und, cells)
         step_sum = sum(share.values())
-        line["kernels_ms_per_step"] = {k: round(v, 5) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}
-        if kb is not None:
-            ach = kb / (avg[dom] / 1e3) / 1e9
-            traffic, traffic_src = ncu_traffic(dom)
-            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": traffic, "traffic_source": traffic_src,
-                                "algorithmic_bytes_per_launch": int(kb), "avg_launch_ms": avg[dom],
-                                "share_of_step": share[dom] / step_sum, "peak_source": peak_src,
-                                "note": "the kernel is L1 / issue bound, not DRAM bound (ncu r1h: L1TEX 77 %, issue 62 %, DRAM 10 % of peak); "
-                                        "its cold-cache DRAM traffic is below the algorithmic bytes because the parked entries and most "
-                                        "of the meta records stay in L2"}
         alg = algorithmic_bytes(n, 2 * e_und)
+        line["kernels_ms_per_step"] = {k: round(v, 5) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}
+        ach = alg / (avg[dom] / 1e3) / 1e9
+        traffic, traffic_src = ncu_traffic(dom)
+        kb = kernel_bytes(dom, n, e_und, cells)
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": avg[dom],
+                            "share_of_step": share[dom] / step_sum, "peak_source": peak_src,
+                            "kernel_own_bytes_per_launch": int(kb) if kb else None,
+                            "kernel_own_frac": (kb / (avg[dom] / 1e3) / 1e9 / peak) if kb else None,
+                            "note": "SURVEY 8(d): achieved = the step's algorithmic bytes (48 N + 8 E_dir: every boundary array once) over the "
+                                    "dominant kernel's launch time; kernel_own_* = that kernel's own inputs + outputs (intermediates included) "
+                                    "over the same time. The kernel is issue / L2-latency bound (ncu: ~60 % issue, DRAM 10 %), not DRAM bound"}
         ach_step = alg / (total_ms / args.steps / 1e3) / 1e9
         line["roofline_step"] = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
                                  "algorithmic_bytes_per_step": int(alg), "bytes_per_nucleus": alg / n,
                                  "note": "SURVEY 8(d): 48 N + 8 E_dir over the whole step (all kernels + launch gaps)"}
-        line["stages"] = other_stages(eng, dev, flush, peak)
+        # ---- the same step at other slide sizes (same density): where the fraction saturates
+        sweep = {}
+        for nn in (250_000, 1_000_000, 4_000_000, 16_000_000):
+            sl = slide if nn == n else C2Slide(eng, dev, nn, synth.SEEDS["C2"])
+            ms = statistics.median(timed_steps(sl.step, flush, 8, 3))
+            a = algorithmic_bytes(nn, 2 * sl.e_und)
+            sweep[str(nn)] = {"ms_per_step": ms, "undirected_edges": sl.e_und, "nuclei_per_s": nn / ms * 1e3,
+                              "achieved_GBs": a / ms / 1e6, "frac": a / ms / 1e6 / peak}
+            if sl is not slide:
+                del sl
+                torch.cuda.empty_cache()
+        line["roofline_sweep"] = sweep
+        line["stages"] = dict(other_stages(eng, dev, flush, peak), **stages_mg)
         if world == 1:
             t0 = time.perf_counter()
-            ne, _, _ = reference_pipeline(xy_np, types_np, RADIUS)
+            ne, _, _ = reference_pipeline(slide.xy_np, slide.types_np, RADIUS)
             dt = time.perf_counter() - t0
             assert ne == e_und
             line["cpu_baseline"] = {

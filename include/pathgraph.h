@@ -248,6 +248,23 @@ int pg_halo_unpack(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_
                    int32_t* gid, int32_t n_base, int32_t capacity, int32_t* count_out,
                    pg_stream stream);
 
+/* Device-side exchange steps of the strip sharding (csrc/pg_shard.cu).
+ * pg_strip_partition: out = the n points as 24-byte records grouped by owning strip (strip q owns x in
+ *   [inner_edges[q-1], inner_edges[q]); inner_edges host f64 [n_strips-1] ascending), input order kept inside every
+ *   strip; totals int32 [n_strips] device = records per strip (the send counts of the all-to-all).
+ * pg_halo_unpack_multi: pg_halo_unpack for n_ranges x-ranges (host f64 [n_ranges][2], appended in that order behind
+ *   slot n_base) in one enqueue; counts_out int32 [n_ranges] device.
+ * pg_gid_maps: id_map int32 [n_ids] = row of every global id among the first n_rows points (-1 elsewhere) and
+ *   type_by_gid int32 [n_ids] = type of every id among all n points (0 elsewhere); either may be NULL. */
+int pg_strip_partition(pg_handle* h, int32_t n, const double* xy, const int32_t* type, const int32_t* gid,
+                       int32_t n_strips, const double* inner_edges, pg_halo_rec* out, int32_t* totals,
+                       pg_stream stream);
+int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, int32_t skip_begin,
+                         int32_t skip_end, int32_t n_ranges, const double* ranges, double* xy, int32_t* type,
+                         int32_t* gid, int32_t n_base, int32_t capacity, int32_t* counts_out, pg_stream stream);
+int pg_gid_maps(pg_handle* h, int32_t n, int32_t n_rows, const int32_t* gid, const int32_t* type, int32_t n_ids,
+                int32_t* id_map, int32_t* type_by_gid, pg_stream stream);
+
 /* ---- K11: graph statistics the reference names (README.md:133-136 "cell-cell interaction patterns",
  * "degree, clustering, centrality") over a symmetric CSR with ascending rows (K6 / K7 output).
  * triangles int32 [n] (through node i), coeff float64 [n] = 2 T / (d (d - 1)), 0 for d < 2 (networkx.clustering);

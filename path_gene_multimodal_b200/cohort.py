@@ -1,0 +1,120 @@
+"""Slide-parallel cohort runs (BASELINE config 4): every slide is the reference's one-slide job
+(/root/reference/main.py:322-335) - its nuclei table goes from HOST arrays through the whole hot path on one GPU:
+H2D of the table, tile->WSI map + polygon morphology, kNN k=8 + undirected union + i<j edges + composition, radius
+graph r=50 px + composition + degree statistics, and a small per-slide summary back.  The graphs stay on the GPU
+that built them.  ``lanes`` slides are in flight per GPU, each on its own stream / handle / host thread, so the
+H2D of one slide overlaps the kernels and the host reads of the other.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import _host
+from .engine import Engine, default_knn_cell, get_engine, radius_cell
+
+TABLE_FIELDS = ("poly_off", "poly_xy", "nuc_tile", "tile_x", "tile_y", "centroid", "bbox", "types")
+
+
+def pin_table(tab, cache: dict | None = None):
+    """Page-lock the arrays of a synth.NucleiTable in place (as a loader reading Parquet straight into pinned buffers
+    would leave them); arrays shared between tables are pinned once (``cache`` maps id(array) -> pinned copy)."""
+    cache = {} if cache is None else cache
+    for name in TABLE_FIELDS:
+        a = getattr(tab, name)
+        hit = cache.get(id(a))
+        if hit is None:
+            buf = _host.pinned_empty(a.shape, a.dtype)
+            buf[...] = a
+            hit = cache[id(a)] = (buf, a)      # keep the source alive: id() stays unique
+        setattr(tab, name, hit[0])
+    return tab
+
+
+def table_bytes(tab) -> int:
+    return int(sum(getattr(tab, name).nbytes for name in TABLE_FIELDS))
+
+
+def process_slide(eng: Engine, tab, k: int = 8, r: float = 50.0, n_types: int = 5) -> dict:
+    """One slide, host table in, summary out (runs on the current stream of the engine's device)."""
+    dev = eng.device
+    n = tab.n
+    side_px = float(tab.n_tiles_side * 508)
+    vt = np.float32 if tab.poly_xy.dtype == np.float32 else np.float64
+    t_off = _host.to_device(tab.poly_off, np.int32, dev)
+    t_xy = _host.to_device(tab.poly_xy, vt, dev)
+    t_tile = _host.to_device(tab.nuc_tile, np.int32, dev)
+    t_tx, t_ty = _host.to_device(tab.tile_x, np.int32, dev), _host.to_device(tab.tile_y, np.int32, dev)
+    t_cen, t_bb = _host.to_device(tab.centroid, np.float64, dev), _host.to_device(tab.bbox, np.int32, dev)
+    t_types = _host.to_device(tab.types, np.int32, dev)
+    mm = eng.map_morph(t_off, t_xy, t_tile, t_tx, t_ty, t_cen, t_bb, write_polygons=True)
+    wsi = mm["wsi_centroid"]
+    bnd = (0.0, 0.0, side_px, side_px)
+    eng.grid_build(wsi, t_types, None, default_knn_cell(n, side_px ** 2, k), bnd)
+    kn = eng.knn(k, dist_dtype=torch.float32)
+    un = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=n_types, symmetric_dist=True)
+    eng.grid_build(wsi, t_types, None, radius_cell(r), bnd)
+    rg = eng.radius_graph(r, upper=True, n_types=n_types, want_dist32=True, want_edges=True)
+    st = eng.decode_stats(rg["stats"], rg["hist"])
+    # small per-slide summary (what a cohort table would keep); ONE device-to-host read synchronises the slide
+    def edge_hash(e):
+        return (e[:, 0] * 1000003 + e[:, 1]).sum() if e.numel() else torch.zeros((), dtype=torch.int64, device=dev)
+
+    sums = torch.stack([mm["area"].double().sum().reshape(1).view(torch.int64)[0], un["degree"].sum(), rg["nbr_count"].sum(),
+                        edge_hash(un["edges"]), edge_hash(rg["edges"])]).tolist()
+    return {"knn_edges": int(un["edges"].shape[0]), "radius_edges": int(rg["edges"].shape[0]),
+            "area_sum": float(np.int64(sums[0]).view(np.float64)), "knn_deg_sum": int(sums[1]), "nbr_sum": int(sums[2]),
+            "knn_edge_hash": int(sums[3]), "radius_edge_hash": int(sums[4]), "radius_mean_degree": st["mean"]}
+
+
+class CohortRunner:
+    """``lanes`` engines + streams on one device; ``run(slides, get_table)`` processes the slides and returns
+    ({slide: summary}, device milliseconds between the first enqueue and the last completion)."""
+
+    def __init__(self, device: int, lanes: int = 2):
+        self.device = int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.lanes = max(1, int(lanes))
+        self.engines = [get_engine(self.device)] + [Engine(self.device) for _ in range(self.lanes - 1)]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.lanes)]
+
+    def close(self):
+        for e in self.engines[1:]:
+            e.close()
+
+    def _lane(self, lane: int, slides, get_table, start_event):
+        torch.cuda.set_device(self.device)
+        out = {}
+        with torch.cuda.stream(self.streams[lane]):
+            self.streams[lane].wait_event(start_event)
+            for s in slides:
+                out[s] = process_slide(self.engines[lane], get_table(s))
+        return out
+
+    def run(self, slides, get_table):
+        torch.cuda.set_device(self.device)
+        main = torch.cuda.current_stream(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        slides = list(slides)
+        with ThreadPoolExecutor(max_workers=self.lanes) as ex:
+            parts = list(ex.map(lambda lane: self._lane(lane, slides[lane::self.lanes], get_table, e0), range(self.lanes)))
+        for st in self.streams:
+            main.wait_stream(st)
+        e1.record(main)
+        e1.synchronize()
+        merged = {}
+        for d in parts:
+            merged.update(d)
+        return merged, e0.elapsed_time(e1)
+
+
+def cohort_checksum(results: dict) -> dict:
+    """Digest of per-slide summaries that does not depend on the number of GPUs / lanes (slides in id order)."""
+    vals = [results[s] for s in sorted(results)]
+    mask = (1 << 63) - 1
+    return {"edges": int(sum(v["knn_edges"] * 3 + v["radius_edges"] * 5 + v["knn_deg_sum"] + v["nbr_sum"] for v in vals)),
+            "edge_hash": int(sum(v["knn_edge_hash"] + v["radius_edge_hash"] for v in vals) & mask),
+            "area_sum": float(sum(v["area_sum"] for v in vals))}

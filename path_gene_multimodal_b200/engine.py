@@ -531,6 +531,37 @@ class Engine:
                                             int(n_base), int(xy.shape[0]), self._p(count, torch.int32, "count"), self._stream()))
         return count
 
+    def strip_partition(self, xy, types, gid, inner_edges):
+        """Records (24 B: x, y, gid, type) of all points grouped by owning strip + per-strip totals (pg_strip_partition)."""
+        n = int(xy.shape[0])
+        world = len(inner_edges) + 1
+        recs = self._empty((max(n, 1), 3), torch.float64)
+        totals = self._empty((world,), torch.int32)
+        e = (C.c_double * max(world - 1, 1))(*[float(v) for v in inner_edges])
+        self._check(self.lib.pg_strip_partition(self._h, n, self._p(xy, torch.float64, "xy"), self._p(types, torch.int32, "types"),
+                                                self._p(gid, torch.int32, "gid"), world, e, C.c_void_p(recs.data_ptr()),
+                                                self._p(totals, torch.int32, "totals"), self._stream()))
+        return recs[:n], totals
+
+    def halo_unpack_multi(self, recs, n_recs, skip_begin, skip_end, ranges, xy, types, gid, n_base):
+        """Append the records of several x-ranges behind slot n_base; returns the device counts int32 [len(ranges)]."""
+        counts = self._empty((len(ranges),), torch.int32)
+        flat = (C.c_double * (2 * len(ranges)))(*[float(v) for ab in ranges for v in ab])
+        self._check(self.lib.pg_halo_unpack_multi(self._h, C.c_void_p(recs.data_ptr()), int(n_recs), int(skip_begin), int(skip_end),
+                                                  len(ranges), flat, self._p(xy, torch.float64, "xy"),
+                                                  self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
+                                                  int(n_base), int(xy.shape[0]), self._p(counts, torch.int32, "counts"), self._stream()))
+        return counts
+
+    def gid_maps(self, gid, types, n_rows, n_ids, want_id_map=True, want_types=True):
+        """Dense id -> row (first n_rows points) and id -> type (all points) maps over n_ids global ids (pg_gid_maps)."""
+        id_map = self._empty((n_ids,), torch.int32) if want_id_map else None
+        tbg = self._empty((n_ids,), torch.int32) if want_types else None
+        self._check(self.lib.pg_gid_maps(self._h, int(gid.numel()), int(n_rows), self._p(gid, torch.int32, "gid"),
+                                         self._p(types, torch.int32, "types"), int(n_ids), self._p(id_map, torch.int32, "id_map"),
+                                         self._p(tbg, torch.int32, "type_by_gid"), self._stream()))
+        return id_map, tbg
+
     def exclusive_scan(self, x):
         n = int(x.numel())
         out = self._empty((n + 1,), torch.int32)

@@ -104,20 +104,17 @@ def equal_count_edges(x: torch.Tensor, world: int, x_min: float, x_max: float, b
     return np.asarray(edges, dtype=np.float64)
 
 
-def partition_by_strips(xy: torch.Tensor, types: torch.Tensor, gid: torch.Tensor, edges, rank: int, world: int):
+def partition_by_strips(eng, xy: torch.Tensor, types: torch.Tensor, gid: torch.Tensor, edges, rank: int, world: int):
     """Generator: move every point to the rank owning its strip (one all-to-all of 24-byte records).
 
-    Used when the table is not born partitioned; returns (xy, types, gid) of this rank's strip."""
-    inner = torch.as_tensor(np.asarray(edges[1:-1], dtype=np.float64), device=xy.device)
-    owner = torch.bucketize(xy[:, 0].contiguous(), inner, right=True)
-    order = torch.argsort(owner, stable=True)
-    counts = torch.bincount(owner, minlength=world).to(torch.int64)
-    rec = torch.empty((xy.shape[0], 3), dtype=torch.float64, device=xy.device)
-    rec[:, :2] = xy
-    rec[:, 2] = torch.stack([gid.to(torch.int32), types.to(torch.int32)], dim=1).contiguous().view(torch.float64).reshape(-1)
-    rec = rec[order].contiguous()
-    recv_counts = yield ("all_to_all_counts", counts)
-    got = yield ("all_to_all_v", rec, counts.tolist(), recv_counts.tolist())
+    Used when the table is not born partitioned; returns (xy, types, gid) of this rank's strip. The send buffer -
+    records grouped by destination strip, input order kept - and the send counts come from pg_strip_partition
+    (count / scan / place kernels); ONE host read (send + receive counts together) sizes the exchange."""
+    recs, totals = eng.strip_partition(xy, types, gid, [float(e) for e in edges[1:-1]])
+    send_counts = totals.to(torch.int64)
+    recv_counts = yield ("all_to_all_counts", send_counts)
+    both = torch.stack([send_counts, recv_counts]).tolist()   # the host synchronisation of this exchange
+    got = yield ("all_to_all_v", recs.contiguous(), both[0], both[1])
     meta = got[:, 2].contiguous().view(torch.int32).reshape(-1, 2)
     return got[:, :2].contiguous(), meta[:, 1].contiguous(), meta[:, 0].contiguous()
 
@@ -126,7 +123,9 @@ def partition_by_strips(xy: torch.Tensor, types: torch.Tensor, gid: torch.Tensor
 def exchange_halo(eng, xy, types, gid, strip: Strip, width: float, rank: int, world: int):
     """Generator: pack this rank's edge points (pg_halo_pack), all-gather counts then the padded payload.
 
-    Returns (all_recs float64 [world * max_cnt, 3] (24-byte records, padding rows are NaN), max_cnt)."""
+    Returns (all_recs float64 [world * max_cnt, 3] (24-byte records, padding rows are NaN), max_cnt). One host
+    read per exchange: the gathered counts (they size the padded payload); the pack kernel cannot overflow, its
+    capacity is the number of points."""
     n = int(xy.shape[0])
     lo_edge = -_INF if strip.is_first else strip.lo + width
     hi_edge = _INF if strip.is_last else strip.hi - width
@@ -135,7 +134,6 @@ def exchange_halo(eng, xy, types, gid, strip: Strip, width: float, rank: int, wo
     recs, count = eng.halo_pack(xy, types, gid, lo_edge, hi_edge, capacity=max(n, 1))
     counts = yield ("all_gather", count)                    # [world, 1] int32
     counts = counts.reshape(-1).tolist()                    # host sync: sizes the padded payload
-    eng.check_overflow()
     max_cnt = max(max(counts), 1)
     payload = torch.full((max_cnt, 3), float("nan"), dtype=torch.float64, device=xy.device)
     payload[:counts[rank]] = recs[:counts[rank]]
@@ -145,7 +143,8 @@ def exchange_halo(eng, xy, types, gid, strip: Strip, width: float, rank: int, wo
 
 def merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges):
     """Append to the owned points the gathered records whose x lies in each [a, b) of ``ranges`` (in that
-    order), skipping this rank's own contribution. Returns (xy_all, types_all, gid_all, [count per range])."""
+    order), skipping this rank's own contribution. Returns (xy_all, types_all, gid_all, [count per range]).
+    One enqueue for all ranges (pg_halo_unpack_multi) and one host read of the counts."""
     n = int(xy.shape[0])
     n_recs = int(all_recs.shape[0])
     cap = n + n_recs
@@ -155,16 +154,11 @@ def merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges):
     xy_all[:n] = xy
     ty_all[:n] = types
     gid_all[:n] = gid
-    base, got = n, []
-    for a, b in ranges:
-        if n_recs == 0 or not (b > a):
-            got.append(0)
-            continue
-        cnt = eng.halo_unpack(all_recs, n_recs, rank * max_cnt, (rank + 1) * max_cnt, a, b, xy_all, ty_all, gid_all, base)
-        c = int(cnt.item())
-        got.append(c)
-        base += c
-    eng.check_overflow()
+    if n_recs == 0:
+        return xy_all[:n], ty_all[:n], gid_all[:n], [0] * len(ranges)
+    counts = eng.halo_unpack_multi(all_recs, n_recs, rank * max_cnt, (rank + 1) * max_cnt, ranges, xy_all, ty_all, gid_all, n)
+    got = counts.tolist()                                   # host sync: the grid build needs the point count
+    base = n + sum(got)
     return xy_all[:base], ty_all[:base], gid_all[:base], got
 
 
@@ -188,12 +182,25 @@ def sharded_radius_graph(eng, xy, types, gid, r: float, strip: Strip, rank: int,
     return g
 
 
+def _strip_bounds(strip: Strip, width: float, bounds):
+    """Bounding box of a strip + halo when the slide's box is known: no reduction over the points, no host read."""
+    if bounds is None:
+        return None
+    x0, y0, x1, y1 = (float(v) for v in bounds)
+    lo = x0 if strip.is_first else max(x0, strip.lo - width)
+    hi = x1 if strip.is_last else min(x1, strip.hi + width)
+    return (lo, y0, max(hi, lo), y1)
+
+
 def sharded_knn_graph(eng, xy, types, gid, k: int, strip: Strip, rank: int, world: int, n_global: int,
                       n_types: int = 5, union: bool = True, h0: float | None = None, density: float | None = None,
                       bounds=None, max_rounds: int = 8):
     """Generator: kNN lists (and the undirected union / composition) for this rank's strip, bit-exact with
     the single-GPU result. The halo width starts at ``h0`` (default 3 sqrt(k / (pi rho))) and doubles until
-    every rank's completeness test passes (all-reduced), so a too-small guess costs a retry, never an error."""
+    every rank's completeness test passes (all-reduced), so a too-small guess costs a retry, never an error.
+
+    ``bounds`` = (x0, y0, x1, y1) of the whole slide lets every rank derive its grid box without touching the
+    points. Host reads per round: the gathered halo counts, the unpack counts, the all-reduced verdict."""
     from .engine import default_knn_cell
 
     n_own = int(xy.shape[0])
@@ -212,25 +219,28 @@ def sharded_knn_graph(eng, xy, types, gid, k: int, strip: Strip, rank: int, worl
         xy_all, ty_all, gid_all, got = merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges)
         n_q = n_own + (got[0] if union else 0)
         n_all = int(xy_all.shape[0])
-        ok_local = 1
         kn = None
+        red = torch.zeros((2,), dtype=torch.float64, device=xy.device)     # [all complete?, -max k-th distance]
         if k >= n_all:
-            ok_local = 0 if world > 1 else ok_local
             if world == 1:
                 raise ValueError(f"k={k} must be smaller than the number of points ({n_all})")
         else:
-            span_x = float(xy_all[:, 0].max() - xy_all[:, 0].min()) if n_all else 1.0
-            span_y = float(xy_all[:, 1].max() - xy_all[:, 1].min()) if n_all else 1.0
-            cell = default_knn_cell(n_all, max(span_x, 1e-9) * max(span_y, 1e-9), k)
-            eng.grid_build(xy_all, ty_all, gid_all, cell, bounds, n_query=n_q)
+            box = _strip_bounds(strip, width, bounds)
+            if box is not None:
+                area = max(box[2] - box[0], 1e-9) * max(box[3] - box[1], 1e-9)
+            else:
+                ext = torch.stack([xy_all.amax(0) - xy_all.amin(0)]).reshape(-1).tolist()
+                area = max(ext[0], 1e-9) * max(ext[1], 1e-9)
+            eng.grid_build(xy_all, ty_all, gid_all, default_knn_cell(n_all, area, k), box, n_query=n_q)
             x_lo = -_INF if strip.is_first else strip.lo - width
             x_hi = _INF if strip.is_last else strip.hi + width
             kn = eng.knn(k, dist_dtype=torch.float64, x_lo=x_lo, x_hi=x_hi, check_halo=True)
-            ok_local = int(kn["halo_ok"].item())
-        dmax = float(kn["dist"][:n_own, k - 1].max()) if (kn is not None and n_own) else 0.0
-        red = torch.tensor([float(ok_local), -dmax], dtype=torch.float64, device=xy.device)
+            red[0] = kn["halo_ok"][0].to(torch.float64)
+            if n_own:
+                red[1] = -kn["dist"][:n_own, k - 1].max()
         red = yield ("all_reduce_min", red)
-        ok, d_global = red[0].item() >= 1.0, -red[1].item()
+        verdict = red.tolist()                                   # the host synchronisation of the round
+        ok, d_global = verdict[0] >= 1.0, -verdict[1]
         if ok and (not union or d_global <= h):
             break
         h = max(2.0 * h, d_global * 1.01)
@@ -239,18 +249,19 @@ def sharded_knn_graph(eng, xy, types, gid, k: int, strip: Strip, rank: int, worl
     out = {"knn_idx": kn["knn_idx"][:n_own], "dist": kn["dist"][:n_own], "row_gid": gid, "halo": h,
            "n_ghost": int(xy_all.shape[0]) - n_own}
     if union:
-        id_map = torch.full((n_global,), -1, dtype=torch.int32, device=xy.device)
-        id_map[gid_all[:n_q].long()] = torch.arange(n_q, dtype=torch.int32, device=xy.device)
-        type_by_gid = torch.zeros((n_global,), dtype=torch.int32, device=xy.device)
-        type_by_gid[gid_all.long()] = ty_all
-        sym = eng.symmetrize(kn["knn_idx"], kn["dist"], row_id=gid_all[:n_q].contiguous(), id_map=id_map)
-        row_ptr = sym["row_ptr"][:n_own + 1].contiguous()
-        e_own = int(row_ptr[-1].item())
-        col, w = sym["col"][:e_own].contiguous(), sym["w64"][:e_own].contiguous()
-        comp = eng.compose_degree(row_ptr, col, type_by_gid, n_types)
-        up = eng.csr_upper(row_ptr, col, w, row_id=gid.contiguous())
-        out.update({"row_ptr": row_ptr, "col": col, "w": w, "edges": up["edges"], "weight": up["w64"],
-                    "degree": comp["degree"], "nbr_count": comp["nbr_count"], "stats": comp["stats"], "hist": comp["hist"]})
+        # rows address their neighbours by global id: dense id -> row / id -> type maps (pg_gid_maps), then the fused
+        # union (pg_knn_union_*: CSR + i<j edge list + composition + degree in one rank pass) over own + ghost rows;
+        # the owned rows are a prefix of every output
+        id_map, type_by_gid = eng.gid_maps(gid_all, ty_all, n_q, n_global)
+        u = eng.knn_union(kn["knn_idx"], kn["dist"], types=type_by_gid, n_types=n_types, row_id=gid_all[:n_q].contiguous(),
+                          id_map=id_map, hist_len=0)
+        ends = torch.stack([u["row_ptr"][n_own], u["up_ptr"][n_own]]).tolist()
+        e_own, eu_own = int(ends[0]), int(ends[1])
+        row_ptr = u["row_ptr"][:n_own + 1]
+        st = eng.compose_degree(row_ptr.contiguous(), None, None, 1, compose=False)     # statistics over the owned rows only
+        out.update({"row_ptr": row_ptr, "col": u["col"][:e_own], "w": u["w"][:e_own], "edges": u["edges"][:eu_own],
+                    "weight": u["edge_w"][:eu_own], "degree": u["degree"][:n_own], "nbr_count": u["nbr_count"][:n_own],
+                    "stats": st["stats"], "hist": st["hist"]})
     return out
 
 
@@ -287,6 +298,20 @@ class TorchComm:
             out = torch.empty((int(sum(recv)),) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
             d.all_to_all_single(out, rec.contiguous(), output_split_sizes=list(recv), input_split_sizes=list(send), group=self.group)
             return out
+        raise ValueError(f"unknown collective {kind}")
+
+
+class LocalComm:
+    """The collectives of a one-rank world (the generators then run unchanged on a single GPU)."""
+
+    world, rank = 1, 0
+
+    def execute(self, req):
+        kind = req[0]
+        if kind == "all_gather":
+            return req[1].contiguous().unsqueeze(0)
+        if kind in ("all_reduce_sum", "all_reduce_min", "all_to_all_counts", "all_to_all_v"):
+            return req[1]
         raise ValueError(f"unknown collective {kind}")
 
 

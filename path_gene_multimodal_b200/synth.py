@@ -130,6 +130,29 @@ def make_table(n: int, seed: int, v_fixed: int | None = None, v_lo: int = 8, v_h
     return NucleiTable(side_t, tile_x, tile_y, nuc_tile, centroid, bbox, types, off, xy)
 
 
+_COHORT_BASES: dict = {}
+
+
+def make_cohort_slide(slide: int, n: int, n_bases: int = 4, dtype=np.float32) -> NucleiTable:
+    """Slide `slide` of the C4 cohort (64 slides x 500 k nuclei, seed 1004 + slide).
+
+    make_table costs ~2.6 s per 500 k-nucleus slide on one host core (trigonometry for 10 M vertices), too slow to
+    generate 64 of them inside a benchmark run, so the cohort is dealt from ``n_bases`` base tables: slide s takes
+    base table s mod n_bases (seed 1004 + s mod n_bases: tile-local centroids, boxes, ragged polygons, types) and
+    its OWN tile assignment drawn from rng(1004 + s) - i.e. its own WSI coordinates and therefore its own graphs.
+    Sizes, dtypes, density and every byte count are those of 64 independent tables. The arrays a slide shares with
+    its base are the same objects (pin them once)."""
+    key = (slide % n_bases, n, np.dtype(dtype).name)
+    base = _COHORT_BASES.get(key)
+    if base is None:
+        base = _COHORT_BASES[key] = make_table(n, SEEDS["C4"] + slide % n_bases, dtype=dtype)
+    rng = np.random.default_rng(SEEDS["C4"] + slide)
+    n_tiles = base.n_tiles_side * base.n_tiles_side
+    nuc_tile = rng.integers(0, n_tiles, size=n, dtype=np.int64).astype(np.int32)
+    return NucleiTable(base.n_tiles_side, base.tile_x, base.tile_y, nuc_tile, base.centroid, base.bbox, base.types,
+                       base.poly_off, base.poly_xy)
+
+
 def tile_png_paths(tab: NucleiTable, out_dir: str = "/data/out") -> list[str]:
     """png_path naming of load_annotation_with_coordinates.py:177-180: <out>/patches/<x>_<y>.png"""
     return [f"{out_dir}/patches/{int(x)}_{int(y)}.png" for x, y in zip(tab.tile_x, tab.tile_y)]

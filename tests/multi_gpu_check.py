@@ -28,7 +28,7 @@ def main():
     l_xy, l_ty = torch.from_numpy(xy[rows]).to(dev), torch.from_numpy(ty[rows]).to(dev)
     l_gid = torch.arange(rows.start, rows.stop, dtype=torch.int32, device=dev)
     edges = sharding.run(sharding.equal_count_edges(l_xy[:, 0].contiguous(), world, 0.0, float(side)), comm)
-    s_xy, s_ty, s_gid = sharding.run(sharding.partition_by_strips(l_xy, l_ty, l_gid, edges, rank, world), comm)
+    s_xy, s_ty, s_gid = sharding.run(sharding.partition_by_strips(eng, l_xy, l_ty, l_gid, edges, rank, world), comm)
     strip = sharding.strips_from_edges(edges)[rank]
     import time
 

@@ -160,3 +160,30 @@ def test_two_engines_in_one_process_share_nothing():
             res = eng.map_morph(torch.from_numpy(tab.poly_off).cuda(d), torch.from_numpy(tab.poly_xy).cuda(d), write_polygons=False)
             np.testing.assert_allclose(res["area"].cpu().numpy(), ref["area"], rtol=1e-5)
         eng.close()
+
+
+def test_cohort_runner_digest_does_not_depend_on_lanes():
+    from path_gene_multimodal_b200 import cohort
+
+    n_slides, n = 5, 20_000
+    cache, tables = {}, {}
+    for s in range(n_slides):
+        tables[s] = cohort.pin_table(synth.make_cohort_slide(s, n, n_bases=2), cache)
+    assert tables[0].poly_xy is tables[2].poly_xy and tables[0].nuc_tile is not tables[2].nuc_tile   # bases shared, deals not
+    digests = []
+    for lanes in (1, 2, 3):
+        runner = cohort.CohortRunner(0, lanes=lanes)
+        res, ms = runner.run(range(n_slides), tables.__getitem__)
+        runner.close()
+        assert sorted(res) == list(range(n_slides)) and ms > 0
+        digests.append(cohort.cohort_checksum(res))
+    assert digests[0] == digests[1] == digests[2]
+    # one slide against the oracle: radius edges and kNN union edges of its WSI centroids
+    coords = tables[3].wsi_centroids()
+    ref = ograph.radius_graph(coords, 50.0)
+    idx, dist = ograph.knn(coords, 8)
+    e, w, rp, col, _ = ograph.undirected_union(idx, dist)
+    one = cohort.process_slide(cohort.get_engine(0), tables[3])
+    assert one["radius_edges"] == len(ref["edges"]) and one["knn_edges"] == len(e)
+    assert one["radius_edge_hash"] == int((ref["edges"][:, 0] * 1000003 + ref["edges"][:, 1]).sum())
+    assert one["knn_edge_hash"] == int((e[:, 0] * 1000003 + e[:, 1]).sum())

@@ -1,5 +1,5 @@
 """GPU: strip-sharded graphs equal the single-GPU graphs bit for bit (ranks emulated in lockstep on one GPU;
-the same generators run over NCCL in tests/multi_gpu_check.py / bench.py --workload c5)."""
+the same generators run over NCCL in tests/multi_gpu_check.py and in the c5_strip_sharded stage of bench.py --gpus N)."""
 import numpy as np
 import pytest
 import torch
@@ -115,3 +115,41 @@ def test_sharded_with_ties_on_strip_edges(engine):
     for r, p in zip(res, parts):
         idx[p[2].cpu().numpy()] = r["knn_idx"].cpu().numpy()
     assert np.array_equal(idx, kn["knn_idx"].cpu().numpy())      # (d^2, global id) tie-break survives sharding
+
+
+def test_partition_kernel_equals_bucketize(engine):
+    # pg_strip_partition against the torch expression it replaces (bucketize right=True + stable argsort)
+    xy, ty, side = synth.make_points(70_001, seed=53)
+    dev = torch.device("cuda", 0)
+    d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+    gid = torch.arange(len(xy), dtype=torch.int32, device=dev) * 3 + 1
+    for inner in ([], [float(side) / 2], [100.0, 100.0, 2500.5, float(side) - 1.0, float(side) + 5.0]):
+        recs, totals = engine.strip_partition(d_xy, d_ty, gid, inner)
+        owner = torch.bucketize(d_xy[:, 0].contiguous(), torch.tensor(inner, dtype=torch.float64, device=dev), right=True)
+        order = torch.argsort(owner, stable=True)
+        assert torch.equal(totals.long(), torch.bincount(owner, minlength=len(inner) + 1))
+        assert torch.equal(recs[:, :2], d_xy[order])
+        meta = recs[:, 2].contiguous().view(torch.int32).reshape(-1, 2)
+        assert torch.equal(meta[:, 0], gid[order]) and torch.equal(meta[:, 1], d_ty[order])
+    # the whole exchange, emulated: every point lands on the rank owning its strip, intact
+    world = 3
+    n = len(xy)
+    chunks = [slice(q * n // world, (q + 1) * n // world) for q in range(world)]
+    edges = np.array([0.0, side / 3, 2 * side / 3, float(side)])
+    parts = sharding.run_emulated([sharding.partition_by_strips(engine, d_xy[c].contiguous(), d_ty[c].contiguous(),
+                                                                gid[c].contiguous(), edges, q, world) for q, c in enumerate(chunks)])
+    seen = torch.cat([p[2] for p in parts])
+    assert torch.equal(torch.sort(seen).values, gid)
+    for q, (pxy, pty, pgid) in enumerate(parts):
+        assert bool(((pxy[:, 0] >= edges[q]) & ((pxy[:, 0] < edges[q + 1]) | (q == world - 1))).all())
+        row = ((pgid - 1) // 3).long()
+        assert torch.equal(pxy, d_xy[row]) and torch.equal(pty, d_ty[row])
+
+
+def test_gid_maps(engine):
+    dev = torch.device("cuda", 0)
+    gid = torch.tensor([7, 2, 9, 0, 5], dtype=torch.int32, device=dev)
+    ty = torch.tensor([1, 2, 3, 4, 5], dtype=torch.int32, device=dev)
+    id_map, tbg = engine.gid_maps(gid, ty, n_rows=3, n_ids=11)
+    assert id_map.tolist() == [-1, -1, 1, -1, -1, -1, -1, 0, -1, 2, -1]
+    assert tbg.tolist() == [4, 0, 2, 0, 0, 5, 0, 1, 0, 3, 0]

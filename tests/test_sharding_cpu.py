@@ -1,6 +1,6 @@
 """CPU: the multi-rank host logic over gloo (world_size 2) and in lockstep emulation - slide assignment,
 equal-count strips, the all-to-all partition, and the halo exchange protocol (counts first, NaN-padded payload).
-The CUDA pack kernel is replaced here by a torch-CPU stand-in with the same contract (test double only)."""
+The CUDA pack / partition kernels are replaced here by torch-CPU stand-ins with the same contract (test doubles only)."""
 import os
 import socket
 
@@ -26,6 +26,16 @@ class FakeEngine:
 
     def check_overflow(self):
         pass
+
+    def strip_partition(self, xy, types, gid, inner_edges):
+        """Stand-in for pg_strip_partition: records grouped by owning strip (input order kept), totals per strip."""
+        inner = torch.as_tensor(np.asarray(inner_edges, dtype=np.float64))
+        owner = torch.bucketize(xy[:, 0].contiguous(), inner, right=True)
+        order = torch.argsort(owner, stable=True)
+        rec = torch.empty((xy.shape[0], 3), dtype=torch.float64)
+        rec[:, :2] = xy
+        rec[:, 2] = torch.stack([gid.to(torch.int32), types.to(torch.int32)], dim=1).contiguous().view(torch.float64).reshape(-1)
+        return rec[order].contiguous(), torch.bincount(owner, minlength=len(inner_edges) + 1).to(torch.int32)
 
 
 def _points(n, seed):
@@ -55,7 +65,7 @@ def test_strips_and_partition_emulated():
     assert e[0] == 0.0 and e[-1] == 1000.0 and np.all(np.diff(e) > 0)
     cnt = np.histogram(xy[:, 0].numpy(), bins=e)[0]
     assert cnt.sum() == 4000 and abs(cnt - 1000).max() < 40        # equal counts up to one histogram bin
-    parts = sharding.run_emulated([sharding.partition_by_strips(xy[c], ty[c], gid[c], e, q, world) for q, c in enumerate(chunks)])
+    parts = sharding.run_emulated([sharding.partition_by_strips(FakeEngine(), xy[c], ty[c], gid[c], e, q, world) for q, c in enumerate(chunks)])
     seen = []
     for q, (pxy, pty, pgid) in enumerate(parts):
         assert bool(((pxy[:, 0] >= e[q]) & ((pxy[:, 0] < e[q + 1]) | (q == world - 1))).all())
@@ -106,7 +116,7 @@ def _gloo_worker(rank, world, port, q):
         gid = torch.arange(4000, dtype=torch.int32)
         mine = slice(rank * 2000, (rank + 1) * 2000)          # each rank starts with an arbitrary half of the table
         edges = sharding.run(sharding.equal_count_edges(xy[mine][:, 0], world, 0.0, 1000.0), comm)
-        pxy, pty, pgid = sharding.run(sharding.partition_by_strips(xy[mine], ty[mine], gid[mine], edges, rank, world), comm)
+        pxy, pty, pgid = sharding.run(sharding.partition_by_strips(FakeEngine(), xy[mine], ty[mine], gid[mine], edges, rank, world), comm)
         strip = sharding.strips_from_edges(edges)[rank]
         ok = bool(((pxy[:, 0] >= strip.x_lo) & (pxy[:, 0] < strip.x_hi)).all()) and torch.equal(pxy, xy[pgid.long()])
         all_recs, max_cnt = sharding.run(sharding.exchange_halo(FakeEngine(), pxy, pty, pgid, strip, 25.0, rank, world), comm)
