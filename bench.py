@@ -774,11 +774,15 @@ def other_stages(eng, dev, flush, peak):
             eng.grid_build(wsi, t_types, None, cell_k, bnd)
             kn = eng.knn(8, dist_dtype=torch.float32, out=keep.get("kn"))
             keep["kn"] = kn
-            eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=N_TYPES, symmetric_dist=True)
+            # outputs sized by their bounds / by the capacity of an earlier exact pass: the whole table pass is one
+            # enqueue, no host read in between
+            keep["un"] = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=N_TYPES, symmetric_dist=True, presized=True)
             if with_radius:
                 eng.grid_build(wsi, t_types, None, radius_cell(RADIUS), bnd)
+                if "rg_cap" not in keep:
+                    keep["rg_cap"] = int(int(eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_edges=True)["total"]) * 1.25) + 1024
                 keep["rg"] = eng.radius_graph(RADIUS, upper=True, n_types=N_TYPES, want_dist32=True, want_edges=True,
-                                              out=keep.get("rg"))
+                                              capacity=keep["rg_cap"], out=keep.get("rg"))
 
         ms = timed(slide, reps=3)
         m_s = int(tab.poly_xy.shape[0])

@@ -205,6 +205,9 @@ typedef struct {
   int32_t hist_len;
   int32_t symmetric_dist; /* non-zero: dist(i->j) == dist(j->i) bit for bit (true for lists made by pg_knn on one
                            * coordinate set), so the weight = min over both directions needs no reverse lookup */
+  int32_t presized;       /* non-zero: the caller sized und_col / und_w / edges by their bounds (2 k n entries, k n
+                           * edges) without reading the totals; the fill pass then sizes its scratch by the same bound
+                           * and never synchronises - the whole count + fill sequence is one enqueue */
 } pg_union_out;
 int pg_knn_union_count(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx, const int32_t* row_id,
                        const int32_t* id_map, int32_t n_ids, int32_t* und_row_ptr, int32_t* up_row_ptr,

@@ -38,7 +38,7 @@ class PgMorphOut(C.Structure):
 class PgUnionOut(C.Structure):
     _fields_ = [("edges", vp), ("edge_w64", vp), ("edge_w32", vp), ("type", vp), ("n_types", C.c_int32),
                 ("nbr_count", vp), ("degree", vp), ("stats", vp), ("hist", vp), ("hist_len", C.c_int32),
-                ("symmetric_dist", C.c_int32)]
+                ("symmetric_dist", C.c_int32), ("presized", C.c_int32)]
 
 
 class PgRasterOut(C.Structure):

@@ -189,6 +189,16 @@ static inline int pg_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b
 #endif
 #define PG_STRIP (1 << PG_STRIP_LOG)
 
+// compute-sanitizer is closed on the GPU pool this library is developed on, so the bounds it would check are
+// asserted by hand in a -DPG_CHECK build (python -m path_gene_multimodal_b200._build with defines=("PG_CHECK=1",);
+// the GPU tests are run once per round against that build: profiles/). Compiled out of the product.
+#ifdef PG_CHECK
+#include <cassert>
+#define PG_ASSERT(cond) assert(cond)
+#else
+#define PG_ASSERT(cond) ((void)0)
+#endif
+
 #ifdef __CUDACC__
 // programmatic dependent launch: let the next kernel on the stream be scheduled / wait for the previous one
 __device__ __forceinline__ void pg_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;"); }

@@ -763,10 +763,15 @@ int pg_knn_union_fill(pg_handle* h, int32_t n, int32_t k, const int32_t* knn_idx
     if (x.stats) PG_CUDA(h, cudaMemsetAsync(x.stats, 0, sizeof(pg_degree_stats), s));
     return PG_OK;
   }
-  // the total of the matching count pass sizes the staging rows
+  // the total of the matching count pass sizes the staging rows - or, for a caller that has sized its own outputs by
+  // their bound and wants no host synchronisation at all, the bound does (every list entry yields at most two entries)
   int64_t total = 0;
-  int rc = pg_knn_union_total(h, &total, nullptr);
-  if (rc) return rc;
+  int rc;
+  if (x.presized) {
+    total = 2 * (int64_t)n * k;
+  } else if ((rc = pg_knn_union_total(h, &total, nullptr))) {
+    return rc;
+  }
   // staging (arrival-order rows) lives in the grid's scratch that is free at this point
   pg_buf& tcol = h->cell_of;
   pg_buf& tw = h->rank;

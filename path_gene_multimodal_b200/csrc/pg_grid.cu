@@ -15,7 +15,13 @@
 
 namespace {
 
-constexpr int TPB = 256;
+#ifndef PG_GRID_TPB
+#define PG_GRID_TPB 256
+#endif
+#ifndef PG_GRID_PTS
+#define PG_GRID_PTS 2
+#endif
+constexpr int TPB = PG_GRID_TPB;
 
 __device__ __forceinline__ unsigned long long dbl_key(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -57,7 +63,7 @@ __global__ void init_bounds_kernel(unsigned long long* keys) {
 
 // K2: PTS points per thread (independent 256-bit loads in flight, one wave of CTAs for 1M points), reduction
 // atomics (no return value, nothing else written)
-constexpr int PTS = 2;
+constexpr int PTS = PG_GRID_PTS;
 __device__ __forceinline__ void ld_xy2(const double2* p, double2& a, double2& b) {
   unsigned long long x0, y0, x1, y1;
   // volatile + not .nc: stays behind pg_pdl_wait (the coordinates may come from the kernel before this one)
@@ -94,6 +100,7 @@ histogram_kernel(const double2* xy, int n, bool aligned32, double x0, double y0,
     const int i = base + (k >> 1) * TPB * 2 + (k & 1);
     if (i < n) {
       const int c = pg_cell_index(nx, pg_cell_coord(p[k].x, x0, inv_cell, nx), pg_cell_coord(p[k].y, y0, inv_cell, ny));
+      PG_ASSERT(c >= 0 && (int64_t)c < (int64_t)nx * (((ny + PG_STRIP - 1) >> PG_STRIP_LOG) << PG_STRIP_LOG));
       atomicAdd(&cell_count[c], 1);
       // cKDTree refuses NaN / inf; here the build goes on (they land in a border cell) and the next call that
       // synchronises reports it
@@ -139,6 +146,7 @@ scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
     const int i = base + (k >> 1) * TPB * 2 + (k & 1);
     if (i < n) {
       const int tshift = (t[k] >= 1 && t[k] <= PG_PACKED_TYPES) ? (t[k] - 1) * PG_TYPE_BITS : PG_TYPE_OTHER_SHIFT;
+      PG_ASSERT(dst[k] >= 0 && dst[k] < n);
       pg_st_rec(rec + dst[k], p[k].x, p[k].y, i, id[k], t[k], tshift);
       if (gid) gid_copy[i] = id[k];
     }

@@ -157,6 +157,7 @@ __device__ __forceinline__ void walk3x3(const pg_grid_view& g, int cx, int cy, F
     auto pos = [&](int t) { return t < tot ? t + (t < n0 ? b0 : (t < n01 ? off1 : off2)) : pad; };
     for (int t = 0; t < tot; t += 4) {
       const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+      PG_ASSERT(j0 >= 0 && j0 <= pad && j1 >= 0 && j1 <= pad && j2 >= 0 && j2 <= pad && j3 >= 0 && j3 <= pad);
       const pg_rec r0 = pg_ld_rec(g.rec + j0), r1 = pg_ld_rec(g.rec + j1);
       const pg_rec r2 = pg_ld_rec(g.rec + j2), r3 = pg_ld_rec(g.rec + j3);
       f(r0); f(r1); f(r2); f(r3);
@@ -219,7 +220,9 @@ knn_select_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* ret
     ok = bstar >= 0 && m <= S;
   }
   if (!ok) {
-    retry[atomicAdd(retry_count, 1)] = p;
+    const int slot = atomicAdd(retry_count, 1);
+    PG_ASSERT(slot >= 0 && slot < g.n);
+    retry[slot] = p;
     return;
   }
   // ---- pass 2: park the survivors
@@ -243,6 +246,7 @@ knn_select_kernel(pg_grid_view g, int k, knn_out o, int32_t* retry, int32_t* ret
       rank += (db < da || (db == da && ib < ia)) ? 1 : 0;
     }
     if (rank < k) {
+      PG_ASSERT(me.row >= 0 && me.row < g.n_query && ia >= 0);
       o.knn_idx[base + rank] = ia;
       const double d = sqrt(da);
       if (o.dist64) o.dist64[base + rank] = d;

@@ -33,8 +33,14 @@ namespace {
 
 constexpr int TPB_WALK = 128;
 constexpr int SLAB = 8;              // row entries staged per thread in shared memory (12 B x SLAB x TPB_WALK = 12 KB)
-constexpr int TPB_ROWS = 256;
-constexpr int ROWS_ITEMS = 4;
+#ifndef PG_ROWS_TPB
+#define PG_ROWS_TPB 256
+#endif
+#ifndef PG_ROWS_ITEMS
+#define PG_ROWS_ITEMS 4
+#endif
+constexpr int TPB_ROWS = PG_ROWS_TPB;
+constexpr int ROWS_ITEMS = PG_ROWS_ITEMS;
 constexpr int ROWS_TILE = TPB_ROWS * ROWS_ITEMS;
 constexpr int TPB_GATHER = 256;
 constexpr int FIELD_MAX = (1 << PG_TYPE_BITS) - 1;
@@ -82,6 +88,7 @@ __device__ __forceinline__ void walk_runs3(const pg_rec* rec, int b0, int e0, in
     const int t1 = min(tot, t0 + FIELD_MAX - 3);
     for (int t = t0; t < t1; t += 4) {
       const int j0 = pos(t), j1 = pos(t + 1), j2 = pos(t + 2), j3 = pos(t + 3);
+      PG_ASSERT(j0 >= 0 && j0 <= pad && j1 >= 0 && j1 <= pad && j2 >= 0 && j2 <= pad && j3 >= 0 && j3 <= pad);
       const pg_rec r0 = pg_ld_rec(rec + j0), r1 = pg_ld_rec(rec + j1);
       const pg_rec r2 = pg_ld_rec(rec + j2), r3 = pg_ld_rec(rec + j3);
       f(r0); f(r1); f(r2); f(r3);
@@ -233,6 +240,7 @@ radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
   if (wbase >= 0 && cnt > 0) {
     const long long off = wbase + (incl - cnt);
     m.off = (int)off;
+    PG_ASSERT(off >= 0 && (unsigned long long)off + (unsigned long long)cnt <= o.ovf_base + o.ovf_cap);
     pg_tmp_ent* dst = o.tmp + off;
     if (cnt <= SLAB) {
       for (int t = 0; t < cnt; ++t) {
@@ -252,6 +260,7 @@ radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
         [&]() {});
     }
   }
+  PG_ASSERT(me.row >= 0 && me.row < g.n_query);
   st_meta(o.meta + me.row, m);  // in ROW order: a scattered full-sector store here buys the row pass coalesced loads
 }
 
@@ -268,6 +277,7 @@ struct fill_out {
 
 __device__ __forceinline__ void emit_entry(const fill_out& o, long long pos, int my_id, int key, double d2) {
   const double d = sqrt(d2);
+  PG_ASSERT(pos >= 0);
   o.col[pos] = key;
   if (o.dist32) o.dist32[pos] = (float)d;
   if (o.dist64) o.dist64[pos] = d;
@@ -303,6 +313,7 @@ __device__ __forceinline__ void gather_rows32(int rp, int end, int off, int id, 
       atomicExch(overflow, 1);  // the row does not fit the caller's buffers (or never got parked): dropped, reported
       continue;
     }
+    PG_ASSERT(p - rbase >= 0 && p - rbase < rcnt);
     const pg_tmp_ent* src = tmp + roff;
     const pg_tmp_ent e = src[p - rbase];
     int rank = 0;  // ids are distinct, so the place of an entry in its row is the number of smaller ids

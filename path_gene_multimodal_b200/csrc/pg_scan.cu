@@ -5,8 +5,11 @@
 
 namespace {
 
+#ifndef PG_SCAN_ITEMS
+#define PG_SCAN_ITEMS 16
+#endif
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_ITEMS = PG_SCAN_ITEMS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // CLEAR: the input is zeroed as it is read (the cell histogram is handed back clean for the next build,

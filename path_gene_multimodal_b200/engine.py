@@ -338,13 +338,15 @@ class Engine:
         return {"row_ptr": row_ptr, "col": col, "w64": w64, "w32": w32, "w": w64 if is64 else w32}
 
     def knn_union(self, knn_idx, knn_dist, types=None, n_types=5, hist_len=64, row_id=None, id_map=None,
-                  want_edges=True, compose=True, symmetric_dist=False):
+                  want_edges=True, compose=True, symmetric_dist=False, presized=False):
         """Undirected union + i<j edge list + composition + degree statistics in one pass chain (pg_knn_union_*).
 
         Returns row_ptr, col, w (dtype of ``knn_dist``), edges int64 [E,2], edge_w, degree, stats, hist and, with
         ``types`` (indexed by column id), nbr_count.  One host synchronisation (the two totals).  ``symmetric_dist``:
         the lists come from ``knn()`` on one coordinate set (d(i,j) == d(j,i) bit for bit), so weight = min needs no
-        reverse lookup."""
+        reverse lookup.  ``presized``: size col / w / edges by their bounds (2 k n symmetric entries, k n edges) instead
+        of reading the totals back - no host synchronisation at all; the valid prefixes are ``row_ptr[-1]`` and
+        ``up_ptr[-1]`` (device values), so a whole table pass can be enqueued (or graph-captured) in one go."""
         n, k = int(knn_idx.shape[0]), int(knn_idx.shape[1])
         row_ptr = self._empty((n + 1,), torch.int32)
         up_ptr = self._empty((n + 1,), torch.int32) if want_edges else None
@@ -354,9 +356,12 @@ class Engine:
                                                 self._p(id_map, torch.int32, "id_map"), n_ids,
                                                 self._p(row_ptr, torch.int32, "row_ptr"),
                                                 self._p(up_ptr, torch.int32, "up_ptr"), self._stream()))
-        total, upper = C.c_int64(), C.c_int64()
-        self._check(self.lib.pg_knn_union_total(self._h, C.byref(total), C.byref(upper)))
-        e, eu = int(total.value), int(upper.value) if want_edges else 0
+        if presized:
+            e, eu = 2 * n * k, (n * k if want_edges else 0)
+        else:
+            total, upper = C.c_int64(), C.c_int64()
+            self._check(self.lib.pg_knn_union_total(self._h, C.byref(total), C.byref(upper)))
+            e, eu = int(total.value), int(upper.value) if want_edges else 0
         is64 = knn_dist.dtype == torch.float64
         wt = torch.float64 if is64 else torch.float32
         col, w = self._empty((e,), torch.int32), self._empty((e,), wt)
@@ -379,6 +384,7 @@ class Engine:
         x.hist = self._p(hist, torch.int32, "hist")
         x.hist_len = int(hist_len) if hist is not None else 0
         x.symmetric_dist = 1 if symmetric_dist else 0
+        x.presized = 1 if presized else 0
         self._check(self.lib.pg_knn_union_fill(
             self._h, n, k, self._p(knn_idx, torch.int32, "knn_idx"),
             self._p(knn_dist, torch.float64, "dist64") if is64 else None,

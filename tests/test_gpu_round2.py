@@ -187,3 +187,19 @@ def test_cohort_runner_digest_does_not_depend_on_lanes():
     assert one["radius_edges"] == len(ref["edges"]) and one["knn_edges"] == len(e)
     assert one["radius_edge_hash"] == int((ref["edges"][:, 0] * 1000003 + ref["edges"][:, 1]).sum())
     assert one["knn_edge_hash"] == int((e[:, 0] * 1000003 + e[:, 1]).sum())
+
+
+def test_knn_union_presized_needs_no_totals(engine):
+    from path_gene_multimodal_b200.engine import default_knn_cell
+
+    xy, types, side = synth.make_points(40_000, 91)
+    d_xy, d_ty = torch.from_numpy(xy).cuda(), torch.from_numpy(types).cuda()
+    engine.grid_build(d_xy, d_ty, None, default_knn_cell(len(xy), float(side) ** 2, 8), None)
+    kn = engine.knn(8, dist_dtype=torch.float32)
+    a = engine.knn_union(kn["knn_idx"], kn["dist32"], types=d_ty, n_types=5, symmetric_dist=True)
+    b = engine.knn_union(kn["knn_idx"], kn["dist32"], types=d_ty, n_types=5, symmetric_dist=True, presized=True)
+    e, eu = int(a["row_ptr"][-1]), int(a["up_ptr"][-1])
+    assert b["col"].shape[0] == 2 * 8 * len(xy) and int(b["row_ptr"][-1]) == e and int(b["up_ptr"][-1]) == eu
+    assert torch.equal(b["row_ptr"], a["row_ptr"]) and torch.equal(b["col"][:e], a["col"]) and torch.equal(b["w"][:e], a["w"])
+    assert torch.equal(b["edges"][:eu], a["edges"]) and torch.equal(b["edge_w"][:eu], a["edge_w"])
+    assert torch.equal(b["degree"], a["degree"]) and torch.equal(b["nbr_count"], a["nbr_count"])
