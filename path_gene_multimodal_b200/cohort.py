@@ -54,19 +54,35 @@ def process_slide(eng: Engine, tab, k: int = 8, r: float = 50.0, n_types: int = 
     bnd = (0.0, 0.0, side_px, side_px)
     eng.grid_build(wsi, t_types, None, default_knn_cell(n, side_px ** 2, k), bnd)
     kn = eng.knn(k, dist_dtype=torch.float32)
-    un = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=n_types, symmetric_dist=True)
+    # union outputs sized by their bounds, radius outputs by the capacity a previous slide of this engine needed:
+    # nothing is read back until the summary, so the slide is ONE enqueue + ONE synchronising read
+    un = eng.knn_union(kn["knn_idx"], kn["dist32"], types=t_types, n_types=n_types, symmetric_dist=True, presized=True)
     eng.grid_build(wsi, t_types, None, radius_cell(r), bnd)
-    rg = eng.radius_graph(r, upper=True, n_types=n_types, want_dist32=True, want_edges=True)
-    st = eng.decode_stats(rg["stats"], rg["hist"])
-    # small per-slide summary (what a cohort table would keep); ONE device-to-host read synchronises the slide
-    def edge_hash(e):
-        return (e[:, 0] * 1000003 + e[:, 1]).sum() if e.numel() else torch.zeros((), dtype=torch.int64, device=dev)
+    cap = getattr(eng, "_cohort_radius_cap", None)
+    if cap is None:
+        rg = eng.radius_graph(r, upper=True, n_types=n_types, want_dist32=True, want_edges=True)
+        cap = int(rg["total"])
+    else:
+        rg = eng.radius_graph(r, upper=True, n_types=n_types, want_dist32=True, want_edges=True, capacity=cap)
 
+    def edge_hash(e, valid):
+        # sum over the valid prefix (a device scalar) of i * 1000003 + j, in wrapping int64
+        keep = torch.arange(e.shape[0], device=dev) < valid
+        return torch.where(keep, e[:, 0] * 1000003 + e[:, 1], torch.zeros((), dtype=torch.int64, device=dev)).sum()
+
+    n_knn, n_rad = un["up_ptr"][-1].long(), rg["row_ptr"][-1].long()
     sums = torch.stack([mm["area"].double().sum().reshape(1).view(torch.int64)[0], un["degree"].sum(), rg["nbr_count"].sum(),
-                        edge_hash(un["edges"]), edge_hash(rg["edges"])]).tolist()
-    return {"knn_edges": int(un["edges"].shape[0]), "radius_edges": int(rg["edges"].shape[0]),
+                        edge_hash(un["edges"], n_knn), edge_hash(rg["edges"], n_rad), n_knn, n_rad,
+                        rg["stats"][1], rg["stats"][3]]).tolist()
+    if sums[6] > cap:   # the capacity hint was too small for this slide: once more, exactly
+        eng.lib.pg_check_overflow(eng._h)
+        eng._cohort_radius_cap = None
+        return process_slide(eng, tab, k, r, n_types)
+    eng._cohort_radius_cap = max(int(sums[6] * 1.25) + 1024, cap if cap < 2 * sums[6] else 0)
+    return {"knn_edges": int(sums[5]), "radius_edges": int(sums[6]),
             "area_sum": float(np.int64(sums[0]).view(np.float64)), "knn_deg_sum": int(sums[1]), "nbr_sum": int(sums[2]),
-            "knn_edge_hash": int(sums[3]), "radius_edge_hash": int(sums[4]), "radius_mean_degree": st["mean"]}
+            "knn_edge_hash": int(sums[3]), "radius_edge_hash": int(sums[4]),
+            "radius_mean_degree": (sums[7] / sums[8]) if sums[8] else float("nan")}
 
 
 class CohortRunner:
