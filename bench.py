@@ -786,8 +786,15 @@ def other_stages(eng, dev, flush, peak):
 
         ms = timed(slide, reps=3)
         m_s = int(tab.poly_xy.shape[0])
-        out[name + "_table_pass(map+morph+kNN8 union" + ("+radius50)" if with_radius else ")")] = {
-            "ms": ms, "nuclei_per_s": n_s / ms * 1e3, "vertices": m_s}
+        entry = {"ms": ms, "nuclei_per_s": n_s / ms * 1e3, "vertices": m_s}
+        try:   # the same pass replayed as ONE CUDA graph (it reads nothing back, so it can be captured whole)
+            graph = eng.capture(slide)
+            g_ms = timed(graph.replay, reps=5)
+            entry.update({"cuda_graph_ms": g_ms, "cuda_graph_nuclei_per_s": n_s / g_ms * 1e3})
+            del graph
+        except Exception as exc:  # noqa: BLE001
+            entry["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
+        out[name + "_table_pass(map+morph+kNN8 union" + ("+radius50)" if with_radius else ")")] = entry
         del t_off, t_xy, keep
     return out
 

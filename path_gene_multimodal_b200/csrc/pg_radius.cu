@@ -31,7 +31,13 @@
 
 namespace {
 
-constexpr int TPB_WALK = 128;
+#ifndef PG_WALK_TPB
+#define PG_WALK_TPB 128
+#endif
+#ifndef PG_WALK_MINB
+#define PG_WALK_MINB 8
+#endif
+constexpr int TPB_WALK = PG_WALK_TPB;
 constexpr int SLAB = 8;              // row entries staged per thread in shared memory (12 B x SLAB x TPB_WALK = 12 KB)
 #ifndef PG_ROWS_TPB
 #define PG_ROWS_TPB 256
@@ -156,7 +162,7 @@ struct walk_out {
 
 // Entries kept: all neighbours (UPPER = false) or only id_j > id_i; degree and type counts are over all neighbours.
 template <bool FAST, bool UPPER, bool WIDE_TYPES>
-__global__ void __launch_bounds__(TPB_WALK, 8)
+__global__ void __launch_bounds__(TPB_WALK, PG_WALK_MINB)
 radius_walk_kernel(pg_grid_view g, double r2, int R, walk_out o) {
   __shared__ double s_d2[SLAB][TPB_WALK];
   __shared__ int s_key[SLAB][TPB_WALK];

@@ -105,6 +105,25 @@ class Engine:
             out.append((name.value.decode(), float(ms.value)))
         return out
 
+    def capture(self, fn, warmup: int = 2):
+        """Capture ``fn()`` - a sequence of calls on this engine that never reads anything back (bounds given to
+        grid_build, ``capacity`` / ``presized`` outputs) - into a CUDA graph and return it (``graph.replay()``).
+
+        The hot path of a small slide is a dozen short kernels; replaying them as one graph removes the per-launch
+        host cost that bounds such a pass. ``fn`` is run ``warmup`` times first (workspace growth and output
+        allocation must not happen during capture) and its tensors must be kept alive by the caller."""
+        stream = torch.cuda.Stream(self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(stream):
+            for _ in range(max(warmup, 1)):
+                fn()
+        torch.cuda.current_stream(self.device).wait_stream(stream)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            fn()
+        return graph
+
     def workspace_bytes(self) -> int:
         return int(self.lib.pg_workspace_bytes(self._h))
 

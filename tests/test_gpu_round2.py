@@ -203,3 +203,35 @@ def test_knn_union_presized_needs_no_totals(engine):
     assert torch.equal(b["row_ptr"], a["row_ptr"]) and torch.equal(b["col"][:e], a["col"]) and torch.equal(b["w"][:e], a["w"])
     assert torch.equal(b["edges"][:eu], a["edges"]) and torch.equal(b["edge_w"][:eu], a["edge_w"])
     assert torch.equal(b["degree"], a["degree"]) and torch.equal(b["nbr_count"], a["nbr_count"])
+
+
+def test_table_pass_replays_as_one_cuda_graph(engine):
+    from path_gene_multimodal_b200.engine import default_knn_cell
+
+    tab = synth.make_table(30_000, seed=41)
+    side_px = float(tab.n_tiles_side * 508)
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(getattr(tab, k)).to(dev) for k in ("poly_off", "poly_xy", "nuc_tile", "tile_x", "tile_y", "centroid", "bbox", "types")}
+    keep = {}
+
+    def table_pass():
+        mm = engine.map_morph(t["poly_off"], t["poly_xy"], t["nuc_tile"], t["tile_x"], t["tile_y"], t["centroid"], t["bbox"], out=keep.get("mm"))
+        keep["mm"] = mm
+        engine.grid_build(mm["wsi_centroid"], t["types"], None, default_knn_cell(tab.n, side_px ** 2, 8), (0.0, 0.0, side_px, side_px))
+        keep["kn"] = engine.knn(8, dist_dtype=torch.float32, out=keep.get("kn"))
+        keep["un"] = engine.knn_union(keep["kn"]["knn_idx"], keep["kn"]["dist32"], types=t["types"], symmetric_dist=True, presized=True)
+
+    table_pass()
+    torch.cuda.synchronize()
+    want = {k: keep["un"][k].clone() for k in ("row_ptr", "col", "edges", "degree", "nbr_count")}
+    graph = engine.capture(table_pass)
+    for k in ("col", "edges", "degree"):
+        keep["un"][k].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    e, eu = int(want["row_ptr"][-1]), int(keep["un"]["up_ptr"][-1])
+    assert torch.equal(keep["un"]["row_ptr"], want["row_ptr"]) and torch.equal(keep["un"]["col"][:e], want["col"][:e])
+    assert torch.equal(keep["un"]["edges"][:eu], want["edges"][:eu]) and torch.equal(keep["un"]["degree"], want["degree"])
+    idx, dist = ograph.knn(tab.wsi_centroids(), 8)
+    ref_e = ograph.undirected_union(idx, dist)[0]
+    assert np.array_equal(keep["un"]["edges"][:eu].cpu().numpy(), ref_e)
