@@ -267,6 +267,9 @@ int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, 
                          int32_t* gid, int32_t n_base, int32_t capacity, int32_t* counts_out, pg_stream stream);
 int pg_gid_maps(pg_handle* h, int32_t n, int32_t n_rows, const int32_t* gid, const int32_t* type, int32_t n_ids,
                 int32_t* id_map, int32_t* type_by_gid, pg_stream stream);
+/* int32 counts (degree, nbr_count) -> uint8 (bits = 8) or uint16 (bits = 16) before they cross PCIe; a value that
+ * does not fit is stored saturated and reported by pg_check_overflow. */
+int pg_narrow_counts(pg_handle* h, const int32_t* src, int64_t n, void* dst, int32_t bits, pg_stream stream);
 
 /* ---- K11: graph statistics the reference names (README.md:133-136 "cell-cell interaction patterns",
  * "degree, clustering, centrality") over a symmetric CSR with ascending rows (K6 / K7 output).

@@ -74,9 +74,9 @@ def as_int32(arr, name: str) -> np.ndarray:
 def _torch_dtype(dt) -> torch.dtype:
     return {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
             np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
-            np.dtype(np.uint8): torch.uint8}[np.dtype(dt)]
+            np.dtype(np.uint8): torch.uint8, np.dtype(np.int16): torch.int16}[np.dtype(dt)]
 
 
 def _numpy_dtype(dt: torch.dtype):
     return {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
-            torch.int64: np.int64, torch.uint8: np.uint8}[dt]
+            torch.int64: np.int64, torch.uint8: np.uint8, torch.int16: np.int16}[dt]

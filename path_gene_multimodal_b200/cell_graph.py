@@ -96,7 +96,8 @@ def build_knn_graph(coords, k: int = 5, types=None, n_types: int = 5, undirected
 
 
 def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mpp: float | None = None,
-                       symmetric_csr: bool = False, bounds=None, device=None, outputs: str = "notebook") -> dict:
+                       symmetric_csr: bool = False, bounds=None, device=None, outputs: str = "notebook",
+                       count_dtype=np.int32) -> dict:
     """Radius graph of cells 23-26: ``d(i, j) <= r`` (inclusive, like query_ball_tree), ``i < j``.
 
     ``mpp`` scales pixel coordinates to micrometres first (``x_um = x_px * mpp``, ipynb:2046).
@@ -108,7 +109,13 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
     ``dist`` float32 [E], ``degree``, ``nbr_count``, ``degree_stats`` - a third of the bytes that cross PCIe (the
     notebook tensors are ``graph_features.edge_index_from_edges(edges, dist)`` away, on whichever device consumes
     them), and the whole call is one enqueue + one synchronisation once the handle has seen a slide of this kind.
+    ``count_dtype`` (compact only): ``np.uint8`` / ``np.uint16`` narrow ``degree`` and ``nbr_count`` on the device
+    before the copy (a quarter / half of their bytes); ``OverflowError`` if a count does not fit.
     """
+    if np.dtype(count_dtype) not in (np.dtype(np.int32), np.dtype(np.uint8), np.dtype(np.uint16)):
+        raise ValueError("count_dtype must be int32, uint8 or uint16")
+    if outputs != "compact" and np.dtype(count_dtype) != np.dtype(np.int32):
+        raise ValueError("count_dtype needs outputs='compact'")
     if outputs not in ("notebook", "compact"):
         raise ValueError("outputs must be 'notebook' or 'compact'")
     eng = get_engine(device)
@@ -121,7 +128,7 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
     with torch.cuda.device(eng.device):
         eng.grid_build(d_xy, d_t, None, radius_cell(r), bounds)  # bounds=None: min/max reduced on the device
         if outputs == "compact":
-            out = _radius_compact(eng, c.shape[0], r, n_types, d_t is not None)
+            out = _radius_compact(eng, c.shape[0], r, n_types, d_t is not None, np.dtype(count_dtype))
         else:
             g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=False, want_edge_index=True)
             e = int(g["total"])
@@ -146,7 +153,7 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
     return out
 
 
-def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool) -> dict:
+def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_dtype=np.dtype(np.int32)) -> dict:
     """The compact output set. With a capacity hint from an earlier slide (edges per nucleus seen on this handle)
     the build is pg_radius_graph - outputs given up front, nothing read back in between - followed by ONE batch of
     device-to-host copies and one synchronisation; the valid prefix is cut on the host. Without a hint, or when the
@@ -165,11 +172,22 @@ def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool) -> dic
         else:
             g = eng.radius_graph(r, upper=True, n_types=n_types, compose=True, want_dist32=True, want_edges32=True)
             cap = int(g["total"])
-        host = _host.to_host_many({"edges": g["edges32"], "dist": g["dist32"], "degree": g["degree"],
-                                   "nbr_count": g["nbr_count"] if has_types else None, "stats": g["stats"],
-                                   "hist": g["hist"], "row_end": g["row_ptr"][-1:]})
+        deg, nbr = g["degree"], (g["nbr_count"] if has_types else None)
+        if count_dtype != np.dtype(np.int32):
+            tdt = torch.uint8 if count_dtype == np.dtype(np.uint8) else torch.int16
+            deg = eng.narrow_counts(deg, tdt)
+            nbr = eng.narrow_counts(nbr, tdt) if nbr is not None else None
+        host = _host.to_host_many({"edges": g["edges32"], "dist": g["dist32"], "degree": deg, "nbr_count": nbr,
+                                   "stats": g["stats"], "hist": g["hist"], "row_end": g["row_ptr"][-1:]})
         e = int(host["row_end"][0])
         if e <= cap:
+            if count_dtype != np.dtype(np.int32):
+                if eng.lib.pg_check_overflow(eng._h) != 0:  # (also clears the flag)
+                    raise OverflowError(f"a degree / neighbour-type count does not fit {count_dtype}")
+                if count_dtype == np.dtype(np.uint16):
+                    host["degree"] = host["degree"].view(np.uint16)
+                    if host.get("nbr_count") is not None:
+                        host["nbr_count"] = host["nbr_count"].view(np.uint16)
             break
         eng.lib.pg_check_overflow(eng._h)  # clears the overflow flag the undersized pass has raised
         hint = None

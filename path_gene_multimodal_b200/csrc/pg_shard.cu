@@ -115,9 +115,48 @@ gid_maps_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ typ
   if (type_by_gid) type_by_gid[g] = type ? type[i] : 0;
 }
 
+// int32 counts -> uint8 / uint16 (what crosses PCIe when the caller asks for narrow counts); values that do not fit
+// raise the handle's overflow flag (pg_check_overflow) and are stored saturated
+template <typename T>
+__global__ void __launch_bounds__(TPB)
+narrow_counts_kernel(const int4* __restrict__ src, int64_t n4, int64_t n, T* __restrict__ dst, int32_t* overflow) {
+  const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n4) return;
+  constexpr int LIM = sizeof(T) == 1 ? 255 : 65535;
+  int v[4];
+  if (4 * i + 4 <= n) { const int4 q = src[i]; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+  else { const int32_t* s1 = reinterpret_cast<const int32_t*>(src); for (int t = 0; t < 4; ++t) v[t] = 4 * i + t < n ? s1[4 * i + t] : 0; }
+  bool bad = false;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { bad |= v[t] < 0 || v[t] > LIM; v[t] = min(max(v[t], 0), LIM); }
+  if (bad) atomicExch(overflow, 1);
+  if (4 * i + 4 <= n) {
+    if (sizeof(T) == 1) reinterpret_cast<uint32_t*>(dst)[i] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    else reinterpret_cast<uint2*>(dst)[i] = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+  } else {
+    for (int t = 0; t < 4; ++t) if (4 * i + t < n) dst[4 * i + t] = (T)v[t];
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int pg_narrow_counts(pg_handle* h, const int32_t* src, int64_t n, void* dst, int32_t bits, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n >= 0 && (bits == 8 || bits == 16) && (n == 0 || (src && dst)), "pg_narrow_counts: bits must be 8 or 16");
+  PG_REQUIRE(h, ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "pg_narrow_counts: src must be 16-byte, dst 8-byte aligned");
+  if (n == 0) return PG_OK;
+  const int64_t n4 = (n + 3) / 4;
+  int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
+  if (bits == 8) PG_LAUNCH(h, s, "narrow_counts_kernel", narrow_counts_kernel<uint8_t><<<pg_div_up(n4, TPB), TPB, 0, s>>>((const int4*)src, n4, n, (uint8_t*)dst, ovf));
+  else PG_LAUNCH(h, s, "narrow_counts_kernel", narrow_counts_kernel<uint16_t><<<pg_div_up(n4, TPB), TPB, 0, s>>>((const int4*)src, n4, n, (uint16_t*)dst, ovf));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
 
 int pg_strip_partition(pg_handle* h, int32_t n, const double* xy, const int32_t* type, const int32_t* gid,
                        int32_t n_strips, const double* inner_edges, pg_halo_rec* out, int32_t* totals, pg_stream stream) {

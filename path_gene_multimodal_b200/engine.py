@@ -587,6 +587,15 @@ class Engine:
                                          self._p(tbg, torch.int32, "type_by_gid"), self._stream()))
         return id_map, tbg
 
+    def narrow_counts(self, x, dtype):
+        """int32 counts -> uint8 / int16-sized unsigned (torch.uint8 / torch.int16 storage) on the device (pg_narrow_counts);
+        values that do not fit are reported by check_overflow()."""
+        bits = 8 if dtype == torch.uint8 else 16
+        out = self._empty(tuple(x.shape), torch.uint8 if bits == 8 else torch.int16)
+        self._check(self.lib.pg_narrow_counts(self._h, self._p(x, torch.int32, "counts"), int(x.numel()),
+                                              C.c_void_p(out.data_ptr()), bits, self._stream()))
+        return out
+
     def exclusive_scan(self, x):
         n = int(x.numel())
         out = self._empty((n + 1,), torch.int32)

@@ -235,3 +235,24 @@ def test_table_pass_replays_as_one_cuda_graph(engine):
     idx, dist = ograph.knn(tab.wsi_centroids(), 8)
     ref_e = ograph.undirected_union(idx, dist)[0]
     assert np.array_equal(keep["un"]["edges"][:eu].cpu().numpy(), ref_e)
+
+
+def test_compact_narrow_counts(golden_graph):
+    from path_gene_multimodal_b200 import build_radius_graph
+
+    coords, types = golden_graph["coords"], golden_graph["types"]
+    full = build_radius_graph(coords, r=25.0, types=types)
+    for dt in (np.uint8, np.uint16):
+        for _ in range(2):
+            c = build_radius_graph(coords, r=25.0, types=types, outputs="compact", count_dtype=dt)
+            assert c["degree"].dtype == dt and c["nbr_count"].dtype == dt
+            assert np.array_equal(c["degree"], full["degree"]) and np.array_equal(c["nbr_count"], full["nbr_count"])
+            assert np.array_equal(c["edges"], full["edges"])
+    # 300 coincident points: degree 299 does not fit uint8 -> OverflowError, and the next call is clean again
+    dense = np.concatenate([np.zeros((300, 2)), coords[:100] + 1e4])
+    with pytest.raises(OverflowError):
+        build_radius_graph(dense, r=1.0, types=np.ones(len(dense), dtype=np.int32), outputs="compact", count_dtype=np.uint8)
+    ok = build_radius_graph(dense, r=1.0, types=np.ones(len(dense), dtype=np.int32), outputs="compact", count_dtype=np.uint16)
+    assert int(ok["degree"].max()) == 299 and int(ok["nbr_count"][0, 0]) == 299
+    with pytest.raises(ValueError):
+        build_radius_graph(coords, r=25.0, count_dtype=np.uint8)
