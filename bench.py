@@ -422,6 +422,8 @@ def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=2):
                  "union_degree_hash": int(((s_gid.long() + 1) * kg["degree"].long()).sum().item())})
     halo, ghosts = kg["halo"], kg["n_ghost"]
     del kg
+    # the exchange step of the kNN build alone (pack kernel + the two all-gathers + the host read of the counts)
+    t_halo = timed(lambda: sharding.exchange_halo(eng, s_xy, s_ty, s_gid, strip, 2.0 * halo, rank, world))[1] if world > 1 else 0.0
     torch.cuda.empty_cache()
     keys = sorted(sums)
     vec = torch.tensor([sums[q] for q in keys], dtype=torch.int64, device=dev)
@@ -429,7 +431,7 @@ def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=2):
         dist.all_reduce(vec, op=dist.ReduceOp.SUM)        # int64 sums wrap the same way on every world size
     total = dict(zip(keys, vec.tolist()))
     out.update({"radius_ms": t_rad, "knn_union_ms": t_knn, "total_ms": out["partition_ms"] + t_rad + t_knn,
-                "nuclei_per_s": n / ((t_rad + t_knn) / 1e3), "halo_px": halo, "ghosts_rank0": ghosts,
+                "nuclei_per_s": n / ((t_rad + t_knn) / 1e3), "halo_px": halo, "ghosts_rank0": ghosts, "halo_exchange_ms": t_halo,
                 "radius_edges": total["radius_edges"], "union_edges": total["union_edges"],
                 "timing": "CUDA events around each sharded build (halo exchange, host reads of counts included), max over ranks, best of %d" % reps})
     if rank == 0:

@@ -52,6 +52,16 @@ eng.node_features(feat, d_ty, torch.arange(1, 6, dtype=torch.int32, device=dev))
 lab = (torch.arange(4096 * 4096, device=dev, dtype=torch.int32).reshape(4096, 4096) // 16 % 4096 // 16 +
        (torch.arange(4096, device=dev, dtype=torch.int32) // 16)[:, None] * 256 + 1).contiguous()
 eng.raster_props(lab, 65536)
+# round 2: strip partition / multi-range unpack / gid maps (C5 exchange steps), neighbour coordinates, count narrowing
+gid = torch.arange(n, dtype=torch.int32, device=dev)
+recs, totals = eng.strip_partition(d_xy, d_ty, gid, [float(side) * q / 8 for q in range(1, 8)])
+xy_all = torch.empty((2 * n, 2), dtype=torch.float64, device=dev)
+ty_all = torch.empty((2 * n,), dtype=torch.int32, device=dev)
+gid_all = torch.empty((2 * n,), dtype=torch.int32, device=dev)
+eng.halo_unpack_multi(recs, n, 0, 0, [(0.0, float(side) / 2), (float(side) / 2, float(side) + 1.0)], xy_all, ty_all, gid_all, n)
+eng.gid_maps(gid, d_ty, n, n)
+eng.knn_neighbor_coords(kres["knn_idx"], d_xy)
+eng.narrow_counts(out["nbr_count"], torch.uint8)
 torch.cuda.synchronize()
 eng.check_overflow()
 print("capture ok", eng.launches)
