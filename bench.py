@@ -69,14 +69,15 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed regions (device-resident steps, then the
-    end-to-end steps) run."""
+    """nvidia-smi clocks / throttle reasons of the first `n_gpus` GPUs, sampled every 50 ms by ONE process (rank 0's)
+    while the timed regions (device-resident steps, then the end-to-end steps) run. It is started before the warm-up:
+    the start-up of nvidia-smi takes driver locks that can stall kernel launches for milliseconds."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
+    def __init__(self, n_gpus: int):
+        self.n_gpus = n_gpus
         self.proc = None
         self.path = None
 
@@ -85,7 +86,8 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", ",".join(str(i) for i in range(self.n_gpus))],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -534,16 +536,25 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
-    timed_steps(slide.step, flush, 0, warm)
+    sampler = ClockSampler(world)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    slide.step()
+    launches_per_step = eng.launches - l0
+    # the step replayed as ONE CUDA graph (same five kernels, same programmatic-dependent-launch edges): host jitter
+    # between the launches of a step (8 ranks + a sampler on one VM) cannot open gaps inside the timed region
+    try:
+        graph = eng.capture(slide.step)
+        run_step, how = graph.replay, "one CUDA graph replay per step (5 kernels, programmatic dependent launch edges kept)"
+    except Exception as exc:  # noqa: BLE001
+        run_step, how = slide.step, f"eager launches (graph capture failed: {type(exc).__name__})"
+    timed_steps(run_step, flush, 0, warm)
     eng.check_overflow()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = eng.launches
+    step_ms = timed_steps(run_step, flush, args.steps, 0)
     barrier()
-    step_ms = timed_steps(slide.step, flush, args.steps, 0)
-    barrier()
-    launches = eng.launches - l0
+    launches = launches_per_step * args.steps
     eng.check_overflow()
     total_ms = float(sum(step_ms))
     assert int(slide.out["row_ptr"][-1]) == e_und
@@ -590,7 +601,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_c32["api"] = "the same call with int32 degree / nbr_count"
     e2e_n = e2e("notebook")
     e2e_n["api"] = "the same call with outputs='notebook': host edge_index int64 [2,2E] / edge_attr float32 [2E,1] / degree / nbr_count"
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": "nuclei/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -599,6 +610,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "nuclei_per_gpu": n, "nuclei_per_step": n, "radius_px": RADIUS, "n_types": N_TYPES,
                    "undirected_edges": e_und, "grid_cells": cells, "parallelism": f"slide-parallel x{world} (one slide per GPU, no data-path collective)",
                    "l2": "512 MB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step, summed, max over ranks",
+                   "launch": how,
                    "outputs": "pre-sized (capacity 1.25 E from one exact pass before the timed region): a step is one enqueue, no host read; "
                               "callers without E take count -> total -> fill (see e2e)"},
         "clocks": clocks, "e2e": e2e_c, "e2e_compact_int32_counts": e2e_c32, "e2e_notebook": e2e_n, "gpu_launches": int(launches),
