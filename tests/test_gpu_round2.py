@@ -256,3 +256,23 @@ def test_compact_narrow_counts(golden_graph):
     assert int(ok["degree"].max()) == 299 and int(ok["nbr_count"][0, 0]) == 299
     with pytest.raises(ValueError):
         build_radius_graph(coords, r=25.0, count_dtype=np.uint8)
+
+
+def test_c4_slide_full_size_against_scipy():
+    """One slide of BASELINE config 4 at full size (500 k nuclei, ragged rings) through the cohort's slide pass; the
+    graphs against scipy (radius edges, kNN-8 lists -> union edges), bit-exact."""
+    from path_gene_multimodal_b200 import cohort
+
+    tab = cohort.pin_table(synth.make_cohort_slide(7, 500_000))
+    one = cohort.process_slide(cohort.get_engine(0), tab)
+    coords = tab.wsi_centroids()
+    ref = ograph.radius_graph(coords, 50.0)
+    assert one["radius_edges"] == len(ref["edges"])
+    assert one["radius_edge_hash"] == int((ref["edges"][:, 0] * 1000003 + ref["edges"][:, 1]).sum())
+    assert one["nbr_sum"] == int(2 * len(ref["edges"]))          # every type is in 1..5: the type counts sum to the degrees
+    idx, dist = ograph.knn(coords, 8)
+    e = ograph.undirected_union(idx, dist)[0]
+    assert one["knn_edges"] == len(e) and one["knn_edge_hash"] == int((e[:, 0] * 1000003 + e[:, 1]).sum())
+    assert one["knn_deg_sum"] == 2 * len(e)
+    feat = omorph.polygon_features_csr(tab.poly_off, tab.poly_xy)
+    np.testing.assert_allclose(one["area_sum"], float(np.float32(feat["area"]).astype(np.float64).sum()), rtol=1e-6)

@@ -153,3 +153,61 @@ def test_gid_maps(engine):
     id_map, tbg = engine.gid_maps(gid, ty, n_rows=3, n_ids=11)
     assert id_map.tolist() == [-1, -1, 1, -1, -1, -1, -1, 0, -1, 2, -1]
     assert tbg.tolist() == [4, 0, 2, 0, 0, 5, 0, 1, 0, 3, 0]
+
+
+def test_c5_full_size_sharded_equals_single(engine):
+    """BASELINE config 5 at full size (20 M nuclei, k = 16, r = 50 px): four emulated ranks (one GPU, lockstep) go
+    through equal-count strips, the all-to-all partition of a row-partitioned table and the halo exchange; the
+    concatenated outputs must equal the single-GPU build bit for bit (size-independent property; scipy at this size
+    takes minutes)."""
+    world, n, k = 4, 20_000_000, 16
+    xy, ty, side = synth.make_points(n, synth.SEEDS["C5"])
+    dev = torch.device("cuda", 0)
+    d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+    gid = torch.arange(n, dtype=torch.int32, device=dev)
+    bounds = (0.0, 0.0, float(side), float(side))
+    chunks = [slice(q * n // world, (q + 1) * n // world) for q in range(world)]
+    edges = sharding.run_emulated([sharding.equal_count_edges(d_xy[c][:, 0].contiguous(), world, 0.0, float(side)) for c in chunks])[0]
+    parts = sharding.run_emulated([sharding.partition_by_strips(engine, d_xy[c].contiguous(), d_ty[c].contiguous(), gid[c].contiguous(),
+                                                                edges, q, world) for q, c in enumerate(chunks)])
+    strips = sharding.strips_from_edges(edges)
+    counts = [int(p[2].numel()) for p in parts]
+    assert sum(counts) == n and max(counts) - min(counts) < n // 200          # equal-count strips
+    # ---- radius graph
+    res = sharding.run_emulated([sharding.sharded_radius_graph(engine, p[0], p[1], p[2], 50.0, s, q, world, bounds=bounds)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])
+    engine.grid_build(d_xy, d_ty, None, radius_cell(50.0), bounds)
+    ref = engine.radius_graph(50.0, upper=True, want_edges=True)
+    e = torch.cat([r["edges"] for r in res])
+    assert e.shape == ref["edges"].shape
+    assert torch.equal(e[torch.argsort(e[:, 0] * n + e[:, 1])], ref["edges"])
+    deg = torch.empty(n, dtype=torch.int32, device=dev)
+    nbr = torch.empty((n, 5), dtype=torch.int32, device=dev)
+    for r, p in zip(res, parts):
+        deg[p[2].long()] = r["degree"]
+        nbr[p[2].long()] = r["nbr_count"]
+    assert torch.equal(deg, ref["degree"]) and torch.equal(nbr, ref["nbr_count"])
+    del res, ref, e, deg, nbr
+    torch.cuda.empty_cache()
+    # ---- kNN lists + undirected union
+    res = sharding.run_emulated([sharding.sharded_knn_graph(engine, p[0], p[1], p[2], k, s, q, world, n_global=n, bounds=bounds)
+                                 for q, (s, p) in enumerate(zip(strips, parts))])
+    engine.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, k), bounds)
+    kn = engine.knn(k, dist_dtype=torch.float64)
+    for r, p in zip(res, parts):
+        g = p[2].long()
+        assert torch.equal(r["knn_idx"], kn["knn_idx"][g]) and torch.equal(r["dist"], kn["dist"][g])
+    un = engine.knn_union(kn["knn_idx"], kn["dist"], types=d_ty, n_types=5, symmetric_dist=True, hist_len=0)
+    e = torch.cat([r["edges"] for r in res])
+    w = torch.cat([r["weight"] for r in res])
+    order = torch.argsort(e[:, 0] * n + e[:, 1])
+    assert torch.equal(e[order], un["edges"]) and torch.equal(w[order], un["edge_w"])
+    deg = torch.empty(n, dtype=torch.int32, device=dev)
+    for r, p in zip(res, parts):
+        deg[p[2].long()] = r["degree"]
+    assert torch.equal(deg, un["degree"])
+    # size-independent properties of the single-GPU result itself
+    rp, col = un["row_ptr"].long(), un["col"]
+    assert int(rp[-1]) == 2 * un["edges"].shape[0]                              # symmetric: every edge twice
+    assert bool((kn["dist"][:, 1:] >= kn["dist"][:, :-1]).all())                # lists ascend by distance
+    assert bool((un["edges"][:, 0] < un["edges"][:, 1]).all())
