@@ -343,11 +343,12 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
   auto kern = extra ? map_morph_kernel<T, true> : map_morph_kernel<T, false>;
   // the opt-in above 48 KB of dynamic shared memory belongs to the DEVICE the handle lives on (cudaFuncSetAttribute
-  // acts on the current device only), so what has been granted is remembered per handle, not per process
+  // acts on the current device only) and SETS the limit rather than raising it: every handle therefore opts in, once,
+  // for the one largest size any launch can ask for, so handles sharing a device cannot lower each other's limit
   size_t& granted = h->morph_smem_set[sizeof(T) == 8 ? 1 : 0][extra ? 1 : 0];
-  if (smem > granted) {
-    PG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    granted = smem;
+  if (granted == 0) {
+    PG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_BYTES_MAX));
+    granted = SLAB_BYTES_MAX;
   }
   PG_LAUNCH(h, s, extra ? "map_morph_kernel<T, true>" : "map_morph_kernel<T, false>",
             kern<<<blocks, TPB, smem, s>>>(n, poly_off, (const V2*)poly_xy, nuc_tile, tile_x, tile_y,

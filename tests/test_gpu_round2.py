@@ -147,19 +147,31 @@ def test_c3_parity_at_250k_polygons(engine):
 
 
 def test_two_engines_in_one_process_share_nothing():
-    # K1's shared-memory opt-in is remembered per handle (it used to be a process-wide static): a second handle -
-    # on another device when there is one - must launch the float64 kernel (67 KB of dynamic shared memory) too
+    # K1's shared-memory opt-in: cudaFuncSetAttribute acts on one device and SETS the limit. A process-wide static
+    # (round 1) skipped the opt-in on a second device; a per-handle "largest size so far" let a second handle on the same
+    # device LOWER the limit under the first one. Every handle now opts in once for the one maximum: big slab on A,
+    # small slab on B (same device, or another one when there is one), big slab on A again.
     from path_gene_multimodal_b200.engine import Engine
 
-    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
-    tab = synth.make_table(3000, seed=33, dtype=np.float64)
-    ref = omorph.polygon_features_csr(tab.poly_off, tab.poly_xy)
-    for d in devs:
-        eng = Engine(d)
+    big = synth.make_table(2000, seed=33, dtype=np.float64, v_lo=60, v_hi=90)      # long rings: a slab well above 48 KB
+    small = synth.make_table(3000, seed=34, dtype=np.float64, v_lo=8, v_hi=12)
+    ref_big = omorph.polygon_features_csr(big.poly_off, big.poly_xy)
+    ref_small = omorph.polygon_features_csr(small.poly_off, small.poly_xy)
+    dev_b = 1 if torch.cuda.device_count() > 1 else 0
+    eng_a, eng_b = Engine(0), Engine(dev_b)
+
+    def run(eng, d, tab, ref):
         with torch.cuda.device(d):
             res = eng.map_morph(torch.from_numpy(tab.poly_off).cuda(d), torch.from_numpy(tab.poly_xy).cuda(d), write_polygons=False)
             np.testing.assert_allclose(res["area"].cpu().numpy(), ref["area"], rtol=1e-5)
-        eng.close()
+            np.testing.assert_allclose(res["perimeter"].cpu().numpy(), ref["perimeter"], rtol=1e-5)
+
+    run(eng_a, 0, big, ref_big)
+    run(eng_b, dev_b, small, ref_small)
+    run(eng_a, 0, big, ref_big)
+    run(eng_b, dev_b, big, ref_big)
+    eng_a.close()
+    eng_b.close()
 
 
 def test_cohort_runner_digest_does_not_depend_on_lanes():
