@@ -194,7 +194,11 @@ def table_api_timings(device):
     nuc, tiles = synth.to_frames(tab)
     tb = pa.Table.from_pandas(nuc, preserve_index=False)
     out = {}
+    import functools
+
     for name, fn, arg in (("add_wsi_coords_to_nuclei(DataFrame)", add_wsi_coords_to_nuclei, nuc),
+                          ("add_wsi_coords_to_nuclei(DataFrame, wsi_polygon_as='arrow')",
+                           functools.partial(add_wsi_coords_to_nuclei, wsi_polygon_as="arrow"), nuc),
                           ("add_wsi_coords_to_table(Arrow)", add_wsi_coords_to_table, tb)):
         fn(arg, tiles, device=device)
         t0 = time.perf_counter()

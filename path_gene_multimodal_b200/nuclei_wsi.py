@@ -27,17 +27,23 @@ def polygons_to_csr(polygons, dtype=np.float64):
     """
     import pyarrow as pa
 
+    arr = None
     if isinstance(polygons, pd.Series):
-        polygons = polygons.to_numpy()
+        if isinstance(polygons.dtype, pd.ArrowDtype):   # an Arrow-backed column (wsi_polygon_as="arrow", read_parquet with
+            chunks = polygons.array._pa_array            # dtype_backend="pyarrow"): its buffers ARE the CSR
+            arr = (chunks.combine_chunks() if isinstance(chunks, pa.ChunkedArray) else chunks).cast(pa.list_(pa.list_(pa.float64())))
+        else:
+            polygons = polygons.to_numpy()
     n = len(polygons)
     if n == 0:
         return np.zeros(1, dtype=np.int32), np.zeros((0, 2), dtype=dtype), np.zeros(0, dtype=bool)
-    try:
-        arr = pa.array(polygons, type=pa.list_(pa.list_(pa.float64())), from_pandas=True)
-    except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
-        # cells that are numpy arrays (what pd.read_parquet returns for list<list<double>>, including the
-        # reference's own *_nuclei_wsi.parquet): normalise ring by ring
-        return _polygons_to_csr_loop(polygons, dtype)
+    if arr is None:
+        try:
+            arr = pa.array(polygons, type=pa.list_(pa.list_(pa.float64())), from_pandas=True)
+        except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
+            # cells that are numpy arrays (what pd.read_parquet returns for list<list<double>>, including the
+            # reference's own *_nuclei_wsi.parquet): normalise ring by ring
+            return _polygons_to_csr_loop(polygons, dtype)
     is_none = np.asarray(arr.is_null().to_numpy(zero_copy_only=False), dtype=bool)
     off = np.asarray(arr.offsets.to_numpy(), dtype=np.int64)
     inner = arr.values  # list<double>, one entry per vertex
@@ -94,6 +100,19 @@ def csr_to_polygons(poly_off, poly_xy, is_none=None):
     return out
 
 
+def csr_to_arrow_series(poly_off, poly_xy, is_none=None, index=None) -> pd.Series:
+    """CSR rings -> pandas Series with ArrowDtype(list<list<double>>) over the same buffers (no Python object per
+    vertex); None where ``is_none``."""
+    import pyarrow as pa
+
+    xy = np.ascontiguousarray(poly_xy, dtype=np.float64).reshape(-1, 2)
+    m = xy.shape[0]
+    inner = pa.ListArray.from_arrays(pa.array(np.arange(0, 2 * m + 1, 2, dtype=np.int32)), pa.array(xy.reshape(-1)))
+    mask = pa.array(np.asarray(is_none, dtype=bool)) if is_none is not None and np.any(is_none) else None
+    outer = pa.ListArray.from_arrays(pa.array(np.asarray(poly_off, dtype=np.int32)), inner, mask=mask)
+    return pd.Series(pd.arrays.ArrowExtensionArray(outer), index=index)
+
+
 def map_morph_arrays(poly_off, poly_xy, nuc_tile=None, tile_x=None, tile_y=None, centroid=None, bbox=None,
                      write_polygons=True, extra=False, device=None) -> dict:
     """Array-level entry: numpy (host) in, numpy out, one fused kernel in between.
@@ -132,6 +151,7 @@ def add_wsi_coords_to_nuclei(
     morphology: bool = False,
     device=None,
     centroid_order: str = "xy",
+    wsi_polygon_as: str = "lists",
 ) -> pd.DataFrame:
     """Shift tile-local centroid / bounding_box / polygon by the tile's top-left (x, y).
 
@@ -144,7 +164,12 @@ def add_wsi_coords_to_nuclei(
     is x, ``centroid[0]`` is y, and the four centroid columns come out in true WSI axes (polygons and boxes are
     (x, y) either way).  ``morphology=True`` additionally appends ``area, perimeter, eccentricity, circularity``
     from the same kernel launch.  Tile offsets must be integral pixel values (int or float dtype).
+    ``wsi_polygon_as="arrow"`` returns ``wsi_polygon`` as an Arrow-backed ``list<list<double>>`` column over the
+    kernel's output buffers instead of Python lists (same values; ``.tolist()`` / element access give the lists): the
+    reference's cell format costs three Python objects per vertex, which is what bounds this function, not the GPU.
     """
+    if wsi_polygon_as not in ("lists", "arrow"):
+        raise ValueError("wsi_polygon_as must be 'lists' (the reference's cells) or 'arrow'")
     if centroid_order not in ("xy", "yx"):
         raise ValueError("centroid_order must be 'xy' (the reference's reading) or 'yx' (HoverNeXt's storage order)")
     out = nuc_df.copy()
@@ -191,8 +216,11 @@ def add_wsi_coords_to_nuclei(
     for c, name in enumerate(["wsi_bbox_xmin", "wsi_bbox_ymin", "wsi_bbox_xmax", "wsi_bbox_ymax"]):
         # bbox + tile_x for the x columns, bbox + tile_y for the y columns: numpy's result dtype of each sum (:316-319)
         out[name] = wsi_b[:, c].astype(np.result_type(bb_raw.dtype, (tiles_x if c % 2 == 0 else tiles_y).dtype))
-    out["wsi_polygon"] = pd.Series(csr_to_polygons(poly_off, res["wsi_poly_xy"], is_none) if n else [],
-                                   index=out.index, dtype=object)
+    if wsi_polygon_as == "arrow":
+        out["wsi_polygon"] = csr_to_arrow_series(poly_off, res["wsi_poly_xy"] if n else np.zeros((0, 2)), is_none, out.index)
+    else:
+        out["wsi_polygon"] = pd.Series(csr_to_polygons(poly_off, res["wsi_poly_xy"], is_none) if n else [],
+                                       index=out.index, dtype=object)
     if morphology:
         for name in MORPH_COLUMNS:
             out[name] = res[name].astype(np.float64) if n else np.zeros(0)

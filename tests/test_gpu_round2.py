@@ -288,3 +288,21 @@ def test_c4_slide_full_size_against_scipy():
     assert one["knn_deg_sum"] == 2 * len(e)
     feat = omorph.polygon_features_csr(tab.poly_off, tab.poly_xy)
     np.testing.assert_allclose(one["area_sum"], float(np.float32(feat["area"]).astype(np.float64).sum()), rtol=1e-6)
+
+
+def test_wsi_polygon_as_arrow_is_the_same_column():
+    from path_gene_multimodal_b200 import add_wsi_coords_to_nuclei
+
+    tab = synth.make_table(400, seed=35, dtype=np.float64)
+    nuc, tiles = synth.to_frames(tab)
+    nuc.loc[nuc.index[3], "polygon"] = None
+    ref = add_wsi_coords_to_nuclei(nuc, tiles)
+    arw = add_wsi_coords_to_nuclei(nuc, tiles, wsi_polygon_as="arrow")
+    assert isinstance(arw["wsi_polygon"].dtype, pd.ArrowDtype)
+    got = [None if v is None or v is pd.NA else [list(p) for p in v] for v in arw["wsi_polygon"].tolist()]
+    assert got == ref["wsi_polygon"].tolist() and got[3] is None
+    # and it feeds straight back in (its buffers are the CSR): the morphology of the shifted rings
+    again = nuc.drop(columns=["polygon"]).assign(polygon=arw["wsi_polygon"])
+    out = add_wsi_coords_to_nuclei(again, tiles, morphology=True)
+    base = add_wsi_coords_to_nuclei(nuc, tiles, morphology=True)
+    np.testing.assert_allclose(out["area"].to_numpy(), base["area"].to_numpy(), rtol=1e-6, equal_nan=True)
