@@ -365,7 +365,7 @@ def checksum_edges(e):
     return int((e[:, 0] * 1000003 + e[:, 1]).sum().item()) if e.numel() else 0
 
 
-def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=2):
+def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=3):
     """BASELINE config 5: one 20M-nuclei slide, radius r=50 graph and kNN k=16 + undirected union, strip-sharded over
     the ranks (equal-count x-strips, all-to-all partition of the row-partitioned table, ONE halo all-gather per build).
     Strong scaling: the slide is fixed. Device time (CUDA events, max over ranks) of partition / radius / kNN builds;

@@ -306,3 +306,39 @@ def test_wsi_polygon_as_arrow_is_the_same_column():
     out = add_wsi_coords_to_nuclei(again, tiles, morphology=True)
     base = add_wsi_coords_to_nuclei(nuc, tiles, morphology=True)
     np.testing.assert_allclose(out["area"].to_numpy(), base["area"].to_numpy(), rtol=1e-6, equal_nan=True)
+
+
+def test_round2_entry_points_on_empty_and_tiny_inputs(engine):
+    from path_gene_multimodal_b200 import build_radius_graph, knn_graph_frame
+
+    dev = torch.device("cuda", 0)
+    e_xy = torch.zeros((0, 2), dtype=torch.float64, device=dev)
+    e_i = torch.zeros((0,), dtype=torch.int32, device=dev)
+    recs, totals = engine.strip_partition(e_xy, e_i, e_i, [10.0, 20.0])
+    assert recs.shape[0] == 0 and totals.tolist() == [0, 0, 0]
+    xy_all = torch.zeros((4, 2), dtype=torch.float64, device=dev)
+    counts = engine.halo_unpack_multi(torch.zeros((0, 3), dtype=torch.float64, device=dev), 0, 0, 0, [(0.0, 1.0), (1.0, 2.0)],
+                                      xy_all, torch.zeros(4, dtype=torch.int32, device=dev), torch.zeros(4, dtype=torch.int32, device=dev), 0)
+    assert counts.tolist() == [0, 0]
+    id_map, tbg = engine.gid_maps(e_i, e_i, 0, 5)
+    assert id_map.tolist() == [-1] * 5 and tbg.tolist() == [0] * 5
+    assert engine.narrow_counts(torch.zeros((0, 5), dtype=torch.int32, device=dev), torch.uint8).shape == (0, 5)
+    odd = torch.arange(7, dtype=torch.int32, device=dev) * 40            # not a multiple of four: the tail path; 240 fits, 280 would not
+    assert engine.narrow_counts(odd, torch.uint8).tolist() == [0, 40, 80, 120, 160, 200, 240]
+    engine.check_overflow()
+    assert engine.knn_neighbor_coords(torch.zeros((0, 3), dtype=torch.int32, device=dev), torch.zeros((5, 2), dtype=torch.float64, device=dev)).shape == (0, 3, 2)
+    # public API on nothing / one point / two points, both output sets
+    for outputs in ("notebook", "compact"):
+        g0 = build_radius_graph(np.zeros((0, 2)), r=5.0, types=np.zeros(0, dtype=np.int32), outputs=outputs)
+        assert g0["edges"].shape == (0, 2) and g0["degree"].shape == (0,)
+        g1 = build_radius_graph(np.array([[1.0, 2.0]]), r=5.0, types=np.array([3]), outputs=outputs)
+        assert g1["edges"].shape == (0, 2) and g1["degree"].tolist() == [0] and g1["nbr_count"].tolist() == [[0, 0, 0, 0, 0]]
+        g2 = build_radius_graph(np.array([[0.0, 0.0], [3.0, 4.0]]), r=5.0, types=np.array([1, 2]), outputs=outputs)
+        assert g2["edges"].tolist() == [[0, 1]] and g2["dist"].tolist() == [5.0] and g2["nbr_count"].tolist() == [[0, 1, 0, 0, 0], [1, 0, 0, 0, 0]]
+    # cell 11 with a `type` column instead of `type_name`, k = N - 1
+    df = pd.DataFrame({"nuc_id": list("abcd"), "centroid": [[0.0, 0.0], [0.0, 1.0], [5.0, 0.0], [5.0, 1.5]], "type": [1, 2, 7, 5]})
+    out, g = knn_graph_frame(df, k=3)
+    assert out["knn_neighbors"].tolist()[0] == [1, 2, 3] and out["color"].tolist() == ["tab:red", "tab:green", "black", "tab:orange"]
+    assert out["knn_neighbor_coords"].iloc[0][0] == (1.0, 0.0)          # centroid cells are [y, x]
+    with pytest.raises(ValueError):
+        knn_graph_frame(df, k=4)
