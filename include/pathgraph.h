@@ -118,6 +118,12 @@ int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, co
  * PG_ERR_INVALID comes from the next call that synchronises: pg_grid_check (synchronises the stream),
  * pg_radius_total or pg_check_overflow. */
 int pg_grid_check(pg_handle* h);
+/* The points of the built grid in CELL ORDER (a spatial sort of the input, one coalesced pass over the records):
+ * xy f64 [n,2], type int32 [n], gid int32 [n] = the id of each point (gid given to pg_grid_build, else its row);
+ * any may be NULL. A caller that owns its row order (a strip of a sharded slide: rows are keyed by global id) feeds
+ * these back in: every row-indexed access of the later passes - the walk's per-row records, the gather, the
+ * neighbours' lists of the kNN union - then stays local. */
+int pg_grid_export(pg_handle* h, double* xy, int32_t* type, int32_t* gid, pg_stream stream);
 /* host-side view of the grid chosen: nx, ny, x0, y0, cell */
 int pg_grid_info(pg_handle* h, int32_t* nx, int32_t* ny, double* x0, double* y0, double* cell);
 

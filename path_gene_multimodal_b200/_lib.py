@@ -63,6 +63,7 @@ SIGNATURES = {
     "pg_map_morph_f32": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PgMorphOut), vp]),
     "pg_map_morph_f64": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PgMorphOut), vp]),
     "pg_grid_build": (C.c_int, [vp, i32, i32, vp, vp, vp, f64, C.POINTER(f64), vp]),
+    "pg_grid_export": (C.c_int, [vp, vp, vp, vp, vp]),
     "pg_grid_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]),
     "pg_knn": (C.c_int, [vp, i32, vp, vp, vp, f64, f64, vp, vp]),
     "pg_knn_neighbor_coords": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp]),

@@ -153,9 +153,34 @@ scatter_kernel(const double2* xy, const int32_t* type, const int32_t* gid,
   }
 }
 
+// the points of the built grid, in cell order, back as plain arrays (a spatial sort of the input: see pg_grid_export)
+__global__ void __launch_bounds__(TPB)
+export_kernel(const pg_rec* __restrict__ rec, int n, double2* __restrict__ xy, int32_t* __restrict__ type, int32_t* __restrict__ gid) {
+  const int p = blockIdx.x * TPB + threadIdx.x;
+  if (p >= n) return;
+  const pg_rec r = pg_ld_rec(rec + p);
+  if (xy) xy[p] = make_double2(r.x, r.y);
+  if (type) type[p] = r.type;
+  if (gid) gid[p] = r.id;
+}
+
 }  // namespace
 
 extern "C" {
+
+int pg_grid_export(pg_handle* h, double* xy, int32_t* type, int32_t* gid, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  if (!h->grid.built) return pg_set_error(h, PG_ERR_STATE, "pg_grid_export: call pg_grid_build first");
+  PG_REQUIRE(h, ((uintptr_t)xy & 15) == 0, "pg_grid_export: xy must be 16-byte aligned");
+  const int n = h->grid.n;
+  if (n == 0) return PG_OK;
+  PG_LAUNCH(h, s, "export_kernel", export_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>((const pg_rec*)h->s_rec.p, n, (double2*)xy, type, gid));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
 
 int pg_grid_build(pg_handle* h, int32_t n, int32_t n_query, const double* xy, const int32_t* type,
                   const int32_t* gid, double cell_size, const double* bounds, pg_stream stream) {

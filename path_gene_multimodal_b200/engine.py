@@ -209,6 +209,16 @@ class Engine:
                                            float(cell_size), b, self._stream()))
         self._n, self._nq = n, nq
 
+    def grid_export(self):
+        """(xy, types, ids) of the built grid's points in cell order (pg_grid_export): a spatial sort of the input."""
+        n = self._n
+        xy = self._empty((n, 2), torch.float64)
+        ty = self._empty((n,), torch.int32)
+        gid = self._empty((n,), torch.int32)
+        self._check(self.lib.pg_grid_export(self._h, self._p(xy, torch.float64, "xy"), self._p(ty, torch.int32, "types"),
+                                            self._p(gid, torch.int32, "gid"), self._stream()))
+        return xy, ty, gid
+
     def grid_info(self) -> dict:
         nx, ny = C.c_int32(), C.c_int32()
         x0, y0, cell = C.c_double(), C.c_double(), C.c_double()

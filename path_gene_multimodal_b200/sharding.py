@@ -119,6 +119,19 @@ def partition_by_strips(eng, xy: torch.Tensor, types: torch.Tensor, gid: torch.T
     return got[:, :2].contiguous(), meta[:, 1].contiguous(), meta[:, 0].contiguous()
 
 
+def spatial_sort(eng, xy, types, gid, cell_size: float, bounds=None):
+    """The strip's points in the cell order of a ``cell_size`` grid (one grid build + pg_grid_export).
+
+    A strip owns its row order - its outputs are keyed by global id - so it may as well be the order in which the
+    query kernels walk the points: the per-row records of the radius walk then land coalesced, the gather reads its
+    parked entries in sequence, and the kNN union finds its neighbours' lists next to its own instead of at random
+    places of a gigabyte-sized array. Returns (xy, types, gid) reordered."""
+    if int(xy.shape[0]) == 0:
+        return xy, types, gid
+    eng.grid_build(xy, types, gid, cell_size, bounds)
+    return eng.grid_export()
+
+
 # ------------------------------------------------------------------------------------------ halo
 def exchange_halo(eng, xy, types, gid, strip: Strip, width: float, rank: int, world: int):
     """Generator: pack this rank's edge points (pg_halo_pack), all-gather counts then the padded payload.

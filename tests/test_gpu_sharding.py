@@ -211,3 +211,31 @@ def test_c5_full_size_sharded_equals_single(engine):
     assert int(rp[-1]) == 2 * un["edges"].shape[0]                              # symmetric: every edge twice
     assert bool((kn["dist"][:, 1:] >= kn["dist"][:, :-1]).all())                # lists ascend by distance
     assert bool((un["edges"][:, 0] < un["edges"][:, 1]).all())
+
+
+def test_spatial_sort_is_a_permutation_that_changes_nothing(engine):
+    xy, ty, side = synth.make_points(80_000, seed=54)
+    dev = torch.device("cuda", 0)
+    d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+    gid = torch.arange(len(xy), dtype=torch.int32, device=dev)
+    s_xy, s_ty, s_gid = sharding.spatial_sort(engine, d_xy, d_ty, gid, radius_cell(50.0))
+    assert torch.equal(torch.sort(s_gid).values, gid)
+    assert torch.equal(s_xy, d_xy[s_gid.long()]) and torch.equal(s_ty, d_ty[s_gid.long()])
+    # the one-rank "sharded" builds over the sorted strip give the same graph, keyed by global id
+    strip = sharding.Strip(0.0, float(side), True, True)
+    comm = sharding.LocalComm()
+    rg = sharding.run(sharding.sharded_radius_graph(engine, s_xy, s_ty, s_gid, 50.0, strip, 0, 1), comm)
+    engine.grid_build(d_xy, d_ty, None, radius_cell(50.0), None)
+    ref = engine.radius_graph(50.0, upper=True, want_edges=True)
+    e = rg["edges"]
+    assert torch.equal(e[torch.argsort(e[:, 0] * len(xy) + e[:, 1])], ref["edges"])
+    deg = torch.empty(len(xy), dtype=torch.int32, device=dev)
+    deg[s_gid.long()] = rg["degree"]
+    assert torch.equal(deg, ref["degree"])
+    kg = sharding.run(sharding.sharded_knn_graph(engine, s_xy, s_ty, s_gid, 8, strip, 0, 1, n_global=len(xy)), comm)
+    engine.grid_build(d_xy, d_ty, None, default_knn_cell(len(xy), float(side) ** 2, 8), None)
+    kn = engine.knn(8, dist_dtype=torch.float64)
+    assert torch.equal(kg["knn_idx"], kn["knn_idx"][s_gid.long()]) and torch.equal(kg["dist"], kn["dist"][s_gid.long()])
+    un = engine.knn_union(kn["knn_idx"], kn["dist"], types=d_ty, symmetric_dist=True)
+    e = kg["edges"]
+    assert torch.equal(e[torch.argsort(e[:, 0] * len(xy) + e[:, 1])], un["edges"])
