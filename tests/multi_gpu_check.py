@@ -30,11 +30,16 @@ def main():
     edges = sharding.run(sharding.equal_count_edges(l_xy[:, 0].contiguous(), world, 0.0, float(side)), comm)
     s_xy, s_ty, s_gid = sharding.run(sharding.partition_by_strips(eng, l_xy, l_ty, l_gid, edges, rank, world), comm)
     strip = sharding.strips_from_edges(edges)[rank]
+    bounds = (0.0, 0.0, float(side), float(side))
+    if os.environ.get("PG_C5_SORT", "1") != "0":   # a strip owns its row order: keep it in cell order (sharding.spatial_sort)
+        s_xy, s_ty, s_gid = sharding.spatial_sort(eng, s_xy, s_ty, s_gid, radius_cell(50.0), bounds)
     import time
 
-    def timed(make, reps=int(os.environ.get("PG_REPS", 2))):
-        """max-over-ranks wall time (barrier + synchronize on both sides) of the sharded build, best of `reps`."""
+    def timed(make, reps=int(os.environ.get("PG_REPS", 3))):
+        """max-over-ranks wall time (barrier + synchronize on both sides) of the sharded build, best of `reps` after one
+        untimed run (workspace growth); bench.py's c5_strip_sharded stage times the same builds with CUDA events."""
         best, out = None, None
+        sharding.run(make(), comm)
         for _ in range(reps):
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -45,8 +50,8 @@ def main():
             best = float(dt.item()) if best is None else min(best, float(dt.item()))
         return out, best
 
-    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world))
-    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n))
+    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world, bounds=bounds))
+    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds))
     if rank == 0:
         print(f"sharded build, world={world} n={n}: radius r=50 {t_rad * 1e3:.2f} ms ({n / t_rad / 1e6:.0f} M nuclei/s), "
               f"kNN k={k} + union + edges {t_knn * 1e3:.2f} ms ({n / t_knn / 1e6:.0f} M nuclei/s)  [halo exchange included]")
