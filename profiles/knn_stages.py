@@ -17,6 +17,11 @@ n = int(1_000_000)
 xy, ty, side = synth.make_points(n, synth.SEEDS["C2"])
 d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
 bounds = (0.0, 0.0, float(side), float(side))
+import os
+if os.environ.get("PG_SORTED_INPUT") == "1":   # the same points with their rows in cell order (how much of the chain is row-order locality?)
+    eng.grid_build(d_xy, d_ty, None, default_knn_cell(n, float(side) ** 2, 8), bounds)
+    d_xy, d_ty, _ = eng.grid_export()
+    print("input rows in cell order")
 for k in [int(a) for a in sys.argv[1:]] or [8, 16]:
     cell = default_knn_cell(n, float(side) ** 2, k)
 
