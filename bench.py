@@ -425,22 +425,50 @@ def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=3):
         (s_xy, s_ty, s_gid), t_sort = timed(lambda: iter_value(sharding.spatial_sort(eng, s_xy, s_ty, s_gid, radius_cell(RADIUS), bounds)))
         out["partition_ms"] += t_sort
         out["spatial_sort_ms"] = t_sort
-    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, RADIUS, strip, rank, world, bounds=bounds))
-    sums = {"radius_edges": int(rg["edges"].shape[0]), "radius_edge_hash": checksum_edges(rg["edges"]),
-            "radius_degree_hash": int(((s_gid.long() + 1) * rg["degree"].long()).sum().item()),
-            "radius_nbr_hash": int(((s_gid.long() + 1)[:, None] * rg["nbr_count"].long()).sum().item())}
-    del rg
-    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds))
     slot = torch.arange(1, k + 1, device=dev, dtype=torch.int64)
-    sums.update({"knn_idx_hash": int((((s_gid.long() + 1)[:, None] * 31 + slot[None, :]) * (kg["knn_idx"].long() + 1)).sum().item()),
-                 "knn_dist_hash": int(((kg["dist"].view(torch.int64) >> 11) * slot[None, :]).sum().item()),
-                 "union_edges": int(kg["edges"].shape[0]), "union_edge_hash": checksum_edges(kg["edges"]),
-                 "union_weight_hash": int((kg["weight"].view(torch.int64) >> 11).sum().item()),
-                 "union_degree_hash": int(((s_gid.long() + 1) * kg["degree"].long()).sum().item())})
-    halo, ghosts = kg["halo"], kg["n_ghost"]
-    del kg
+
+    def builds(peer):
+        """both sharded builds (timed) -> order-independent checksums of this rank's outputs"""
+        rg, t_r = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, RADIUS, strip, rank, world, bounds=bounds, peer=peer))
+        sm = {"radius_edges": int(rg["edges"].shape[0]), "radius_edge_hash": checksum_edges(rg["edges"]),
+              "radius_degree_hash": int(((s_gid.long() + 1) * rg["degree"].long()).sum().item()),
+              "radius_nbr_hash": int(((s_gid.long() + 1)[:, None] * rg["nbr_count"].long()).sum().item())}
+        del rg
+        kg, t_k = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds, peer=peer))
+        sm.update({"knn_idx_hash": int((((s_gid.long() + 1)[:, None] * 31 + slot[None, :]) * (kg["knn_idx"].long() + 1)).sum().item()),
+                   "knn_dist_hash": int(((kg["dist"].view(torch.int64) >> 11) * slot[None, :]).sum().item()),
+                   "union_edges": int(kg["edges"].shape[0]), "union_edge_hash": checksum_edges(kg["edges"]),
+                   "union_weight_hash": int((kg["weight"].view(torch.int64) >> 11).sum().item()),
+                   "union_degree_hash": int(((s_gid.long() + 1) * kg["degree"].long()).sum().item())})
+        return sm, t_r, t_k, kg["halo"], kg["n_ghost"]
+
+    sums, t_rad, t_knn, halo, ghosts = builds(None)
     # the exchange step of the kNN build alone (pack kernel + the two all-gathers + the host read of the counts)
     t_halo = timed(lambda: sharding.exchange_halo(eng, s_xy, s_ty, s_gid, strip, 2.0 * halo, rank, world))[1] if world > 1 else 0.0
+    out["halo_path"] = "nccl all-gather" if world > 1 else "none (one rank)"
+    if world > 1 and os.environ.get("PG_C5_PEER", "1") != "0":
+        # the same two builds with the halo exchange as one pack+store kernel over NVLink peer memory (sharding.PeerHalo);
+        # taken as the stage's time only if every rank reproduces the NCCL path's checksums
+        try:
+            peer = sharding.PeerHalo(int(os.environ.get("PG_C5_PEER_CAP", 262144)), dev)
+            ok_t = torch.ones((1,), device=dev, dtype=torch.int32)
+        except Exception as exc:                                           # symmetric memory unavailable on this box
+            peer, ok_t = None, torch.zeros((1,), device=dev, dtype=torch.int32)
+            out["peer_memory_error"] = repr(exc)[:200]
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        if int(ok_t.item()) == 1:
+            p_sums, p_rad, p_knn, _, _ = builds(peer)
+            same = torch.tensor([int(p_sums == sums)], device=dev, dtype=torch.int32)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            ranges = [(strip.lo - 2 * halo, strip.hi + 2 * halo)]
+            p_halo = timed(lambda: iter_value(peer.exchange(eng, s_xy, s_ty, s_gid, strip, 2.0 * halo, ranges)))[1]
+            out["nvlink_peer_halo"] = {"radius_ms": p_rad, "knn_union_ms": p_knn, "halo_exchange_and_merge_ms": p_halo,
+                                       "identical_to_nccl_path": bool(same.item()), "slab_records_per_rank": peer.cap,
+                                       "nccl_path": {"radius_ms": t_rad, "knn_union_ms": t_knn, "halo_exchange_ms": t_halo}}
+            if bool(same.item()) and p_rad + p_knn < t_rad + t_knn:
+                t_rad, t_knn = p_rad, p_knn
+                out["halo_path"] = "pg_halo_push over NVLink peer memory (pack + all-gather in one kernel)"
+        del peer
     torch.cuda.empty_cache()
     keys = sorted(sums)
     vec = torch.tensor([sums[q] for q in keys], dtype=torch.int64, device=dev)

@@ -273,6 +273,18 @@ int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, 
                          int32_t* gid, int32_t n_base, int32_t capacity, int32_t* counts_out, pg_stream stream);
 int pg_gid_maps(pg_handle* h, int32_t n, int32_t n_rows, const int32_t* gid, const int32_t* type, int32_t n_ids,
                 int32_t* id_map, int32_t* type_by_gid, pg_stream stream);
+/* The halo exchange as one step over NVLink peer memory (pack + all-gather fused; csrc/pg_shard.cu). Every rank owns a
+ * receive slab of world x cap pg_halo_rec followed by world int32 counts, mapped into every rank (symmetric memory);
+ * peer_ptrs_dev = device array of the world slab addresses as seen from this rank. pg_halo_push packs like
+ * pg_halo_pack and stores each record straight into slot [rank][o] of every peer's slab, then publishes its count
+ * (records beyond cap raise the overflow flag). After a barrier across the ranks, pg_halo_unpack_slab appends the
+ * valid records of the local slab that fall into the x-ranges (as pg_halo_unpack_multi). */
+int pg_halo_push(pg_handle* h, int32_t n, const double* xy, const int32_t* type, const int32_t* gid, double lo_edge,
+                 double hi_edge, const uint64_t* peer_ptrs_dev, int32_t world, int32_t rank, int32_t cap,
+                 pg_stream stream);
+int pg_halo_unpack_slab(pg_handle* h, const void* slab, int32_t world, int32_t rank, int32_t cap, int32_t n_ranges,
+                        const double* ranges, double* xy, int32_t* type, int32_t* gid, int32_t n_base,
+                        int32_t capacity, int32_t* counts_out, pg_stream stream);
 /* int32 counts (degree, nbr_count) -> uint8 (bits = 8) or uint16 (bits = 16) before they cross PCIe; a value that
  * does not fit is stored saturated and reported by pg_check_overflow. */
 int pg_narrow_counts(pg_handle* h, const int32_t* src, int64_t n, void* dst, int32_t bits, pg_stream stream);

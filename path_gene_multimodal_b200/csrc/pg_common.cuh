@@ -108,6 +108,7 @@ struct pg_kernel_scope {
 // misc buffer layout (byte offsets)
 #define PG_MISC_BOUNDS 0      // 4 x uint64 ordered-encoded min/max
 #define PG_MISC_OVERFLOW 64   // int32 overflow flag
+#define PG_MISC_HALOCNT 80    // int32: records packed by the last pg_halo_push
 #define PG_MISC_KNN_RETRY 76  // int32: points the kNN select pass handed to the ring pass
 #define PG_MISC_BADINPUT 72   // int32: build epoch of the last pg_grid_build that met a non-finite coordinate
 #define PG_MISC_TOTALS 128    // int32 x 8 totals copied to pinned memory: [0] radius [1] union [2] upper [3] contour scans; [4..5] uint64 overflow-region entries the last count pass needed

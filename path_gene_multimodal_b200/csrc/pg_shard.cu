@@ -104,6 +104,83 @@ halo_unpack_range_kernel(const pg_halo_rec* __restrict__ recs, int n_recs, int s
   }
 }
 
+// ---- the halo exchange as ONE step over NVLink peer memory: pack + all-gather fused -----------------------------
+// Every rank owns a receive slab [world][cap] of 24-byte records followed by [world] int32 counts, mapped into all
+// ranks (symmetric memory). The pack kernel of rank r writes each selected record straight into slot [r][o] of every
+// peer's slab (P2P stores through NVSwitch); a one-warp kernel then publishes the count. No staging buffer, no padded
+// payload, no collective library call, and no host read to size anything - the receiver's unpack kernel walks
+// world x cap slots and takes the first count[src] of every source.
+__global__ void __launch_bounds__(TPB)
+halo_push_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ type, const int32_t* __restrict__ gid, int n,
+                 double lo_edge, double hi_edge, const unsigned long long* __restrict__ peer_ptrs, int world, int rank, int cap,
+                 int32_t* count, int32_t* overflow) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  bool take = false;
+  double2 p = make_double2(0, 0);
+  if (i < n) { p = xy[i]; take = p.x < lo_edge || p.x >= hi_edge; }
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (!take) return;
+  const int o = base + __popc(m & ((1u << lane) - 1u));
+  if (o >= cap) { atomicExch(overflow, 1); return; }
+  pg_halo_rec r;
+  r.x = p.x; r.y = p.y; r.gid = gid ? gid[i] : i; r.type = type ? type[i] : 0;
+  for (int q = 0; q < world; ++q)
+    if (q != rank) reinterpret_cast<pg_halo_rec*>(peer_ptrs[q])[(size_t)rank * cap + o] = r;
+}
+
+__global__ void halo_push_counts_kernel(const unsigned long long* __restrict__ peer_ptrs, int world, int rank, int cap,
+                                        const int32_t* __restrict__ count) {
+  const int q = threadIdx.x;
+  if (q >= world || q == rank) return;
+  int32_t* counts = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(peer_ptrs[q]) + (size_t)world * cap * sizeof(pg_halo_rec));
+  counts[rank] = *count;                  // unclamped: a receiver that sees more than cap raises its overflow flag too
+  __threadfence_system();
+}
+
+// the receiver's side: slot s of the slab = entry s % cap of source s / cap, valid while below that source's count
+__global__ void __launch_bounds__(TPB)
+halo_unpack_slab_kernel(const pg_halo_rec* __restrict__ slab, int world, int rank, int cap, double x_lo, double x_hi,
+                        double2* __restrict__ xy, int32_t* __restrict__ type, int32_t* __restrict__ gid, int n_base,
+                        int capacity, int32_t* counts, int range, int32_t* overflow) {
+  const int64_t s = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const int32_t* src_counts = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(slab) + (size_t)world * cap * sizeof(pg_halo_rec));
+  int first = n_base;
+  for (int q = 0; q < range; ++q) first += counts[q];
+  bool take = false;
+  pg_halo_rec r;
+  r.x = r.y = 0; r.gid = r.type = 0;
+  if (s < (int64_t)world * cap) {
+    const int src = (int)(s / cap), idx = (int)(s - (int64_t)src * cap);
+    const int cnt = src != rank ? src_counts[src] : 0;
+    if (idx == 0 && cnt > cap) atomicExch(overflow, 1);
+    if (idx < min(cnt, cap)) {
+      r = slab[s];
+      take = r.x >= x_lo && r.x < x_hi;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int at = 0;
+  if (lane == __ffs(m) - 1) at = atomicAdd(&counts[range], __popc(m));
+  at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+  if (take) {
+    const int o = first + at + __popc(m & ((1u << lane) - 1u));
+    if (o < capacity) {
+      xy[o] = make_double2(r.x, r.y);
+      if (type) type[o] = r.type;
+      if (gid) gid[o] = r.gid;
+    } else {
+      atomicExch(overflow, 1);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB)
 gid_maps_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ type, int n, int n_rows, int n_ids,
                 int32_t* __restrict__ id_map, int32_t* __restrict__ type_by_gid) {
@@ -210,6 +287,49 @@ int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, 
     if (!(ranges[2 * r + 1] > ranges[2 * r])) continue;  // empty range
     PG_LAUNCH(h, s, "halo_unpack_range_kernel", halo_unpack_range_kernel<<<pg_div_up(n_recs, TPB), TPB, 0, s>>>(
         recs, n_recs, skip_begin, skip_end, ranges[2 * r], ranges[2 * r + 1], (double2*)xy, type, gid, n_base, capacity, counts_out, r, ovf));
+    PG_LAUNCH_CHECK(h);
+  }
+  return PG_OK;
+}
+
+int pg_halo_push(pg_handle* h, int32_t n, const double* xy, const int32_t* type, const int32_t* gid, double lo_edge,
+                 double hi_edge, const uint64_t* peer_ptrs_dev, int32_t world, int32_t rank, int32_t cap, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n >= 0 && world >= 1 && world <= 1024 && rank >= 0 && rank < world && cap >= 1 && peer_ptrs_dev,
+             "pg_halo_push: bad argument");
+  PG_REQUIRE(h, (int64_t)world * cap < 0x7fffffff, "pg_halo_push: world x cap must stay below 2^31 slots");
+  int32_t* count = (int32_t*)((char*)h->misc.p + PG_MISC_HALOCNT);
+  PG_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int32_t), s));
+  if (n > 0) {
+    PG_LAUNCH(h, s, "halo_push_kernel", halo_push_kernel<<<pg_div_up(n, TPB), TPB, 0, s>>>(
+        (const double2*)xy, type, gid, n, lo_edge, hi_edge, (const unsigned long long*)peer_ptrs_dev, world, rank, cap, count,
+        (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW)));
+    PG_LAUNCH_CHECK(h);
+  }
+  PG_LAUNCH(h, s, "halo_push_counts_kernel", halo_push_counts_kernel<<<1, 1024, 0, s>>>((const unsigned long long*)peer_ptrs_dev, world, rank, cap, count));
+  PG_LAUNCH_CHECK(h);
+  return PG_OK;
+}
+
+int pg_halo_unpack_slab(pg_handle* h, const void* slab, int32_t world, int32_t rank, int32_t cap, int32_t n_ranges,
+                        const double* ranges, double* xy, int32_t* type, int32_t* gid, int32_t n_base, int32_t capacity,
+                        int32_t* counts_out, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, slab && world >= 1 && rank >= 0 && rank < world && cap >= 1 && n_base >= 0 && capacity >= n_base &&
+                    n_ranges >= 1 && n_ranges <= 8 && ranges && counts_out && xy, "pg_halo_unpack_slab: bad argument");
+  PG_CUDA(h, cudaMemsetAsync(counts_out, 0, (size_t)n_ranges * sizeof(int32_t), s));
+  int32_t* ovf = (int32_t*)((char*)h->misc.p + PG_MISC_OVERFLOW);
+  const int64_t slots = (int64_t)world * cap;
+  for (int r = 0; r < n_ranges; ++r) {
+    if (!(ranges[2 * r + 1] > ranges[2 * r])) continue;
+    PG_LAUNCH(h, s, "halo_unpack_slab_kernel", halo_unpack_slab_kernel<<<pg_div_up(slots, TPB), TPB, 0, s>>>(
+        (const pg_halo_rec*)slab, world, rank, cap, ranges[2 * r], ranges[2 * r + 1], (double2*)xy, type, gid, n_base, capacity, counts_out, r, ovf));
     PG_LAUNCH_CHECK(h);
   }
   return PG_OK;

@@ -588,6 +588,23 @@ class Engine:
                                                   int(n_base), int(xy.shape[0]), self._p(counts, torch.int32, "counts"), self._stream()))
         return counts
 
+    def halo_push(self, xy, types, gid, lo_edge, hi_edge, peer_ptrs_dev: int, world: int, rank: int, cap: int):
+        """Pack the edge points and store them straight into every peer's receive slab (pg_halo_push)."""
+        self._check(self.lib.pg_halo_push(self._h, int(xy.shape[0]), self._p(xy, torch.float64, "xy"),
+                                          self._p(types, torch.int32, "types"), self._p(gid, torch.int32, "gid"),
+                                          float(lo_edge), float(hi_edge), C.c_void_p(int(peer_ptrs_dev)), int(world), int(rank),
+                                          int(cap), self._stream()))
+
+    def halo_unpack_slab(self, slab, world, rank, cap, ranges, xy, types, gid, n_base):
+        """Append the valid records of the local receive slab that fall into the x-ranges; device counts per range."""
+        counts = self._empty((len(ranges),), torch.int32)
+        flat = (C.c_double * (2 * len(ranges)))(*[float(v) for ab in ranges for v in ab])
+        self._check(self.lib.pg_halo_unpack_slab(self._h, C.c_void_p(slab.data_ptr()), int(world), int(rank), int(cap), len(ranges),
+                                                 flat, self._p(xy, torch.float64, "xy"), self._p(types, torch.int32, "types"),
+                                                 self._p(gid, torch.int32, "gid"), int(n_base), int(xy.shape[0]),
+                                                 self._p(counts, torch.int32, "counts"), self._stream()))
+        return counts
+
     def gid_maps(self, gid, types, n_rows, n_ids, want_id_map=True, want_types=True):
         """Dense id -> row (first n_rows points) and id -> type (all points) maps over n_ids global ids (pg_gid_maps)."""
         id_map = self._empty((n_ids,), torch.int32) if want_id_map else None

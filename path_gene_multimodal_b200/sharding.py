@@ -175,18 +175,70 @@ def merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges):
     return xy_all[:base], ty_all[:base], gid_all[:base], got
 
 
+class PeerHalo:
+    """This rank's halo receive slab, mapped into every rank of the group over NVLink (torch symmetric memory):
+    ``world x cap`` 24-byte records followed by ``world`` int32 counts. With it the halo exchange is ONE kernel that
+    packs and stores into the peers' slabs (pg_halo_push) between two device-side barriers - no NCCL call, no padded
+    payload and no host read to size it. ``cap`` bounds the records one rank may contribute per exchange; exceeding
+    it raises on every rank (all of them see every count)."""
+
+    def __init__(self, cap: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.cap = dist.get_world_size(group), dist.get_rank(group), int(cap)
+        nbytes = self.world * self.cap * 24 + 8 * ((self.world * 4 + 7) // 8)
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    def exchange(self, eng, xy, types, gid, strip: "Strip", width: float, ranges, ghost_cap: int | None = None):
+        """Push this rank's edge points to every peer, then append the received records of each x-range to the owned
+        points. Same return as merge_halo. One host read (the unpack counts + the overflow flag)."""
+        n = int(xy.shape[0])
+        lo_edge = -_INF if strip.is_first else strip.lo + width
+        hi_edge = _INF if strip.is_last else strip.hi - width
+        self.hdl.barrier(channel=0)                             # every peer is done reading the previous exchange
+        eng.halo_push(xy, types, gid, lo_edge, hi_edge, self.ptrs_dev, self.world, self.rank, self.cap)
+        self.hdl.barrier(channel=0)                             # all records and counts have landed
+        ghost_cap = int(ghost_cap) if ghost_cap is not None else min(self.world - 1, 4) * self.cap
+        cap = n + ghost_cap
+        xy_all = torch.empty((cap, 2), dtype=torch.float64, device=xy.device)
+        ty_all = torch.empty((cap,), dtype=torch.int32, device=xy.device)
+        gid_all = torch.empty((cap,), dtype=torch.int32, device=xy.device)
+        xy_all[:n] = xy
+        ty_all[:n] = types
+        gid_all[:n] = gid
+        counts = eng.halo_unpack_slab(self.buf, self.world, self.rank, self.cap, ranges, xy_all, ty_all, gid_all, n)
+        got = counts.tolist()                                   # host sync: the grid build needs the point count
+        try:
+            eng.check_overflow()
+        except RuntimeError as exc:
+            raise RuntimeError(f"PeerHalo: a rank packed more than cap={self.cap} halo records (or more than {ghost_cap} "
+                               "ghosts arrived here); build the PeerHalo with a larger cap") from exc
+        base = n + sum(got)
+        return xy_all[:base], ty_all[:base], gid_all[:base], got
+
+
 def sharded_radius_graph(eng, xy, types, gid, r: float, strip: Strip, rank: int, world: int, n_types: int = 5,
-                         upper: bool = True, bounds=None):
+                         upper: bool = True, bounds=None, peer: PeerHalo | None = None):
     """Generator: radius graph rows of this rank's strip, columns in global ids.
 
     Returns the dict of Engine.radius_graph (row_ptr / col / dist32 / edges / degree / nbr_count / stats / hist)
     over the owned rows, plus ``row_gid`` (global id of each row) and ``n_ghost``."""
     from .engine import radius_cell
 
-    all_recs, max_cnt = yield from exchange_halo(eng, xy, types, gid, strip, r, rank, world)
     lo = -_INF if strip.is_first else strip.lo - r
     hi = _INF if strip.is_last else strip.hi + r
-    xy_all, ty_all, gid_all, got = merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, [(lo, hi)])
+    if peer is not None and world > 1:
+        xy_all, ty_all, gid_all, got = peer.exchange(eng, xy, types, gid, strip, r, [(lo, hi)])
+    else:
+        all_recs, max_cnt = yield from exchange_halo(eng, xy, types, gid, strip, r, rank, world)
+        xy_all, ty_all, gid_all, got = merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, [(lo, hi)])
     n_own = int(xy.shape[0])
     eng.grid_build(xy_all, ty_all, gid_all, radius_cell(r), bounds, n_query=n_own)
     g = eng.radius_graph(r, upper=upper, n_types=n_types, want_dist32=True, want_dist64=True, want_edges=upper)
@@ -207,7 +259,7 @@ def _strip_bounds(strip: Strip, width: float, bounds):
 
 def sharded_knn_graph(eng, xy, types, gid, k: int, strip: Strip, rank: int, world: int, n_global: int,
                       n_types: int = 5, union: bool = True, h0: float | None = None, density: float | None = None,
-                      bounds=None, max_rounds: int = 8):
+                      bounds=None, max_rounds: int = 8, peer: PeerHalo | None = None):
     """Generator: kNN lists (and the undirected union / composition) for this rank's strip, bit-exact with
     the single-GPU result. The halo width starts at ``h0`` (default 3 sqrt(k / (pi rho))) and doubles until
     every rank's completeness test passes (all-reduced), so a too-small guess costs a retry, never an error.
@@ -223,13 +275,16 @@ def sharded_knn_graph(eng, xy, types, gid, k: int, strip: Strip, rank: int, worl
     h = float(h0)
     for _ in range(max_rounds):
         width = 2.0 * h if union else h
-        all_recs, max_cnt = yield from exchange_halo(eng, xy, types, gid, strip, width, rank, world)
         lo1 = -_INF if strip.is_first else strip.lo - h
         hi1 = _INF if strip.is_last else strip.hi + h
         ranges = [(lo1, hi1)]
         if union:
             ranges += [(-_INF if strip.is_first else strip.lo - 2 * h, lo1), (hi1, _INF if strip.is_last else strip.hi + 2 * h)]
-        xy_all, ty_all, gid_all, got = merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges)
+        if peer is not None and world > 1:
+            xy_all, ty_all, gid_all, got = peer.exchange(eng, xy, types, gid, strip, width, ranges)
+        else:
+            all_recs, max_cnt = yield from exchange_halo(eng, xy, types, gid, strip, width, rank, world)
+            xy_all, ty_all, gid_all, got = merge_halo(eng, xy, types, gid, all_recs, max_cnt, rank, ranges)
         n_q = n_own + (got[0] if union else 0)
         n_all = int(xy_all.shape[0])
         kn = None

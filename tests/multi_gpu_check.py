@@ -33,6 +33,8 @@ def main():
     bounds = (0.0, 0.0, float(side), float(side))
     if os.environ.get("PG_C5_SORT", "1") != "0":   # a strip owns its row order: keep it in cell order (sharding.spatial_sort)
         s_xy, s_ty, s_gid = sharding.spatial_sort(eng, s_xy, s_ty, s_gid, radius_cell(50.0), bounds)
+    # PG_PEER=1: the halo exchange as one pack+store kernel over NVLink peer memory instead of the NCCL all-gathers
+    peer = sharding.PeerHalo(int(os.environ.get("PG_PEER_CAP", 262144)), dev) if os.environ.get("PG_PEER") == "1" else None
     import time
 
     def timed(make, reps=int(os.environ.get("PG_REPS", 3))):
@@ -50,10 +52,10 @@ def main():
             best = float(dt.item()) if best is None else min(best, float(dt.item()))
         return out, best
 
-    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world, bounds=bounds))
-    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds))
+    rg, t_rad = timed(lambda: sharding.sharded_radius_graph(eng, s_xy, s_ty, s_gid, 50.0, strip, rank, world, bounds=bounds, peer=peer))
+    kg, t_knn = timed(lambda: sharding.sharded_knn_graph(eng, s_xy, s_ty, s_gid, k, strip, rank, world, n_global=n, bounds=bounds, peer=peer))
     if rank == 0:
-        print(f"sharded build, world={world} n={n}: radius r=50 {t_rad * 1e3:.2f} ms ({n / t_rad / 1e6:.0f} M nuclei/s), "
+        print(f"sharded build, world={world} n={n} halo={'nvlink peer memory' if peer else 'nccl'}: radius r=50 {t_rad * 1e3:.2f} ms ({n / t_rad / 1e6:.0f} M nuclei/s), "
               f"kNN k={k} + union + edges {t_knn * 1e3:.2f} ms ({n / t_knn / 1e6:.0f} M nuclei/s)  [halo exchange included]")
     # gather to rank 0 for the comparison
     def gather(t):

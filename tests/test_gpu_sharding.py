@@ -239,3 +239,63 @@ def test_spatial_sort_is_a_permutation_that_changes_nothing(engine):
     un = engine.knn_union(kn["knn_idx"], kn["dist"], types=d_ty, symmetric_dist=True)
     e = kg["edges"]
     assert torch.equal(e[torch.argsort(e[:, 0] * len(xy) + e[:, 1])], un["edges"])
+
+
+def test_peer_slab_halo_equals_allgather_path(engine):
+    """pg_halo_push / pg_halo_unpack_slab (the halo exchange over peer memory) against pg_halo_pack + all-gather +
+    pg_halo_unpack_multi. Three emulated ranks on one GPU: the "peer" slabs are three local buffers, so the very same
+    kernels run, only the stores do not cross NVLink (tests/multi_gpu_check.py with PG_PEER=1 is the real thing)."""
+    world, n, cap, width = 3, 60_000, 8192, 40.0
+    xy, ty, side = synth.make_points(n, 4242)
+    dev = torch.device("cuda", 0)
+    d_xy, d_ty = torch.from_numpy(xy).to(dev), torch.from_numpy(ty).to(dev)
+    gid = torch.arange(n, dtype=torch.int32, device=dev)
+    cuts = [0.0, side * 0.3, side * 0.55, float(side)]
+    strips = sharding.strips_from_edges(cuts)
+    own = [torch.nonzero((d_xy[:, 0] >= cuts[q]) & (d_xy[:, 0] < cuts[q + 1])).reshape(-1) for q in range(world)]
+    parts = [(d_xy[o].contiguous(), d_ty[o].contiguous(), gid[o].contiguous()) for o in own]
+    slab_bytes = world * cap * 24 + 8 * ((world * 4 + 7) // 8)
+    slabs = [torch.zeros(slab_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    ptrs = torch.tensor([s.data_ptr() for s in slabs], dtype=torch.int64, device=dev)
+    inf = float("inf")
+    for q, (s, p) in enumerate(zip(strips, parts)):
+        engine.halo_push(p[0], p[1], p[2], -inf if s.is_first else s.lo + width, inf if s.is_last else s.hi - width,
+                         ptrs.data_ptr(), world, q, cap)
+    # reference path: pack + gather
+    packed = []
+    for q, (s, p) in enumerate(zip(strips, parts)):
+        recs, cnt = engine.halo_pack(p[0], p[1], p[2], -inf if s.is_first else s.lo + width, inf if s.is_last else s.hi - width,
+                                     capacity=int(p[0].shape[0]))
+        packed.append(recs[:int(cnt.item())])
+    max_cnt = max(int(r.shape[0]) for r in packed)
+    assert 0 < max_cnt <= cap
+    pad = torch.full((world, max_cnt, 3), float("nan"), dtype=torch.float64, device=dev)
+    for q, r in enumerate(packed):
+        pad[q, :r.shape[0]] = r
+    for q, (s, p) in enumerate(zip(strips, parts)):
+        ranges = [(-inf if s.is_first else s.lo - width / 2, inf if s.is_last else s.hi + width / 2),
+                  (-inf if s.is_first else s.lo - width, -inf if s.is_first else s.lo - width / 2)]
+        m = int(p[0].shape[0])
+        a = [torch.empty((m + world * cap, 2), dtype=torch.float64, device=dev), torch.empty(m + world * cap, dtype=torch.int32, device=dev),
+             torch.empty(m + world * cap, dtype=torch.int32, device=dev)]
+        got = engine.halo_unpack_slab(slabs[q], world, q, cap, ranges, a[0], a[1], a[2], m).tolist()
+        engine.check_overflow()
+        want = sharding.merge_halo(engine, p[0], p[1], p[2], pad.reshape(world * max_cnt, 3).contiguous(), max_cnt, q, ranges)
+        assert got == want[3] and sum(got) > 0
+        at = m
+        for c in got:                                       # same SET per range (append order inside a range is free)
+            ga, gb = a[2][at:at + c], want[2][at:at + c]
+            ia, ib = torch.argsort(ga), torch.argsort(gb)
+            assert torch.equal(ga[ia], gb[ib]) and torch.equal(a[0][at:at + c][ia], want[0][at:at + c][ib])
+            assert torch.equal(a[1][at:at + c][ia], want[1][at:at + c][ib])
+            at += c
+    # a slab that is too small is reported, on the packing side and on the receiving side
+    tiny = [torch.zeros(world * 16 * 24 + 16, dtype=torch.uint8, device=dev) for _ in range(world)]
+    tptr = torch.tensor([s.data_ptr() for s in tiny], dtype=torch.int64, device=dev)
+    engine.halo_push(parts[1][0], parts[1][1], parts[1][2], strips[1].lo + width, strips[1].hi - width, tptr.data_ptr(), world, 1, 16)
+    with pytest.raises(RuntimeError):
+        engine.check_overflow()
+    buf = [torch.empty((n, 2), dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)]
+    engine.halo_unpack_slab(tiny[0], world, 0, 16, [(-inf, inf)], buf[0], buf[1], buf[2], 0)
+    with pytest.raises(RuntimeError):
+        engine.check_overflow()
