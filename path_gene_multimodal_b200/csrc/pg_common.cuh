@@ -75,7 +75,7 @@ struct pg_handle {
   int32_t contour_labels = -1;   // labels of the last pg_instance_contours_count (-1: none), for the fill call
   bool contour_empty = false;
   int64_t contour_raw = 0;
-  size_t morph_smem_set[2][2] = {{0, 0}, {0, 0}};  // K1: dynamic shared memory opted in on this handle's device, per [T][EXTRA]
+  size_t morph_smem_set[2][3] = {{0, 0, 0}, {0, 0, 0}};  // K1: dynamic shared memory opted in on this handle's device, per [T][EXTRA]
   double morph_mean_verts = 0;  // pg_map_morph_hint: expected vertices per ring (sizes K1's shared-memory slabs)
   // launch accounting / optional per-kernel CUDA-event timing (pg_profile_*)
   int64_t launches = 0;

@@ -106,8 +106,11 @@ __device__ __forceinline__ void edge_terms(ring_sums& r, double xa, double ya, d
   r.Ixy += (sxx * syy + xa * ya + xb * yb) * a;   // xa*yb + 2xa*ya + 2xb*yb + xb*ya
 }
 
-template <typename T, bool EXTRA>
-__global__ void __launch_bounds__(TPB)
+// MINB = CTAs per SM the register allocation leaves room for. The kernel is latency-bound per warp (bulk load ->
+// walk -> bulk store), so what it delivers follows the warps per SM: MINB = 7 (72 registers instead of 80 for float32
+// vertices) is picked by the launcher whenever the slabs are small enough for 7 CTAs to fit shared memory.
+template <typename T, bool EXTRA, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
 map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec2_of<T>::type* __restrict__ poly,
                  const int32_t* __restrict__ nuc_tile, const int32_t* __restrict__ tile_x,
                  const int32_t* __restrict__ tile_y, const double2* __restrict__ centroid,
@@ -336,16 +339,18 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   // rings (mean from pg_map_morph_hint - the Python layer knows M) get 32 rings of the mean length + 40 % spread
   int slab_verts = SLAB_VERTS_MIN;
   if (h->morph_mean_verts > 33.0) slab_verts = (int)std::ceil(46.0 * h->morph_mean_verts) + 2;
-  else if (h->morph_mean_verts > 0.0 && h->morph_mean_verts <= 23.0)  // short rings: smaller slabs, one more CTA per SM
-    slab_verts = std::max(512, (int)std::ceil(46.0 * h->morph_mean_verts) + 2);
+  else if (h->morph_mean_verts > 0.0 && h->morph_mean_verts <= 23.0)  // short rings: smaller slabs, more CTAs per SM
+    slab_verts = std::max(512, (int)std::ceil(40.0 * h->morph_mean_verts) + 2);  // 32 rings of the mean length + 25 %
   slab_verts = std::min(slab_verts, (int)(SLAB_BYTES_MAX / (WARPS * sizeof(V2))));
   slab_verts &= ~1;  // whole 16-byte units per warp
   const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
-  auto kern = extra ? map_morph_kernel<T, true> : map_morph_kernel<T, false>;
+  // 7 CTAs per SM fit shared memory (227 KB minus 1 KB per CTA) -> the 72-register build of the float32 kernel
+  const bool dense = sizeof(T) == 4 && !extra && 7 * (smem + 1024 + 128) <= 227 * 1024;
+  auto kern = extra ? map_morph_kernel<T, true, 1> : (dense ? map_morph_kernel<T, false, 7> : map_morph_kernel<T, false, 1>);
   // the opt-in above 48 KB of dynamic shared memory belongs to the DEVICE the handle lives on (cudaFuncSetAttribute
   // acts on the current device only) and SETS the limit rather than raising it: every handle therefore opts in, once,
   // for the one largest size any launch can ask for, so handles sharing a device cannot lower each other's limit
-  size_t& granted = h->morph_smem_set[sizeof(T) == 8 ? 1 : 0][extra ? 1 : 0];
+  size_t& granted = h->morph_smem_set[sizeof(T) == 8 ? 1 : 0][extra ? 1 : (dense ? 2 : 0)];
   if (granted == 0) {
     PG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_BYTES_MAX));
     granted = SLAB_BYTES_MAX;
