@@ -94,6 +94,15 @@ struct ring_sums {
   double fx, fy;  // frame origin
 };
 
+// length of one edge in float32: MUFU.SQRT (sqrt.approx, relative error <= 2^-22) instead of the IEEE sqrtf sequence
+// (MUFU.RSQ + Newton step + a guarded slow path: ~9 instructions and a branch per vertex of the inner loop). The
+// perimeter is a float32 output compared at 1e-5; the sum of <= 32 such terms is folded into float64 (ring_sums).
+__device__ __forceinline__ float edge_len(float dx, float dy) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(dx, dx, dy * dy)));
+  return r;
+}
+
 // one edge (xa,ya) -> (xb,yb), frame coordinates
 __device__ __forceinline__ void edge_terms(ring_sums& r, double xa, double ya, double xb, double yb) {
   const double a = xa * yb - xb * ya;
@@ -200,14 +209,14 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
         const double xb = (double)v.x - r.fx, yb = (double)v.y - r.fy;
         edge_terms(r, xa, ya, xb, yb);
         const float dx = (float)(v.x - px), dy = (float)(v.y - py);
-        r.P += sqrtf(dx * dx + dy * dy);
+        r.P += edge_len(dx, dy);
         if ((k & 31) == 0) { r.Pd += (double)r.P; r.P = 0.f; }
         if (EXTRA) { bx0 = min(bx0, v.x); bx1 = max(bx1, v.x); by0 = min(by0, v.y); by1 = max(by1, v.y); }
         xa = xb; ya = yb; px = v.x; py = v.y;
       }
       {  // closing edge back to the start vertex (the frame origin: no area terms)
         const float dx = (float)(fxT - px), dy = (float)(fyT - py);
-        r.P += sqrtf(dx * dx + dy * dy);
+        r.P += edge_len(dx, dy);
       }
     }
     if (wsi_poly) {
@@ -248,7 +257,7 @@ map_morph_kernel(int n, const int32_t* __restrict__ poly_off, const typename vec
           const double xb = (double)vb.x - (double)v0.x, yb = (double)vb.y - (double)v0.y;
           edge_terms(a, xa, ya, xb, yb);
           const float dx = (float)(vb.x - va.x), dy = (float)(vb.y - va.y);
-          a.Pd += (double)sqrtf(dx * dx + dy * dy);  // long rings live on this path: float64 accumulation throughout
+          a.Pd += (double)edge_len(dx, dy);  // long rings live on this path: float64 accumulation throughout
           if (EXTRA) { mnx = min(mnx, va.x); mxx = max(mxx, va.x); mny = min(mny, va.y); mxy = max(mxy, va.y); }
         }
       }
@@ -345,8 +354,13 @@ int launch_map_morph(pg_handle* h, int32_t n, const int32_t* poly_off, const T* 
   slab_verts &= ~1;  // whole 16-byte units per warp
   const size_t smem = (size_t)WARPS * slab_verts * sizeof(V2);
   // 7 CTAs per SM fit shared memory (227 KB minus 1 KB per CTA) -> the 72-register build of the float32 kernel
-  const bool dense = sizeof(T) == 4 && !extra && 7 * (smem + 1024 + 128) <= 227 * 1024;
-  auto kern = extra ? map_morph_kernel<T, true, 1> : (dense ? map_morph_kernel<T, false, 7> : map_morph_kernel<T, false, 1>);
+  // register caps that cost no spills: 6 CTAs per SM for float32 vertices (5 with the extra outputs), 5 / 4 for float64
+  constexpr int MINB0 = sizeof(T) == 4 ? 6 : 5, MINB0X = sizeof(T) == 4 ? 5 : 4;
+#ifndef PG_MORPH_DENSE
+#define PG_MORPH_DENSE 7
+#endif
+  const bool dense = PG_MORPH_DENSE > 0 && sizeof(T) == 4 && !extra && PG_MORPH_DENSE * (smem + 1024 + 128) <= 227 * 1024;
+  auto kern = extra ? map_morph_kernel<T, true, MINB0X> : (dense ? map_morph_kernel<T, false, PG_MORPH_DENSE> : map_morph_kernel<T, false, MINB0>);
   // the opt-in above 48 KB of dynamic shared memory belongs to the DEVICE the handle lives on (cudaFuncSetAttribute
   // acts on the current device only) and SETS the limit rather than raising it: every handle therefore opts in, once,
   // for the one largest size any launch can ask for, so handles sharing a device cannot lower each other's limit
