@@ -510,7 +510,7 @@ def c5_stage(eng, dev, dist, rank, world, n=20_000_000, k=16, reps=3):
     return out
 
 
-def c4_stage(dev, local_rank, dist, rank, world, n_slides=64, n=500_000, lanes=2):
+def c4_stage(dev, local_rank, dist, rank, world, n_slides=64, n=500_000, lanes=4, staging="float"):
     """BASELINE config 4: 64 slides x 500k nuclei from page-locked HOST tables, slide-parallel over the ranks
     (sharding.assign_slides), `lanes` slides in flight per GPU. Device time between the first enqueue and the last
     completion, max over ranks; the digest of all per-slide summaries must not depend on the number of GPUs."""
@@ -521,7 +521,7 @@ def c4_stage(dev, local_rank, dist, rank, world, n_slides=64, n=500_000, lanes=2
     mine = sharding.assign_slides(n_slides, world, sizes=[n] * n_slides)[rank]
     cache, tables = {}, {}
     for sl in mine:
-        tables[sl] = cohort.pin_table(synth.make_cohort_slide(sl, n), cache)
+        tables[sl] = cohort.pin_table(synth.make_cohort_slide(sl, n), cache, staging=staging)
     runner = cohort.CohortRunner(local_rank, lanes=lanes)
     runner.run(mine[:lanes], tables.__getitem__)                        # warm-up: allocations, first launches
     torch.cuda.synchronize()
@@ -543,6 +543,7 @@ def c4_stage(dev, local_rank, dist, rank, world, n_slides=64, n=500_000, lanes=2
     return {"slides": n_slides, "nuclei_per_slide": n, "world": world, "lanes": lanes, "ms": ms,
             "nuclei_per_s": n_slides * n / (ms / 1e3), "ms_per_slide_per_gpu": ms / max(len(mine), 1),
             "h2d_bytes_per_slide": h2d // max(len(mine), 1), "digest": cohort.cohort_checksum(res),
+            "polygon_staging": "float32 pixels (8 B / vertex)" if staging == "float" else "int16 half-pixels (4 B / vertex), widened on the device",
             "note": "slides dealt from 4 base tables (synth.make_cohort_slide); every slide = H2D of its table + map + morphology "
                     "+ kNN-8 union + radius-50 graph + summary read; CUDA events, max over ranks"}
 
@@ -676,7 +677,15 @@ def run_ours(args, rank, world, local_rank):
         stages_mg["c5_strip_sharded"] = {"error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.empty_cache()
     try:
-        stages_mg["c4_cohort"] = c4_stage(dev, local_rank, dist, rank, world)
+        # the cohort twice: polygons staged as float32 pixels and as int16 half-pixels (the lattice find_contours emits);
+        # the second is the stage's figure only if its digest equals the first's
+        c4_f = c4_stage(dev, local_rank, dist, rank, world)
+        torch.cuda.empty_cache()
+        c4_h = c4_stage(dev, local_rank, dist, rank, world, staging="halfpx16")
+        same = c4_h["digest"] == c4_f["digest"]
+        c4_h["digest_equals_float32_staging"] = same
+        stages_mg["c4_cohort"] = c4_h if same else c4_f
+        stages_mg["c4_cohort_float32_tables"] = c4_f
     except Exception as exc:  # noqa: BLE001
         stages_mg["c4_cohort"] = {"error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.empty_cache()

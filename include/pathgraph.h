@@ -273,6 +273,11 @@ int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, 
                          int32_t* gid, int32_t n_base, int32_t capacity, int32_t* counts_out, pg_stream stream);
 int pg_gid_maps(pg_handle* h, int32_t n, int32_t n_rows, const int32_t* gid, const int32_t* type, int32_t n_ids,
                 int32_t* id_map, int32_t* type_by_gid, pg_stream stream);
+/* Compact staging of contour vertices (the f1 "table files" row): skimage.measure.find_contours(mask, 0.5)
+ * (aggregated_hovernet_run.py:185-197) leaves every vertex on the half-pixel lattice of its tile, so a table may carry
+ * its polygons as int16 half-pixels (q = 2 * coordinate): 4 bytes per vertex over the host link instead of 8 / 16.
+ * out[i] = 0.5f * in[i], exact; in / out 16-byte aligned. */
+int pg_widen_halfpx(pg_handle* h, int64_t n_values, const int16_t* in, float* out, pg_stream stream);
 /* The halo exchange as one step over NVLink peer memory (pack + all-gather fused; csrc/pg_shard.cu). Every rank owns a
  * receive slab of world x cap pg_halo_rec followed by world int32 counts, mapped into every rank (symmetric memory);
  * peer_ptrs_dev = device array of the world slab addresses as seen from this rank. pg_halo_push packs like

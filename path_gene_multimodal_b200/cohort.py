@@ -18,17 +18,34 @@ from .engine import Engine, default_knn_cell, get_engine, radius_cell
 TABLE_FIELDS = ("poly_off", "poly_xy", "nuc_tile", "tile_x", "tile_y", "centroid", "bbox", "types")
 
 
-def pin_table(tab, cache: dict | None = None):
+def to_halfpx(poly_xy: np.ndarray) -> np.ndarray:
+    """Tile-local contour vertices as int16 half-pixels (q = 2 * coordinate). skimage.measure.find_contours(mask, 0.5)
+    (aggregated_hovernet_run.py:185-197) puts every vertex on the half-pixel lattice, so this is exact for the
+    reference's polygons; anything else is refused rather than rounded."""
+    q = np.asarray(poly_xy, dtype=np.float64) * 2.0
+    r = np.rint(q)
+    if not (np.array_equal(q, r) and (np.abs(r) <= 32767).all()):
+        raise ValueError("to_halfpx: vertices are not on the half-pixel lattice of a tile (or exceed int16)")
+    return r.astype(np.int16)
+
+
+def pin_table(tab, cache: dict | None = None, staging: str = "float"):
     """Page-lock the arrays of a synth.NucleiTable in place (as a loader reading Parquet straight into pinned buffers
-    would leave them); arrays shared between tables are pinned once (``cache`` maps id(array) -> pinned copy)."""
+    would leave them); arrays shared between tables are pinned once (``cache`` maps id(array) -> pinned copy).
+    ``staging="halfpx16"`` stores the polygon vertices as int16 half-pixels (to_halfpx): half the bytes of float32
+    over the host link, widened on the device (Engine.widen_halfpx) to the very same float32 values."""
+    if staging not in ("float", "halfpx16"):
+        raise ValueError("staging must be 'float' or 'halfpx16'")
     cache = {} if cache is None else cache
     for name in TABLE_FIELDS:
         a = getattr(tab, name)
-        hit = cache.get(id(a))
+        key = (id(a), staging if name == "poly_xy" else "")
+        hit = cache.get(key)
         if hit is None:
-            buf = _host.pinned_empty(a.shape, a.dtype)
-            buf[...] = a
-            hit = cache[id(a)] = (buf, a)      # keep the source alive: id() stays unique
+            src = to_halfpx(a) if (name == "poly_xy" and staging == "halfpx16" and a.dtype != np.int16) else a
+            buf = _host.pinned_empty(src.shape, src.dtype)
+            buf[...] = src
+            hit = cache[key] = (buf, a)      # keep the source alive: id() stays unique
         setattr(tab, name, hit[0])
     return tab
 
@@ -42,9 +59,11 @@ def process_slide(eng: Engine, tab, k: int = 8, r: float = 50.0, n_types: int = 
     dev = eng.device
     n = tab.n
     side_px = float(tab.n_tiles_side * 508)
-    vt = np.float32 if tab.poly_xy.dtype == np.float32 else np.float64
     t_off = _host.to_device(tab.poly_off, np.int32, dev)
-    t_xy = _host.to_device(tab.poly_xy, vt, dev)
+    if tab.poly_xy.dtype == np.int16:      # half-pixel staging: 4 bytes per vertex over the link, widened here (exact)
+        t_xy = eng.widen_halfpx(_host.to_device(tab.poly_xy, np.int16, dev))
+    else:
+        t_xy = _host.to_device(tab.poly_xy, np.float32 if tab.poly_xy.dtype == np.float32 else np.float64, dev)
     t_tile = _host.to_device(tab.nuc_tile, np.int32, dev)
     t_tx, t_ty = _host.to_device(tab.tile_x, np.int32, dev), _host.to_device(tab.tile_y, np.int32, dev)
     t_cen, t_bb = _host.to_device(tab.centroid, np.float64, dev), _host.to_device(tab.bbox, np.int32, dev)

@@ -104,6 +104,30 @@ halo_unpack_range_kernel(const pg_halo_rec* __restrict__ recs, int n_recs, int s
   }
 }
 
+// ---- compact staging format of contour vertices: int16 half-pixels -> float32 pixels.
+// skimage.measure.find_contours(mask, 0.5) (aggregated_hovernet_run.py:185) puts every vertex on the half-pixel
+// lattice of its tile, so 2 * coordinate is a small integer: a table staged as int16 pairs carries the polygons in 4
+// bytes per vertex instead of 8 (float32) or 16 (float64) over the host link, and widening is exact (x = 0.5 * q).
+__global__ void __launch_bounds__(TPB)
+widen_halfpx_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n_values) {
+  const int64_t i8 = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 8;
+  if (i8 + 8 <= n_values) {
+    const int4 q = *reinterpret_cast<const int4*>(in + i8);
+    const int w[4] = {q.x, q.y, q.z, q.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = 0.5f * (float)(int16_t)(w[k] & 0xffff);
+      f[2 * k + 1] = 0.5f * (float)(int16_t)((unsigned)w[k] >> 16);
+    }
+    float4* o = reinterpret_cast<float4*>(out + i8);
+    o[0] = make_float4(f[0], f[1], f[2], f[3]);
+    o[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (int64_t i = i8; i < n_values; ++i) out[i] = 0.5f * (float)in[i];
+  }
+}
+
 // ---- the halo exchange as ONE step over NVLink peer memory: pack + all-gather fused -----------------------------
 // Every rank owns a receive slab [world][cap] of 24-byte records followed by [world] int32 counts, mapped into all
 // ranks (symmetric memory). The pack kernel of rank r writes each selected record straight into slot [r][o] of every
@@ -289,6 +313,19 @@ int pg_halo_unpack_multi(pg_handle* h, const pg_halo_rec* recs, int32_t n_recs, 
         recs, n_recs, skip_begin, skip_end, ranges[2 * r], ranges[2 * r + 1], (double2*)xy, type, gid, n_base, capacity, counts_out, r, ovf));
     PG_LAUNCH_CHECK(h);
   }
+  return PG_OK;
+}
+
+int pg_widen_halfpx(pg_handle* h, int64_t n_values, const int16_t* in, float* out, pg_stream stream) {
+  if (!h) return PG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA(h, cudaSetDevice(h->device));
+  h->last_stream = s;
+  PG_REQUIRE(h, n_values >= 0 && (n_values == 0 || (in && out)), "pg_widen_halfpx: bad argument");
+  PG_REQUIRE(h, (((uintptr_t)in | (uintptr_t)out) & 15) == 0, "pg_widen_halfpx: in / out must be 16-byte aligned");
+  if (n_values == 0) return PG_OK;
+  PG_LAUNCH(h, s, "widen_halfpx_kernel", widen_halfpx_kernel<<<pg_div_up(pg_div_up(n_values, 8), TPB), TPB, 0, s>>>(in, out, n_values));
+  PG_LAUNCH_CHECK(h);
   return PG_OK;
 }
 

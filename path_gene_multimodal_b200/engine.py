@@ -588,6 +588,15 @@ class Engine:
                                                   int(n_base), int(xy.shape[0]), self._p(counts, torch.int32, "counts"), self._stream()))
         return counts
 
+    def widen_halfpx(self, q: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """int16 half-pixel vertices (q = 2 * coordinate, any shape) -> float32 pixels, exact (pg_widen_halfpx)."""
+        if q.dtype != torch.int16 or not q.is_contiguous():
+            raise TypeError("widen_halfpx: a contiguous int16 tensor is required")
+        out = out if out is not None else self._empty(tuple(q.shape), torch.float32)
+        self._check(self.lib.pg_widen_halfpx(self._h, int(q.numel()), C.c_void_p(q.data_ptr()), self._p(out, torch.float32, "out"),
+                                             self._stream()))
+        return out
+
     def halo_push(self, xy, types, gid, lo_edge, hi_edge, peer_ptrs_dev: int, world: int, rank: int, cap: int):
         """Pack the edge points and store them straight into every peer's receive slab (pg_halo_push)."""
         self._check(self.lib.pg_halo_push(self._h, int(xy.shape[0]), self._p(xy, torch.float64, "xy"),

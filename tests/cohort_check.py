@@ -3,7 +3,8 @@
     python tests/cohort_check.py                                   # 1 GPU
     torchrun --nproc-per-node 8 tests/cohort_check.py              # 8 GPUs, slides dealt out by nuclei count
 
-PG_SLIDES (64) slides of PG_SLIDE_N (500000) nuclei, PG_LANES (2) in flight per GPU; prints the stage's JSON."""
+PG_SLIDES (64) slides of PG_SLIDE_N (500000) nuclei, PG_LANES (4) in flight per GPU, PG_STAGING float | halfpx16 (polygon
+vertices as float32 pixels or int16 half-pixels); prints the stage's JSON."""
 import json
 import os
 import sys
@@ -27,7 +28,8 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     out = bench.c4_stage(dev, local, dist, rank, world, n_slides=int(os.environ.get("PG_SLIDES", 64)),
-                         n=int(os.environ.get("PG_SLIDE_N", 500_000)), lanes=int(os.environ.get("PG_LANES", 2)))
+                         n=int(os.environ.get("PG_SLIDE_N", 500_000)), lanes=int(os.environ.get("PG_LANES", 4)),
+                         staging=os.environ.get("PG_STAGING", "float"))
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:

@@ -342,3 +342,25 @@ def test_round2_entry_points_on_empty_and_tiny_inputs(engine):
     assert out["knn_neighbor_coords"].iloc[0][0] == (1.0, 0.0)          # centroid cells are [y, x]
     with pytest.raises(ValueError):
         knn_graph_frame(df, k=4)
+
+
+def test_halfpx_staging_is_exact_and_changes_nothing(engine):
+    """Contour vertices staged as int16 half-pixels (cohort.to_halfpx) widen to the very same float32 values
+    (pg_widen_halfpx), so a cohort slide gives the same summary either way; off-lattice vertices are refused."""
+    from path_gene_multimodal_b200 import cohort, synth
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    for m in (0, 1, 7, 8, 9, 4099):
+        q = rng.integers(-32768, 32768, size=(m, 2), dtype=np.int64).astype(np.int16)
+        got = engine.widen_halfpx(torch.from_numpy(q).to(dev)).cpu().numpy()
+        assert got.dtype == np.float32 and np.array_equal(got, q.astype(np.float32) * np.float32(0.5))
+    with pytest.raises(ValueError):
+        cohort.to_halfpx(np.array([[0.25, 1.0]]))
+    with pytest.raises(ValueError):
+        cohort.to_halfpx(np.array([[20000.0, 1.0]]))
+    n = 60_000
+    a = cohort.pin_table(synth.make_cohort_slide(3, n), {})
+    b = cohort.pin_table(synth.make_cohort_slide(3, n), {}, staging="halfpx16")
+    assert a.poly_xy.dtype == np.float32 and b.poly_xy.dtype == np.int16 and b.poly_xy.nbytes * 2 == a.poly_xy.nbytes
+    ra, rb = cohort.process_slide(engine, a), cohort.process_slide(engine, b)
+    assert ra == rb and ra["knn_edges"] > 0 and ra["radius_edges"] > 0
