@@ -62,6 +62,15 @@ eng.halo_unpack_multi(recs, n, 0, 0, [(0.0, float(side) / 2), (float(side) / 2, 
 eng.gid_maps(gid, d_ty, n, n)
 eng.knn_neighbor_coords(kres["knn_idx"], d_xy)
 eng.narrow_counts(out["nbr_count"], torch.uint8)
+# round 2 (late): halo exchange over peer memory - here with two local slabs standing in for the peers - and the
+# half-pixel vertex staging of the cohort tables
+cap, world = 1 << 18, 2
+slabs = [torch.zeros(world * cap * 24 + 16, dtype=torch.uint8, device=dev) for _ in range(world)]
+ptrs = torch.tensor([s_.data_ptr() for s_ in slabs], dtype=torch.int64, device=dev)
+eng.halo_push(d_xy, d_ty, gid, float(side) * 0.1, float(side) * 0.9, ptrs.data_ptr(), world, 0, cap)
+eng.halo_unpack_slab(slabs[1], world, 1, cap, [(-1.0, float(side) + 1.0)], xy_all, ty_all, gid_all, n)
+q16 = torch.randint(-2000, 2000, (20_000_000, 2), dtype=torch.int16, device=dev)
+eng.widen_halfpx(q16)
 torch.cuda.synchronize()
 eng.check_overflow()
 print("capture ok", eng.launches)
