@@ -153,6 +153,7 @@ halo_push_kernel(const double2* __restrict__ xy, const int32_t* __restrict__ typ
   if (o >= cap) { atomicExch(overflow, 1); return; }
   pg_halo_rec r;
   r.x = p.x; r.y = p.y; r.gid = gid ? gid[i] : i; r.type = type ? type[i] : 0;
+  PG_ASSERT(o >= 0 && o < cap && rank >= 0 && rank < world);
   for (int q = 0; q < world; ++q)
     if (q != rank) reinterpret_cast<pg_halo_rec*>(peer_ptrs[q])[(size_t)rank * cap + o] = r;
 }
@@ -195,6 +196,7 @@ halo_unpack_slab_kernel(const pg_halo_rec* __restrict__ slab, int world, int ran
   at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
   if (take) {
     const int o = first + at + __popc(m & ((1u << lane) - 1u));
+    PG_ASSERT(o >= n_base);
     if (o < capacity) {
       xy[o] = make_double2(r.x, r.y);
       if (type) type[o] = r.type;
