@@ -631,8 +631,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         if outputs == "compact":
-            cap = int(getattr(eng, "_radius_cap", e_und))   # the one-enqueue path copies its whole capacity (hint x 1.15) and cuts on the host
-            d2h = cap * (8 + 4) + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4 + 4
+            d2h = res["edges"].nbytes + res["dist"].nbytes + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4 + 4
         else:
             d2h = res["edge_index"].nbytes + res["edge_attr"].nbytes + res["degree"].nbytes + res["nbr_count"].nbytes + 32 + 64 * 4
         return {"value": world * n * steps / (ms / 1e3), "unit": "nuclei/s", "h2d_bytes_per_step": int(h_xy.nbytes + h_ty.nbytes),

@@ -108,7 +108,7 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
     ``outputs="compact"`` returns the same graph without the redundant int64 tensors: ``edges`` int32 [E,2],
     ``dist`` float32 [E], ``degree``, ``nbr_count``, ``degree_stats`` - a third of the bytes that cross PCIe (the
     notebook tensors are ``graph_features.edge_index_from_edges(edges, dist)`` away, on whichever device consumes
-    them), and the whole call is one enqueue + one synchronisation once the handle has seen a slide of this kind.
+    them), and the whole call is one enqueue + two synchronising copies once the handle has seen a slide of this kind.
     ``count_dtype`` (compact only): ``np.uint8`` / ``np.uint16`` narrow ``degree`` and ``nbr_count`` on the device
     before the copy (a quarter / half of their bytes); ``OverflowError`` if a count does not fit.
     """
@@ -155,9 +155,10 @@ def build_radius_graph(coords, r: float = 40.0, types=None, n_types: int = 5, mp
 
 def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_dtype=np.dtype(np.int32)) -> dict:
     """The compact output set. With a capacity hint from an earlier slide (edges per nucleus seen on this handle)
-    the build is pg_radius_graph - outputs given up front, nothing read back in between - followed by ONE batch of
-    device-to-host copies and one synchronisation; the valid prefix is cut on the host. Without a hint, or when the
-    hint proves too small, the exact count -> total -> fill sequence runs (and leaves a hint behind)."""
+    the build is pg_radius_graph - outputs given up front, nothing read back in between - followed by two batches of
+    device-to-host copies: the per-nucleus arrays with the edge count, then exactly E edges (the capacity's head-room
+    stays on the device). Without a hint, or when the hint proves too small, the exact count -> total -> fill sequence
+    runs (and leaves a hint behind)."""
     hint = getattr(eng, "_radius_edges_per_point", None)
     for attempt in range(2):
         if hint is not None and attempt == 0 and n > 0:
@@ -177,10 +178,13 @@ def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_
             tdt = torch.uint8 if count_dtype == np.dtype(np.uint8) else torch.int16
             deg = eng.narrow_counts(deg, tdt)
             nbr = eng.narrow_counts(nbr, tdt) if nbr is not None else None
-        host = _host.to_host_many({"edges": g["edges32"], "dist": g["dist32"], "degree": deg, "nbr_count": nbr,
-                                   "stats": g["stats"], "hist": g["hist"], "row_end": g["row_ptr"][-1:]})
+        # two batches of copies: the per-nucleus arrays and the edge count first, then exactly E edges - the capacity's
+        # 15 % head-room never crosses the link (the second synchronisation costs less than copying it)
+        host = _host.to_host_many({"degree": deg, "nbr_count": nbr, "stats": g["stats"], "hist": g["hist"],
+                                   "row_end": g["row_ptr"][-1:]})
         e = int(host["row_end"][0])
         if e <= cap:
+            host.update(_host.to_host_many({"edges": g["edges32"][:e], "dist": g["dist32"][:e]}))
             if count_dtype != np.dtype(np.int32):
                 if eng.lib.pg_check_overflow(eng._h) != 0:  # (also clears the flag)
                     raise OverflowError(f"a degree / neighbour-type count does not fit {count_dtype}")
@@ -194,7 +198,7 @@ def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_
     if n > 0:
         eng._radius_edges_per_point = max(e / n, 1e-3)
     eng.grid_check()
-    out = {"edges": host["edges"][:e], "dist": host["dist"][:e], "degree": host["degree"],
+    out = {"edges": host["edges"], "dist": host["dist"], "degree": host["degree"],
            "degree_stats": eng.decode_stats(host["stats"], host["hist"])}
     if has_types:
         out["nbr_count"] = host["nbr_count"]
