@@ -39,8 +39,9 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return pinned.numpy()
 
 
-def to_host_many(tensors: dict) -> dict:
-    """Several device tensors -> numpy with one stream synchronisation."""
+def to_host_many(tensors: dict, sync: bool = True) -> dict:
+    """Several device tensors -> numpy with one stream synchronisation (``sync=False``: the caller synchronises the
+    stream itself before it reads the arrays)."""
     out, dev = {}, None
     for k, t in tensors.items():
         if t is None:
@@ -52,7 +53,7 @@ def to_host_many(tensors: dict) -> dict:
         pinned.copy_(t, non_blocking=True)
         out[k] = pinned
         dev = t.device
-    if dev is not None:
+    if dev is not None and sync:
         torch.cuda.current_stream(dev).synchronize()
     return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _host
+from . import _host, _lib
 from .engine import default_knn_cell, get_engine, radius_cell
 
 TYPE_NAMES = {1: "neoplastic", 2: "inflammatory", 3: "connective", 4: "dead", 5: "epithelial"}       # ipynb:1774-1780
@@ -184,10 +184,14 @@ def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_
                                    "row_end": g["row_ptr"][-1:]})
         e = int(host["row_end"][0])
         if e <= cap:
-            host.update(_host.to_host_many({"edges": g["edges32"][:e], "dist": g["dist32"][:e]}))
+            # the edge copies are waited for by the flag read that follows them on the stream (pg_check_overflow /
+            # pg_grid_check synchronise): one synchronisation for the copies, the overflow flag and the input flag
+            host.update(_host.to_host_many({"edges": g["edges32"][:e], "dist": g["dist32"][:e]}, sync=False))
             if count_dtype != np.dtype(np.int32):
-                if eng.lib.pg_check_overflow(eng._h) != 0:  # (also clears the flag)
+                rc = eng.lib.pg_check_overflow(eng._h)  # (also clears the flag; a non-finite input is reported first)
+                if rc == _lib.PG_ERR_CAPACITY:
                     raise OverflowError(f"a degree / neighbour-type count does not fit {count_dtype}")
+                eng._check(rc)
                 if count_dtype == np.dtype(np.uint16):
                     host["degree"] = host["degree"].view(np.uint16)
                     if host.get("nbr_count") is not None:
@@ -197,7 +201,8 @@ def _radius_compact(eng, n: int, r: float, n_types: int, has_types: bool, count_
         hint = None
     if n > 0:
         eng._radius_edges_per_point = max(e / n, 1e-3)
-    eng.grid_check()
+    if count_dtype == np.dtype(np.int32):
+        eng.grid_check()  # synchronises (the edge copies above) and reports a non-finite input
     out = {"edges": host["edges"], "dist": host["dist"], "degree": host["degree"],
            "degree_stats": eng.decode_stats(host["stats"], host["hist"])}
     if has_types:

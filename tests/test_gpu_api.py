@@ -171,6 +171,10 @@ def test_non_finite_coordinates_raise(golden_graph):
         for bounds in (None, (0.0, 0.0, 600.0, 600.0)):
             with pytest.raises(ValueError, match="finite"):
                 build_radius_graph(c, r=40.0, bounds=bounds)
+            for cd in (np.int32, np.uint8, np.uint16):      # the compact path reads its flags with the output copies
+                for _ in range(2):                           # (second call: with the capacity hint of the first)
+                    with pytest.raises(ValueError, match="finite"):
+                        build_radius_graph(c, r=40.0, bounds=bounds, outputs="compact", count_dtype=cd)
             with pytest.raises(ValueError, match="finite"):
                 build_knn_graph(c, k=3, bounds=bounds)
     # and the handle is usable again afterwards
