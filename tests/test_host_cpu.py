@@ -133,3 +133,21 @@ def test_bench_reference_pipeline_small():
 
     assert ne == len(ograph.radius_graph(xy, 50.0)["edges"]) and ei == (4, ne) and ea == (2 * ne, 1)
     assert bench.algorithmic_bytes(10, 4) == 512
+
+
+def test_halfpx_staging_host_side():
+    """cohort.to_halfpx: exact on the half-pixel lattice find_contours emits (aggregated_hovernet_run.py:185), refusing
+    anything it would have to round; the synthetic tables are on that lattice, so the staging halves their polygon bytes."""
+    from path_gene_multimodal_b200 import cohort, synth
+
+    off, xy = synth.make_polygons(500, 5)
+    q = cohort.to_halfpx(xy)
+    assert q.dtype == np.int16 and q.shape == xy.shape and q.nbytes * 2 == xy.nbytes
+    assert np.array_equal(q.astype(np.float32) * np.float32(0.5), xy)          # what pg_widen_halfpx computes
+    assert np.array_equal(cohort.to_halfpx(xy.astype(np.float64)), q)
+    for bad in ([[0.25, 1.0]], [[1.0, np.nan]], [[16384.0, 0.0]], [[-16384.0, 0.0]]):
+        with pytest.raises(ValueError):
+            cohort.to_halfpx(np.array(bad))
+    assert np.array_equal(cohort.to_halfpx(np.array([[16383.5, -16383.5]])), np.array([[32767, -32767]], dtype=np.int16))
+    with pytest.raises(ValueError):
+        cohort.pin_table(None, staging="int8")
