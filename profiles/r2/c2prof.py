@@ -15,6 +15,10 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "run"
 sweep = len(sys.argv) > 2
 dev = torch.device("cuda", 0)
 R = 50.0
+import os
+CELL_DIV = float(os.environ.get("PG_CELL_DIV", "1"))   # cells of r / CELL_DIV: the walk then takes the general (2R+1)^2 block path
+_rc = radius_cell
+radius_cell = lambda r: _rc(r) / CELL_DIV  # noqa: E731
 eng = get_engine(0)
 flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 out = {"tag": tag}
