@@ -38,7 +38,10 @@ namespace {
 #define PG_WALK_MINB 8
 #endif
 constexpr int TPB_WALK = PG_WALK_TPB;
-constexpr int SLAB = 8;              // row entries staged per thread in shared memory (12 B x SLAB x TPB_WALK = 12 KB)
+#ifndef PG_WALK_SLAB
+#define PG_WALK_SLAB 8
+#endif
+constexpr int SLAB = PG_WALK_SLAB;   // row entries staged per thread in shared memory (12 B x SLAB x TPB_WALK = 12 KB)
 #ifndef PG_ROWS_TPB
 #define PG_ROWS_TPB 256
 #endif
