@@ -218,6 +218,8 @@ class PeerHalo:
         try:
             eng.check_overflow()
         except RuntimeError as exc:
+            if getattr(exc, "code", None) != -4:      # PG_ERR_CAPACITY; anything else (a non-finite input ...) as it is
+                raise
             raise RuntimeError(f"PeerHalo: a rank packed more than cap={self.cap} halo records (or more than {ghost_cap} "
                                "ghosts arrived here); build the PeerHalo with a larger cap") from exc
         base = n + sum(got)
